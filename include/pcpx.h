@@ -1,0 +1,273 @@
+/*
+ * pcpx — C ABI of the B200-native neighbourhood engine (libpcpx.so).
+ *
+ * This is the drop-in boundary for the ONE data-parallel hot path of
+ * Q-Minh/point-cloud-processing (pcp): batched k-nearest-neighbour and radius search,
+ * tangent-plane PCA normal estimation and the density outlier filter.  pcp itself is a
+ * header-only C++17 template library with no FFI, so every entry point below cites the
+ * reference interface it replaces (paths relative to the reference's include/pcp/), and
+ * include/pcpx/ holds the C++17 headers that keep pcp's own call signatures on top of it.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative pcpx_status otherwise; it never
+ *     throws and never falls back to a CPU path.  pcpx_last_error() gives the message of
+ *     the last failure on the calling thread.
+ *   - plain pointers and sizes only.  Every data pointer may be a HOST pointer (pageable or
+ *     pinned) or a DEVICE pointer of the index's GPU; the library detects which
+ *     (cudaPointerGetAttributes) and stages host buffers itself.  Device pointers let a
+ *     caller keep clouds and results resident in HBM.
+ *   - points are fp32 xyz, `stride_bytes` apart (12 for std::vector<pcp::point_t>,
+ *     common/points/point.hpp:85).
+ *   - indices are ORIGINAL positions in the indexed range (what
+ *     `view.point() - cloud.data()` is for a pcp::point_view_t element).
+ *   - an index is immutable after creation and may be queried from several host threads.
+ */
+#ifndef PCPX_H
+#define PCPX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCPX_VERSION 100
+
+typedef enum pcpx_status
+{
+    PCPX_OK                = 0,
+    PCPX_ERR_INVALID_ARG   = -1,
+    PCPX_ERR_CUDA          = -2,
+    PCPX_ERR_NO_DEVICE     = -3,
+    PCPX_ERR_OUT_OF_MEMORY = -4,
+    PCPX_ERR_UNSUPPORTED   = -5
+} pcpx_status;
+
+#define PCPX_NO_NEIGHBOUR 0xFFFFFFFFu /* padding value in kNN index rows */
+
+typedef struct pcpx_index pcpx_index; /* opaque: the GPU-resident spatial index */
+
+/*
+ * Index parameters.  Replaces pcp::octree_parameters_t (octree/linked_octree_node.hpp:31-40)
+ * and pcp::kdtree::construction_params_t (kdtree/linked_kdtree.hpp:26-33): tree shape does
+ * not change the result of an exact search, so node_capacity / max_depth have no
+ * counterpart; the one structure-dependent behaviour that survives is the root voxel grid:
+ * with use_voxel_grid != 0, points outside [voxel_min, voxel_max] (inclusive,
+ * common/axis_aligned_bounding_box.hpp:111-124) are NOT indexed, as
+ * basic_linked_octree_node_t::insert rejects them (octree/linked_octree_node.hpp:174).
+ * Zero-initialise for defaults.
+ */
+typedef struct pcpx_index_params
+{
+    int32_t device;         /* CUDA device ordinal; -1 = current device */
+    int32_t use_voxel_grid; /* 0 = auto bounding box (octree/linked_octree.hpp:103-121) */
+    float voxel_min[3];
+    float voxel_max[3];
+    uint32_t max_level;  /* finest grid level (cells per axis = 2^level); 0 = auto */
+    uint32_t min_cell_occupancy; /* finest stored level keeps mean occupancy >= this; 0 = auto */
+    uint32_t reserved[8];
+} pcpx_index_params;
+
+/* Facts about a built index (all filled by pcpx_index_info). */
+typedef struct pcpx_index_info
+{
+    uint64_t n_input;   /* points handed to pcpx_index_create */
+    uint64_t n_indexed; /* points actually indexed == octree.size() (octree/linked_octree.hpp:127) */
+    float bbox_min[3];  /* root voxel: pcp::bounding_box (common/axis_aligned_bounding_box.hpp:214-251) */
+    float bbox_max[3];  /*   or the user's voxel grid */
+    uint32_t code_bits;    /* Morton bits sorted on */
+    uint32_t finest_level; /* finest level with a cell table */
+    uint64_t n_cells;      /* cells over all stored levels */
+    uint64_t device_bytes; /* HBM held by the index */
+    int32_t device;
+    float build_ms; /* device time of the build (CUDA events) */
+} pcpx_index_info;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+
+int pcpx_device_count(void);
+const char* pcpx_last_error(void);
+
+/*
+ * Build the index on the GPU: bbox reduce -> quantise + Morton encode -> radix sort ->
+ * per-level cell tables -> float4 SoA reorder; nothing is built on the host.
+ * Replaces basic_linked_octree_t's range constructors (octree/linked_octree.hpp:83-121) and
+ * basic_linked_kdtree_t's constructor (kdtree/linked_kdtree.hpp:100-135).
+ * n == 0 is valid (every query then returns nothing).
+ */
+int pcpx_index_create(
+    const float* xyz,
+    size_t n,
+    size_t stride_bytes,
+    const pcpx_index_params* params /* may be NULL */,
+    pcpx_index** out_index);
+
+void pcpx_index_destroy(pcpx_index* index);
+int pcpx_index_info_get(const pcpx_index* index, pcpx_index_info* out_info);
+
+/* ---- queries ----------------------------------------------------------------------------
+ * `queries`: nq points (fp32 xyz, query_stride_bytes apart), or NULL for "the indexed cloud's
+ * own points, in their original order" (then nq must equal n_input; points that were not
+ * indexed because of the voxel grid are still valid query targets).
+ */
+
+/*
+ * Batched exact kNN.  Replaces basic_linked_octree_t::nearest_neighbours
+ * (octree/linked_octree.hpp:245-254 -> octree/linked_octree_node.hpp:453-570) and
+ * basic_linked_kdtree_t::nearest_neighbours (kdtree/linked_kdtree.hpp:200-263).
+ *   - row i of out_idx (k entries) = the neighbours of query i nearest -> furthest, ordered by
+ *     (fp32 squared distance, original index); rows shorter than k are padded with
+ *     PCPX_NO_NEIGHBOUR (out_d2 with +inf); out_count[i] = number of valid entries.
+ *   - distance = ((dx*dx) + (dy*dy)) + (dz*dz) in fp32 without FMA (common/norm.hpp:102-112).
+ *   - a point is excluded iff |dx| < eps && |dy| < eps && |dz| < eps in fp32
+ *     (common/vector3d_queries.hpp:31-35,48-64 applied at octree/linked_octree_node.hpp:540),
+ *     which also drops foreign near-duplicates; eps is cast to float like the reference does.
+ *   - k == 0 -> nothing is written, returns PCPX_OK (octree/linked_octree_node.hpp:464).
+ * out_d2 and out_count may be NULL.
+ */
+int pcpx_knn(
+    const pcpx_index* index,
+    const float* queries,
+    size_t nq,
+    size_t query_stride_bytes,
+    uint32_t k,
+    double eps,
+    uint32_t* out_idx,
+    float* out_d2,
+    uint32_t* out_count);
+
+/*
+ * Sphere range search, count only.  Replaces `range_search(sphere).size()`
+ * (octree/linked_octree.hpp:264-276 -> octree/linked_octree_node.hpp:581-614,
+ * kdtree/linked_kdtree.hpp:270-316) with predicate pcp::sphere_t::contains
+ * (common/sphere.hpp:27-35): fl(d2) <= fl(r*r).  The query point itself is counted when it is
+ * an indexed point.  radii != NULL gives one radius per query, else `radius` is used.
+ * Note: the reference prunes with d2 <= r (common/intersections.hpp:101) and can therefore
+ * MISS in-range points when r > 1; this library always returns the exact set.
+ */
+int pcpx_radius_count(
+    const pcpx_index* index,
+    const float* queries,
+    size_t nq,
+    size_t query_stride_bytes,
+    const float* radii,
+    float radius,
+    uint32_t* out_count);
+
+/*
+ * Sphere range search, CSR lists.  out_offsets has nq + 1 entries.  *out_idx is allocated by
+ * the library in HOST memory (free with pcpx_free) unless out_idx_device != 0, in which case
+ * it is device memory of the index's GPU.  Within a query the order is the index's traversal
+ * order (deterministic, unspecified — as in the reference, whose order is the tree's DFS).
+ */
+int pcpx_radius_search(
+    const pcpx_index* index,
+    const float* queries,
+    size_t nq,
+    size_t query_stride_bytes,
+    const float* radii,
+    float radius,
+    uint64_t* out_offsets,
+    uint32_t** out_idx,
+    int out_idx_device);
+
+void pcpx_free(void* p, int is_device);
+
+/*
+ * Fused kNN -> 3x3 scatter matrix -> symmetric eigensolve -> normal.  Replaces
+ * pcp::algorithm::estimate_normals (algorithm/estimate_normals.hpp:50-93,116-164) driven by a
+ * kNN map over the index, with pcp::estimate_normal (common/normals/normal_estimation.hpp:32-78)
+ * as the per-neighbourhood body and default_normal_transform (algorithm/common.hpp:31-34):
+ * fp32 mean, centred UN-normalised scatter, unit eigenvector of the smallest eigenvalue.
+ * The sign is not canonical (the reference returns whatever Eigen does): compare with |dot|.
+ * Neighbourhoods with fewer than 3 points have no defined plane; the result is (0,0,1).
+ * out_normals: nq x 3 fp32.
+ */
+int pcpx_estimate_normals(
+    const pcpx_index* index,
+    const float* queries,
+    size_t nq,
+    size_t query_stride_bytes,
+    uint32_t k,
+    double eps,
+    float* out_normals);
+
+/*
+ * As pcpx_estimate_normals, and also writes the neighbourhood centroid: the tangent plane
+ * (point, normal) of pcp::algorithm::estimate_tangent_planes
+ * (algorithm/estimate_tangent_planes.hpp:82-94).  out_points: nq x 3 fp32.
+ */
+int pcpx_estimate_tangent_planes(
+    const pcpx_index* index,
+    const float* queries,
+    size_t nq,
+    size_t query_stride_bytes,
+    uint32_t k,
+    double eps,
+    float* out_points,
+    float* out_normals);
+
+/*
+ * Mean distance to the k nearest neighbours of every indexed point.  Replaces
+ * pcp::algorithm::average_distances_to_neighbors / average_distance_to_neighbors
+ * (algorithm/average_distance_to_neighbors.hpp:39-113): per point the sequential fp32 sum of
+ * sqrt(d2) nearest -> furthest divided by the neighbour count (bit-exact); *out_mean is the
+ * mean of those values accumulated in fp64 by a fixed-shape tree (the reference's fp32
+ * std::reduce order is unspecified).  out_per_point (n_input entries) and out_mean may be NULL.
+ */
+int pcpx_mean_knn_distance(
+    const pcpx_index* index,
+    uint32_t k,
+    double eps,
+    float* out_per_point,
+    double* out_mean);
+
+/*
+ * Density outlier filter: keep point i iff |{j : d2(p_i, p_j) <= radius^2}| >= threshold, the
+ * count including p_i itself.  Replaces the remove_if of
+ * examples/filter_point_cloud_noise_by_density.cpp:81-91 evaluated on the immutable input.
+ * out_keep_mask: n_input bytes (1 = kept), may be NULL.  out_xyz: kept points, packed xyz in
+ * original relative order (std::remove_if is stable), capacity n_input*3 floats, may be NULL.
+ * out_n: number kept.
+ */
+int pcpx_density_filter(
+    const pcpx_index* index,
+    float radius,
+    uint32_t threshold,
+    uint8_t* out_keep_mask,
+    float* out_xyz,
+    size_t* out_n);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+
+/* Device time (CUDA events on the launching stream) of the last call of each kind made
+ * through this index on the calling thread's most recent call; < 0 when never run. */
+typedef struct pcpx_timings
+{
+    float build_ms;     /* whole index build */
+    float sort_ms;      /*   of which radix sort */
+    float query_sort_ms;/* sorting external queries by cell */
+    float kernel_ms;    /* the query kernel proper (kNN / normals / radius / filter) */
+    float total_ms;     /* whole call on the device incl. H2D / D2H staging */
+    uint32_t kernel_launches; /* kernels launched by the last call */
+    uint32_t retry_queries;   /* queries that needed the exact tie / expansion slow path */
+} pcpx_timings;
+
+int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
+
+/* Process-wide tunables (performance only, never results).  Known names:
+ *   "level_factor"  start level of a kNN search = finest level whose own cell holds at least
+ *                   level_factor * k points (default 0.5). */
+int pcpx_set_tuning(const char* name, double value);
+
+/* Search work of a self-kNN over the whole cloud, summed over queries:
+ * out4 = { candidate distance evaluations, cell-table lookups, levels tried,
+ *          queries that needed more than one level }. */
+int pcpx_debug_knn_stats(const pcpx_index* index, uint32_t k, double eps, uint64_t* out4);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PCPX_H */

@@ -1,0 +1,1 @@
+#include "../pcpx_ranges_standin.hpp"

@@ -1,0 +1,526 @@
+// The C ABI of libpcpx.so (include/pcpx.h): argument checking, host <-> device staging,
+// timing.  All compute is in index.cu / query.cu; there is no CPU path.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "query.hpp"
+
+using namespace pcpx;
+
+namespace {
+
+// A user buffer that kernels can read: the pointer itself when it is device memory, otherwise a
+// packed device copy.
+struct InBuf
+{
+    const float* d = nullptr;
+    uint32_t stride_f = 3;
+    DevBuf<float> staged;
+    size_t h2d_bytes = 0;
+
+    // n rows of `width` floats, `stride_bytes` apart
+    void stage(const float* p, size_t n, size_t stride_bytes, int width, cudaStream_t s)
+    {
+        if (!p || n == 0)
+            return;
+        if (is_device_pointer(p))
+        {
+            d = p, stride_f = (uint32_t)(stride_bytes / 4);
+            return;
+        }
+        staged.alloc(n * (size_t)width);
+        PCPX_CUDA(cudaMemcpy2DAsync(staged.get(), (size_t)width * 4, p, stride_bytes,
+                                    (size_t)width * 4, n, cudaMemcpyHostToDevice, s));
+        d = staged.get(), stride_f = (uint32_t)width;
+        h2d_bytes = n * (size_t)width * 4;
+    }
+};
+
+// A user result buffer kernels can write: in place when it is device memory, otherwise a device
+// temporary copied back by finish().
+template <typename T>
+struct OutBuf
+{
+    T* user = nullptr;
+    T* d    = nullptr;
+    size_t n = 0;
+    DevBuf<T> tmp;
+    bool direct = false;
+
+    void prepare(T* p, size_t count)
+    {
+        user = p, n = count;
+        if (!p || count == 0)
+            return;
+        direct = is_device_pointer(p);
+        if (direct)
+            d = p;
+        else
+        {
+            tmp.alloc(count);
+            d = tmp.get();
+        }
+    }
+    void finish(cudaStream_t s, size_t count = (size_t)-1)
+    {
+        if (user && !direct && n)
+            PCPX_CUDA(cudaMemcpyAsync(user, d, std::min(n, count) * sizeof(T),
+                                      cudaMemcpyDeviceToHost, s));
+    }
+};
+
+struct CallTimer
+{
+    pcpx_index& ix;
+    Event t0, k0, k1, t1;
+    explicit CallTimer(pcpx_index& i) : ix(i)
+    {
+        ix.timings.query_sort_ms   = 0.f;
+        ix.timings.kernel_launches = 0;
+        ix.timings.retry_queries   = 0;
+        t0.record(ix.stream);
+    }
+    void kernel_begin() { k0.record(ix.stream); }
+    void kernel_end() { k1.record(ix.stream); }
+    void done()
+    {
+        t1.record(ix.stream);
+        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        ix.timings.kernel_ms = elapsed_ms(k0, k1);
+        ix.timings.total_ms  = elapsed_ms(t0, t1);
+    }
+};
+
+// queries + their processing order
+struct Batch
+{
+    InBuf in;
+    DevBuf<uint32_t> order;
+    QueryBatch qb{nullptr, 3u, nullptr, 0u};
+
+    void prepare(pcpx_index& ix, const float* queries, size_t nq, size_t stride_bytes)
+    {
+        if (nq >= 0xFFFFFFFFull)
+            fail(PCPX_ERR_UNSUPPORTED, "more than 2^32 - 2 queries in one call");
+        if (!queries)
+        {
+            if (nq != ix.n_input)
+                fail(PCPX_ERR_INVALID_ARG,
+                     "queries == NULL means the indexed cloud itself: nq must be %llu, got %llu",
+                     (unsigned long long)ix.n_input, (unsigned long long)nq);
+            qb = QueryBatch{nullptr, 3u, nullptr, (uint32_t)nq};
+            return;
+        }
+        if (stride_bytes == 0)
+            stride_bytes = 12;
+        if (stride_bytes < 12 || stride_bytes % 4)
+            fail(PCPX_ERR_INVALID_ARG, "query_stride_bytes must be a multiple of 4 and >= 12");
+        in.stage(queries, nq, stride_bytes, 3, ix.stream);
+        qb = QueryBatch{in.d, in.stride_f, nullptr, (uint32_t)nq};
+        if (nq > 1)
+        {
+            Event s0, s1;
+            s0.record(ix.stream);
+            order.alloc(nq);
+            sort_queries_by_cell(ix, in.d, in.stride_f, (uint32_t)nq, order.get());
+            s1.record(ix.stream);
+            PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+            ix.timings.query_sort_ms = elapsed_ms(s0, s1);
+            qb.order                 = order.get();
+        }
+    }
+};
+
+template <class F>
+int guarded(F&& f)
+{
+    try
+    {
+        f();
+        return PCPX_OK;
+    }
+    catch (Error const& e)
+    {
+        last_error_storage() = e.msg;
+        return e.code;
+    }
+    catch (std::bad_alloc const&)
+    {
+        last_error_storage() = "host allocation failed";
+        return PCPX_ERR_OUT_OF_MEMORY;
+    }
+    catch (std::exception const& e)
+    {
+        last_error_storage() = e.what();
+        return PCPX_ERR_CUDA;
+    }
+}
+
+pcpx_index& checked(const pcpx_index* ix)
+{
+    if (!ix)
+        fail(PCPX_ERR_INVALID_ARG, "index is NULL");
+    return *const_cast<pcpx_index*>(ix);
+}
+
+} // namespace
+
+extern "C" {
+
+int pcpx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* pcpx_last_error(void) { return last_error_storage().c_str(); }
+
+int pcpx_index_create(const float* xyz, size_t n, size_t stride_bytes,
+                      const pcpx_index_params* params, pcpx_index** out_index)
+{
+    return guarded([&] {
+        if (!out_index)
+            fail(PCPX_ERR_INVALID_ARG, "out_index is NULL");
+        *out_index = nullptr;
+        *out_index = build_index(xyz, n, stride_bytes, params);
+    });
+}
+
+void pcpx_index_destroy(pcpx_index* index)
+{
+    if (!index)
+        return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(index->device);
+    delete index;
+    if (prev >= 0)
+        cudaSetDevice(prev);
+}
+
+int pcpx_index_info_get(const pcpx_index* index, pcpx_index_info* out)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        if (!out)
+            fail(PCPX_ERR_INVALID_ARG, "out_info is NULL");
+        std::memset(out, 0, sizeof *out);
+        out->n_input   = ix.n_input;
+        out->n_indexed = ix.n_indexed;
+        for (int a = 0; a < 3; ++a)
+            out->bbox_min[a] = ix.bbox_min[a], out->bbox_max[a] = ix.bbox_max[a];
+        out->code_bits    = ix.code_bits;
+        out->finest_level = (uint32_t)ix.grid.lfine;
+        out->n_cells      = ix.n_cells;
+        out->device_bytes = ix.device_bytes();
+        out->device       = ix.device;
+        out->build_ms     = ix.timings.build_ms;
+    });
+}
+
+int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t query_stride_bytes,
+             uint32_t k, double eps, uint32_t* out_idx, float* out_d2, uint32_t* out_count)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        if (k == 0 || nq == 0) // octree/linked_octree_node.hpp:464: k == 0 -> {}
+        {
+            if (!queries && nq != ix.n_input && nq != 0)
+                fail(PCPX_ERR_INVALID_ARG, "nq must equal the indexed cloud's size");
+            return;
+        }
+        if (!out_idx)
+            fail(PCPX_ERR_INVALID_ARG, "out_idx is NULL");
+        std::lock_guard<std::mutex> lock(ix.mtx);
+        ScopedDevice guard(ix.device);
+        CallTimer timer(ix);
+        Batch batch;
+        batch.prepare(ix, queries, nq, query_stride_bytes);
+        OutBuf<uint32_t> idx, cnt;
+        OutBuf<float> d2;
+        idx.prepare(out_idx, nq * (size_t)k);
+        d2.prepare(out_d2, nq * (size_t)k);
+        cnt.prepare(out_count, nq);
+        timer.kernel_begin();
+        launch_knn(ix, batch.qb, k, (float)eps, idx.d, d2.d, cnt.d);
+        timer.kernel_end();
+        ix.timings.kernel_launches = 1;
+        idx.finish(ix.stream), d2.finish(ix.stream), cnt.finish(ix.stream);
+        timer.done();
+    });
+}
+
+int pcpx_radius_count(const pcpx_index* index, const float* queries, size_t nq,
+                      size_t query_stride_bytes, const float* radii, float radius,
+                      uint32_t* out_count)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        if (nq == 0)
+            return;
+        if (!out_count)
+            fail(PCPX_ERR_INVALID_ARG, "out_count is NULL");
+        std::lock_guard<std::mutex> lock(ix.mtx);
+        ScopedDevice guard(ix.device);
+        CallTimer timer(ix);
+        Batch batch;
+        batch.prepare(ix, queries, nq, query_stride_bytes);
+        InBuf rad;
+        rad.stage(radii, nq, 4, 1, ix.stream);
+        OutBuf<uint32_t> cnt;
+        cnt.prepare(out_count, nq);
+        timer.kernel_begin();
+        launch_radius_count(ix, batch.qb, rad.d, radius, cnt.d);
+        timer.kernel_end();
+        ix.timings.kernel_launches = 1;
+        cnt.finish(ix.stream);
+        timer.done();
+    });
+}
+
+int pcpx_radius_search(const pcpx_index* index, const float* queries, size_t nq,
+                       size_t query_stride_bytes, const float* radii, float radius,
+                       uint64_t* out_offsets, uint32_t** out_idx, int out_idx_device)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        if (!out_offsets || !out_idx)
+            fail(PCPX_ERR_INVALID_ARG, "out_offsets / out_idx is NULL");
+        *out_idx = nullptr;
+        std::lock_guard<std::mutex> lock(ix.mtx);
+        ScopedDevice guard(ix.device);
+        CallTimer timer(ix);
+        Batch batch;
+        batch.prepare(ix, queries, nq, query_stride_bytes);
+        InBuf rad;
+        rad.stage(radii, nq, 4, 1, ix.stream);
+        DevBuf<uint32_t> cnt(std::max<size_t>(nq, 1));
+        OutBuf<uint64_t> off;
+        off.prepare(out_offsets, nq + 1);
+        timer.kernel_begin();
+        launch_radius_count(ix, batch.qb, rad.d, radius, cnt.get());
+        launch_exclusive_scan_u32(ix, cnt.get(), (uint32_t)nq, off.d);
+        uint64_t total = 0;
+        PCPX_CUDA(cudaMemcpyAsync(&total, off.d + nq, 8, cudaMemcpyDeviceToHost, ix.stream));
+        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        DevBuf<uint32_t> lists(std::max<uint64_t>(total, 1));
+        launch_radius_fill(ix, batch.qb, rad.d, radius, off.d, lists.get());
+        timer.kernel_end();
+        ix.timings.kernel_launches = 5;
+        off.finish(ix.stream);
+        if (out_idx_device)
+        {
+            timer.done();
+            *out_idx = lists.detach();
+        }
+        else
+        {
+            uint32_t* host = (uint32_t*)std::malloc(std::max<uint64_t>(total, 1) * 4);
+            if (!host)
+                fail(PCPX_ERR_OUT_OF_MEMORY, "host allocation of %llu indices failed",
+                     (unsigned long long)total);
+            cudaError_t e = cudaMemcpyAsync(host, lists.get(), total * 4, cudaMemcpyDeviceToHost,
+                                            ix.stream);
+            if (e == cudaSuccess)
+                e = cudaStreamSynchronize(ix.stream);
+            if (e != cudaSuccess)
+            {
+                std::free(host);
+                fail(PCPX_ERR_CUDA, "copying radius lists back failed: %s", cudaGetErrorString(e));
+            }
+            timer.done();
+            *out_idx = host;
+        }
+    });
+}
+
+void pcpx_free(void* p, int is_device)
+{
+    if (!p)
+        return;
+    if (is_device)
+        cudaFree(p);
+    else
+        std::free(p);
+}
+
+static void normals_impl(const pcpx_index* index, const float* queries, size_t nq,
+                         size_t query_stride_bytes, uint32_t k, double eps, float* out_points,
+                         float* out_normals)
+{
+    pcpx_index& ix = checked(index);
+    if (nq == 0)
+        return;
+    if (!out_normals)
+        fail(PCPX_ERR_INVALID_ARG, "out_normals is NULL");
+    std::lock_guard<std::mutex> lock(ix.mtx);
+    ScopedDevice guard(ix.device);
+    CallTimer timer(ix);
+    Batch batch;
+    batch.prepare(ix, queries, nq, query_stride_bytes);
+    OutBuf<float> nrm, ctr;
+    nrm.prepare(out_normals, nq * 3);
+    ctr.prepare(out_points, nq * 3);
+    DevBuf<uint32_t> ties(1);
+    PCPX_CUDA(cudaMemsetAsync(ties.get(), 0, 4, ix.stream));
+    timer.kernel_begin();
+    launch_normals(ix, batch.qb, k, (float)eps, ctr.d, nrm.d, ties.get());
+    timer.kernel_end();
+    ix.timings.kernel_launches = 1;
+    nrm.finish(ix.stream), ctr.finish(ix.stream);
+    uint32_t h_ties = 0;
+    PCPX_CUDA(cudaMemcpyAsync(&h_ties, ties.get(), 4, cudaMemcpyDeviceToHost, ix.stream));
+    timer.done();
+    ix.timings.retry_queries = h_ties;
+}
+
+int pcpx_estimate_normals(const pcpx_index* index, const float* queries, size_t nq,
+                          size_t query_stride_bytes, uint32_t k, double eps, float* out_normals)
+{
+    return guarded(
+        [&] { normals_impl(index, queries, nq, query_stride_bytes, k, eps, nullptr, out_normals); });
+}
+
+int pcpx_estimate_tangent_planes(const pcpx_index* index, const float* queries, size_t nq,
+                                 size_t query_stride_bytes, uint32_t k, double eps,
+                                 float* out_points, float* out_normals)
+{
+    return guarded([&] {
+        if (nq && !out_points)
+            fail(PCPX_ERR_INVALID_ARG, "out_points is NULL");
+        normals_impl(index, queries, nq, query_stride_bytes, k, eps, out_points, out_normals);
+    });
+}
+
+int pcpx_mean_knn_distance(const pcpx_index* index, uint32_t k, double eps, float* out_per_point,
+                           double* out_mean)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        size_t const n = ix.n_input;
+        if (n == 0)
+        {
+            if (out_mean)
+                *out_mean = std::nan("");
+            return;
+        }
+        std::lock_guard<std::mutex> lock(ix.mtx);
+        ScopedDevice guard(ix.device);
+        CallTimer timer(ix);
+        QueryBatch qb{nullptr, 3u, nullptr, (uint32_t)n};
+        OutBuf<float> means;
+        DevBuf<float> scratch;
+        if (out_per_point)
+            means.prepare(out_per_point, n);
+        else
+        {
+            scratch.alloc(n);
+            means.d = scratch.get();
+        }
+        DevBuf<double> sum(1);
+        DevBuf<uint32_t> valid(1);
+        timer.kernel_begin();
+        launch_mean_distance(ix, qb, k, (float)eps, means.d);
+        launch_mean_reduce(ix, means.d, (uint32_t)n, sum.get(), valid.get());
+        timer.kernel_end();
+        ix.timings.kernel_launches = 3;
+        means.finish(ix.stream);
+        double h_sum = 0;
+        uint32_t h_valid = 0;
+        PCPX_CUDA(cudaMemcpyAsync(&h_sum, sum.get(), 8, cudaMemcpyDeviceToHost, ix.stream));
+        PCPX_CUDA(cudaMemcpyAsync(&h_valid, valid.get(), 4, cudaMemcpyDeviceToHost, ix.stream));
+        timer.done();
+        if (out_mean)
+            *out_mean = h_valid == n ? h_sum / (double)n : std::nan("");
+    });
+}
+
+int pcpx_density_filter(const pcpx_index* index, float radius, uint32_t threshold,
+                        uint8_t* out_keep_mask, float* out_xyz, size_t* out_n)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        size_t const n = ix.n_input;
+        if (out_n)
+            *out_n = 0;
+        if (n == 0)
+            return;
+        std::lock_guard<std::mutex> lock(ix.mtx);
+        ScopedDevice guard(ix.device);
+        CallTimer timer(ix);
+        OutBuf<uint8_t> keep;
+        DevBuf<uint8_t> keep_scratch;
+        if (out_keep_mask)
+            keep.prepare(out_keep_mask, n);
+        else
+        {
+            keep_scratch.alloc(n);
+            keep.d = keep_scratch.get();
+        }
+        OutBuf<float> pts;
+        pts.prepare(out_xyz, n * 3);
+        DevBuf<uint64_t> scan(n + 1);
+        timer.kernel_begin();
+        launch_density_keep(ix, radius, threshold, keep.d);
+        launch_exclusive_scan_u8(ix, keep.d, (uint32_t)n, scan.get());
+        if (out_xyz)
+            launch_compact_points(ix, keep.d, scan.get(), pts.d);
+        timer.kernel_end();
+        ix.timings.kernel_launches = out_xyz ? 5 : 4;
+        uint64_t kept = 0;
+        PCPX_CUDA(cudaMemcpyAsync(&kept, scan.get() + n, 8, cudaMemcpyDeviceToHost, ix.stream));
+        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        keep.finish(ix.stream);
+        pts.finish(ix.stream, kept * 3);
+        timer.done();
+        if (out_n)
+            *out_n = (size_t)kept;
+    });
+}
+
+int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        if (!out)
+            fail(PCPX_ERR_INVALID_ARG, "out is NULL");
+        *out = ix.timings;
+    });
+}
+
+int pcpx_set_tuning(const char* name, double value)
+{
+    return guarded([&] {
+        if (!name)
+            fail(PCPX_ERR_INVALID_ARG, "name is NULL");
+        if (!std::strcmp(name, "level_factor"))
+            tuning().level_factor = (float)value;
+        else
+            fail(PCPX_ERR_INVALID_ARG, "unknown tuning parameter '%s'", name);
+    });
+}
+
+int pcpx_debug_knn_stats(const pcpx_index* index, uint32_t k, double eps, uint64_t* out4)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        if (!out4)
+            fail(PCPX_ERR_INVALID_ARG, "out4 is NULL");
+        std::lock_guard<std::mutex> lock(ix.mtx);
+        ScopedDevice guard(ix.device);
+        DevBuf<unsigned long long> st(4);
+        PCPX_CUDA(cudaMemsetAsync(st.get(), 0, 32, ix.stream));
+        launch_knn_stats(ix, k, (float)eps, st.get());
+        PCPX_CUDA(cudaMemcpyAsync(out4, st.get(), 32, cudaMemcpyDeviceToHost, ix.stream));
+        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+    });
+}
+
+} // extern "C"

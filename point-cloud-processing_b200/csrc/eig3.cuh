@@ -1,0 +1,87 @@
+// Symmetric 3x3 eigen-decomposition for the PCA normal: the unit eigenvector of the smallest
+// eigenvalue of the fp32 scatter matrix (common/normals/normal_estimation.hpp:52-73, where the
+// reference calls Eigen::SelfAdjointEigenSolver<Matrix3f>).  Cyclic Jacobi on the matrix scaled
+// by its largest |entry| (Eigen scales the same way before its QL iteration); a fixed number of
+// sweeps so that every lane of a warp runs the same instruction stream.
+#pragma once
+#include "grid_core.cuh"
+
+namespace pcpx {
+
+struct Sym3
+{
+    float xx, xy, xz, yy, yz, zz;
+};
+
+#define PCPX_JACOBI_ROTATE(app, aqq, apq, arp, arq, vp0, vq0, vp1, vq1, vp2, vq2)              \
+    do                                                                                         \
+    {                                                                                          \
+        float const apq_ = (apq);                                                              \
+        if (fabsf(apq_) > 1e-30f)                                                              \
+        {                                                                                      \
+            float const theta = ((aqq) - (app)) / (2.f * apq_);                                \
+            float const t =                                                                    \
+                copysignf(1.f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));       \
+            float const c = 1.f / sqrtf(fmaf(t, t, 1.f));                                      \
+            float const s = t * c;                                                             \
+            (app) -= t * apq_;                                                                 \
+            (aqq) += t * apq_;                                                                 \
+            (apq)           = 0.f;                                                             \
+            float const rp_ = (arp), rq_ = (arq);                                              \
+            (arp) = c * rp_ - s * rq_;                                                         \
+            (arq) = s * rp_ + c * rq_;                                                         \
+            float tp, tq;                                                                      \
+            tp = (vp0), tq = (vq0), (vp0) = c * tp - s * tq, (vq0) = s * tp + c * tq;          \
+            tp = (vp1), tq = (vq1), (vp1) = c * tp - s * tq, (vq1) = s * tp + c * tq;          \
+            tp = (vp2), tq = (vq2), (vp2) = c * tp - s * tq, (vq2) = s * tp + c * tq;          \
+        }                                                                                      \
+    } while (0)
+
+// Returns the eigenvalues' relative gap (l1 - l0) / l2 via *gap when non-null.
+PCPX_HD void smallest_eigenvector(Sym3 m, float& nx, float& ny, float& nz, float* gap)
+{
+    float scale = fmaxf(fmaxf(fabsf(m.xx), fabsf(m.yy)), fabsf(m.zz));
+    scale       = fmaxf(scale, fmaxf(fmaxf(fabsf(m.xy), fabsf(m.xz)), fabsf(m.yz)));
+    if (!(scale > 0.f) || !(scale < INFINITY))
+    {
+        // zero (or non-finite) scatter: < 2 distinct neighbours — no plane is defined
+        nx = 0.f, ny = 0.f, nz = 1.f;
+        if (gap)
+            *gap = 0.f;
+        return;
+    }
+    float const inv = 1.f / scale;
+    float a00 = m.xx * inv, a01 = m.xy * inv, a02 = m.xz * inv;
+    float a11 = m.yy * inv, a12 = m.yz * inv, a22 = m.zz * inv;
+    float v00 = 1.f, v01 = 0.f, v02 = 0.f; // V[row][col]; columns are eigenvectors
+    float v10 = 0.f, v11 = 1.f, v12 = 0.f;
+    float v20 = 0.f, v21 = 0.f, v22 = 1.f;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 6; ++sweep)
+    {
+        // (p,q) = (0,1): third index r = 2 -> a02 (r,p), a12 (r,q)
+        PCPX_JACOBI_ROTATE(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21);
+        // (p,q) = (0,2): r = 1 -> a01 (p,r), a12 (r,q)
+        PCPX_JACOBI_ROTATE(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22);
+        // (p,q) = (1,2): r = 0 -> a01 (r,p), a02 (r,q)
+        PCPX_JACOBI_ROTATE(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22);
+    }
+    // smallest eigenvalue; on exact ties the reference's cascade of ifs lets the later column
+    // of the ascending order win (:60-73) — any member of a tied eigenspace is equally valid.
+    float l0 = a00, l1 = a11, l2 = a22;
+    float ex = v00, ey = v10, ez = v20, lmin = l0;
+    if (l1 < lmin)
+        ex = v01, ey = v11, ez = v21, lmin = l1;
+    if (l2 < lmin)
+        ex = v02, ey = v12, ez = v22, lmin = l2;
+    float const nrm = 1.f / sqrtf(ex * ex + ey * ey + ez * ez);
+    nx = ex * nrm, ny = ey * nrm, nz = ez * nrm;
+    if (gap)
+    {
+        float const lmax = fmaxf(l0, fmaxf(l1, l2));
+        float const lmid = (l0 + l1 + l2) - lmin - lmax;
+        *gap             = (lmid - lmin) / fmaxf(lmax, 1e-30f);
+    }
+}
+
+} // namespace pcpx

@@ -1,0 +1,42 @@
+// The GPU-resident index object behind the opaque pcpx_index handle.
+#pragma once
+#include <mutex>
+
+#include "grid_core.cuh"
+#include "host_util.hpp"
+
+struct pcpx_index
+{
+    int device          = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t n_input    = 0; // points handed in (sorted array length)
+    uint64_t n_indexed  = 0; // points inside the root voxel
+    float bbox_min[3]{}, bbox_max[3]{};
+    uint32_t code_bits = 0;
+    uint64_t n_cells   = 0;
+    pcpx::GridView grid{}; // device pointers into the buffers below
+    pcpx::DevBuf<float4> pts;          // n_input entries, Morton order; w = original index
+    pcpx::DevBuf<pcpx::HashSlot> table; // all levels
+    pcpx_timings timings{-1.f, -1.f, -1.f, -1.f, -1.f, 0u, 0u};
+    std::mutex mtx; // one call at a time per index (calls serialise on `stream`)
+
+    ~pcpx_index()
+    {
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+    size_t device_bytes() const { return pts.bytes() + table.bytes(); }
+};
+
+namespace pcpx {
+
+// index.cu
+pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
+                        const pcpx_index_params* params);
+
+// Sort helper exported by index.cu for query batches: fills `order` (device, nq entries) with
+// the query permutation sorted by fine Morton code of the query positions.
+void sort_queries_by_cell(const pcpx_index& ix, const float* d_queries, uint32_t stride_floats,
+                          uint32_t nq, uint32_t* d_order);
+
+} // namespace pcpx

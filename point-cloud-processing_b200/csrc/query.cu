@@ -1,0 +1,541 @@
+// Query kernels: one thread per query, queries processed in Morton order so that the lanes of a
+// warp walk the same few cells (their candidate loads coalesce into a handful of L1 lines).
+// No tensor cores: nothing here is a dense contraction; the work is fp32 compares, 64-bit
+// compare-selects and cached 16-byte loads.
+#include <algorithm>
+
+#include "normals_core.cuh"
+#include "query.hpp"
+#include "radius_core.cuh"
+
+namespace pcpx {
+
+Tuning& tuning()
+{
+    static Tuning t;
+    return t;
+}
+
+namespace {
+
+constexpr int kQBlock = 128;
+
+inline uint32_t grid_for(uint32_t n, int block) { return std::max(1u, (n + block - 1) / block); }
+
+__device__ __forceinline__ bool fetch_query(const GridView& g, const QueryBatch& qb, uint32_t t,
+                                            float& x, float& y, float& z, uint32_t& row)
+{
+    if (t >= qb.nq)
+        return false;
+    if (qb.q == nullptr)
+    {
+        float4 const c = __ldg(g.pts + t);
+        x = c.x, y = c.y, z = c.z;
+        row = __float_as_uint(c.w);
+    }
+    else
+    {
+        row            = qb.order ? qb.order[t] : t;
+        const float* p = qb.q + (size_t)row * qb.stride_f;
+        x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    }
+    return true;
+}
+
+// ---- kNN -----------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kQBlock) knn_kernel(
+    GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
+    uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, uint32_t* __restrict__ out_count)
+{
+    float x, y, z;
+    uint32_t row;
+    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
+        return;
+    TopK<K> top;
+    knn_search<K, TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, top, nullptr);
+    uint32_t n = 0;
+    size_t const base = (size_t)row * k;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if ((uint32_t)j < k)
+        {
+            bool const valid = top.a[j] != kEmptyEntry;
+            out_idx[base + j] = valid ? (uint32_t)top.a[j] : PCPX_NO_NEIGHBOUR;
+            if (out_d2)
+                out_d2[base + j] = valid ? __uint_as_float((uint32_t)(top.a[j] >> 32)) : INFINITY;
+            n += valid;
+        }
+    if (out_count)
+        out_count[row] = n;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kQBlock) mean_distance_kernel(
+    GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
+    float* __restrict__ out_mean)
+{
+    float x, y, z;
+    uint32_t row;
+    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
+        return;
+    TopK<K> top;
+    knn_search<K, TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, top, nullptr);
+    out_mean[row] = mean_distance(top, k);
+}
+
+// ---- fused kNN + PCA normal ----------------------------------------------------------------
+// K >= k + 1 so that entry k exposes a distance tie across the neighbourhood boundary.
+template <int K>
+__global__ void __launch_bounds__(kQBlock) normals_kernel(
+    GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
+    float* __restrict__ out_centroid, float* __restrict__ out_normal,
+    uint32_t* __restrict__ tie_counter)
+{
+    float x, y, z;
+    uint32_t row;
+    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
+        return;
+    TopK<K> top;
+    int const level =
+        knn_search<K, TIE_SORTED_POSITION>(g, x, y, z, k, eps, min_count, top, nullptr);
+    float n3[3], c3[3];
+    uint64_t const ek = top.kth(k), ek1 = top.kth(k + 1);
+    bool const tie = ek1 != kEmptyEntry && (uint32_t)(ek >> 32) == (uint32_t)(ek1 >> 32);
+    if (!tie)
+        normal_from_positions(g, top, k, n3, c3, nullptr);
+    else
+    {
+        // which of the equidistant points is a neighbour is decided by the original index
+        TopK<K> ids;
+        knn_search<K, TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, ids, nullptr);
+        normal_from_ids(g, query_cell(g, x, y, z), level, ids, k, n3, c3, nullptr);
+        if (tie_counter)
+            atomicAdd(tie_counter, 1u);
+    }
+    out_normal[3 * (size_t)row]     = n3[0];
+    out_normal[3 * (size_t)row + 1] = n3[1];
+    out_normal[3 * (size_t)row + 2] = n3[2];
+    if (out_centroid)
+    {
+        out_centroid[3 * (size_t)row]     = c3[0];
+        out_centroid[3 * (size_t)row + 1] = c3[1];
+        out_centroid[3 * (size_t)row + 2] = c3[2];
+    }
+}
+
+// ---- instrumentation: what the search does per query ---------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
+    GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
+    unsigned long long* __restrict__ stats4)
+{
+    float x, y, z;
+    uint32_t row;
+    SearchStats st;
+    bool const live = fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row);
+    if (live)
+    {
+        TopK<K> top;
+        knn_search<K, TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, top, &st);
+    }
+    unsigned long long v[4] = {st.candidates, st.lookups, st.attempts,
+                               (unsigned long long)(st.attempts > 1)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
+        if ((threadIdx.x & 31) == 0 && v[i])
+            atomicAdd(&stats4[i], v[i]);
+    }
+}
+
+// ---- radius --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kQBlock) radius_count_kernel(
+    GridView g, QueryBatch qb, const float* __restrict__ radii, float r,
+    uint32_t* __restrict__ out_count)
+{
+    float x, y, z;
+    uint32_t row;
+    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
+        return;
+    float const rq = radii ? radii[row] : r;
+    uint32_t cnt   = 0;
+    radius_visit(g, x, y, z, rq, [&](float4 const&, uint32_t) {
+        ++cnt;
+        return false;
+    });
+    out_count[row] = cnt;
+}
+
+__global__ void __launch_bounds__(kQBlock) radius_fill_kernel(
+    GridView g, QueryBatch qb, const float* __restrict__ radii, float r,
+    const uint64_t* __restrict__ offsets, uint32_t* __restrict__ out_idx)
+{
+    float x, y, z;
+    uint32_t row;
+    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
+        return;
+    float const rq = radii ? radii[row] : r;
+    uint64_t w     = offsets[row];
+    radius_visit(g, x, y, z, rq, [&](float4 const& c, uint32_t) {
+        out_idx[w++] = __float_as_uint(c.w);
+        return false;
+    });
+}
+
+// Density filter, first half: radius count with early exit at the threshold -> keep flag,
+// written at the point's ORIGINAL position (examples/filter_point_cloud_noise_by_density.cpp:81-91).
+__global__ void __launch_bounds__(kQBlock) density_keep_kernel(
+    GridView g, uint32_t n_total, float r, uint32_t threshold, uint8_t* __restrict__ keep)
+{
+    uint32_t const t = blockIdx.x * kQBlock + threadIdx.x;
+    if (t >= n_total)
+        return;
+    float4 const q = __ldg(g.pts + t);
+    uint32_t cnt   = 0;
+    if (threshold > 0)
+        radius_visit(g, q.x, q.y, q.z, r, [&](float4 const&, uint32_t) {
+            return ++cnt >= threshold;
+        });
+    keep[__float_as_uint(q.w)] = cnt >= threshold; // !(density < threshold)
+}
+
+// ---- scans / compaction / reduction --------------------------------------------------------
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile  = kScanBlock * kScanItems;
+
+template <typename T>
+__global__ void __launch_bounds__(kScanBlock) tile_sums_kernel(
+    const T* __restrict__ in, uint32_t n, uint64_t* __restrict__ tile_sums)
+{
+    uint32_t const base = blockIdx.x * kScanTile;
+    uint32_t s          = 0;
+    for (int r = 0; r < kScanItems; ++r)
+    {
+        uint32_t const i = base + r * kScanBlock + threadIdx.x;
+        if (i < n)
+            s += in[i];
+    }
+    __shared__ uint32_t sh[kScanBlock / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0)
+        sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint64_t tot = 0;
+        for (int w = 0; w < kScanBlock / 32; ++w)
+            tot += sh[w];
+        tile_sums[blockIdx.x] = tot;
+    }
+}
+
+// single CTA: exclusive scan of the tile sums in place; total appended at [n_tiles]
+__global__ void __launch_bounds__(kScanBlock) scan_tile_sums_kernel(uint64_t* tile_sums,
+                                                                    uint32_t n_tiles)
+{
+    __shared__ uint64_t wsum[kScanBlock / 32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t t0 = 0; t0 < n_tiles; t0 += kScanBlock)
+    {
+        uint32_t const t = t0 + threadIdx.x;
+        uint64_t const v = t < n_tiles ? tile_sums[t] : 0ull;
+        uint64_t incl    = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint64_t const up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o)
+                incl += up;
+        }
+        if (lane == 31)
+            wsum[warp] = incl;
+        __syncthreads();
+        uint64_t wbase = 0;
+        for (int w = 0; w < warp; ++w)
+            wbase += wsum[w];
+        uint64_t const c = carry;
+        if (t < n_tiles)
+            tile_sums[t] = c + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == kScanBlock - 1)
+            carry = c + wbase + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        tile_sums[n_tiles] = carry;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kScanBlock) tile_scan_kernel(
+    const T* __restrict__ in, uint32_t n, const uint64_t* __restrict__ tile_sums,
+    uint32_t n_tiles, uint64_t* __restrict__ out)
+{
+    // thread-blocked layout: thread owns kScanItems consecutive values
+    uint32_t const base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r)
+    {
+        v[r] = base + r < n ? (uint32_t)in[base + r] : 0u;
+        s += v[r];
+    }
+    __shared__ uint32_t wsum[kScanBlock / 32];
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t const up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o)
+            incl += up;
+    }
+    if (lane == 31)
+        wsum[warp] = incl;
+    __syncthreads();
+    uint64_t run = tile_sums[blockIdx.x] + (incl - s);
+    for (int w = 0; w < warp; ++w)
+        run += wsum[w];
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r)
+    {
+        if (base + r < n)
+            out[base + r] = run;
+        run += v[r];
+    }
+    if (blockIdx.x == n_tiles - 1 && threadIdx.x == 0)
+        out[n] = tile_sums[n_tiles];
+}
+
+// kept points out in ORIGINAL relative order (std::remove_if is stable)
+__global__ void __launch_bounds__(kQBlock) compact_points_kernel(
+    GridView g, uint32_t n_total, const uint8_t* __restrict__ keep,
+    const uint64_t* __restrict__ scan, float* __restrict__ out_xyz)
+{
+    uint32_t const t = blockIdx.x * kQBlock + threadIdx.x;
+    if (t >= n_total)
+        return;
+    float4 const p   = __ldg(g.pts + t);
+    uint32_t const o = __float_as_uint(p.w);
+    if (keep[o])
+    {
+        uint64_t const d   = scan[o];
+        out_xyz[3 * d]     = p.x;
+        out_xyz[3 * d + 1] = p.y;
+        out_xyz[3 * d + 2] = p.z;
+    }
+}
+
+// fixed-shape fp64 tree: per-CTA partial sums over a fixed slice, then one CTA adds the partials
+// in index order -> bit-reproducible for a given n.  NaN means (0 neighbours) are skipped and
+// counted out.
+constexpr int kRedBlocks = 1024;
+__global__ void __launch_bounds__(256) mean_partial_kernel(
+    const float* __restrict__ v, uint32_t n, double* __restrict__ partial,
+    uint32_t* __restrict__ partial_valid)
+{
+    uint64_t const per = ((uint64_t)n + kRedBlocks - 1) / kRedBlocks;
+    uint64_t const b = per * blockIdx.x, e = min((uint64_t)n, b + per);
+    double s   = 0.0;
+    uint32_t c = 0;
+    for (uint64_t i = b + threadIdx.x; i < e; i += 256)
+    {
+        float const f = v[i];
+        if (f == f)
+            s += (double)f, ++c;
+    }
+    __shared__ double sh[256];
+    __shared__ uint32_t shc[256];
+    sh[threadIdx.x] = s, shc[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if ((int)threadIdx.x < o)
+            sh[threadIdx.x] += sh[threadIdx.x + o], shc[threadIdx.x] += shc[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        partial[blockIdx.x] = sh[0], partial_valid[blockIdx.x] = shc[0];
+}
+__global__ void mean_final_kernel(const double* partial, const uint32_t* partial_valid,
+                                  double* out_sum, uint32_t* out_valid)
+{
+    double s   = 0.0;
+    uint32_t c = 0;
+    for (int i = 0; i < kRedBlocks; ++i)
+        s += partial[i], c += partial_valid[i];
+    *out_sum = s, *out_valid = c;
+}
+
+uint32_t min_count_for(uint32_t k)
+{
+    float const t = tuning().level_factor * (float)k;
+    return (uint32_t)std::max(1.f, std::ceil(t));
+}
+
+} // namespace
+
+#define PCPX_DISPATCH_K(KR, CALL)                                                              \
+    switch (KR)                                                                                \
+    {                                                                                          \
+    case 4: { constexpr int KK = 4; CALL; } break;                                             \
+    case 8: { constexpr int KK = 8; CALL; } break;                                             \
+    case 12: { constexpr int KK = 12; CALL; } break;                                           \
+    case 16: { constexpr int KK = 16; CALL; } break;                                           \
+    case 20: { constexpr int KK = 20; CALL; } break;                                           \
+    case 24: { constexpr int KK = 24; CALL; } break;                                           \
+    case 28: { constexpr int KK = 28; CALL; } break;                                           \
+    case 32: { constexpr int KK = 32; CALL; } break;                                           \
+    case 36: { constexpr int KK = 36; CALL; } break;                                           \
+    default: fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kMaxK);        \
+    }
+
+void launch_knn(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps, uint32_t* idx,
+                float* d2, uint32_t* count)
+{
+    if (qb.nq == 0 || k == 0)
+        return;
+    if (k > kMaxK)
+        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kMaxK);
+    uint32_t const kr = (k + 3) / 4 * 4, mc = min_count_for(k);
+    dim3 const grid(grid_for(qb.nq, kQBlock));
+    PCPX_DISPATCH_K(kr, (knn_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(ix.grid, qb, k, eps, mc,
+                                                                         idx, d2, count)));
+    PCPX_CHECK_LAUNCH();
+}
+
+void launch_mean_distance(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
+                          float* means)
+{
+    if (qb.nq == 0)
+        return;
+    if (k == 0 || k > kMaxK)
+        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
+    uint32_t const kr = (k + 3) / 4 * 4, mc = min_count_for(k);
+    dim3 const grid(grid_for(qb.nq, kQBlock));
+    PCPX_DISPATCH_K(kr, (mean_distance_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
+                            ix.grid, qb, k, eps, mc, means)));
+    PCPX_CHECK_LAUNCH();
+}
+
+void launch_normals(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
+                    float* centroids, float* normals, uint32_t* tie_counter)
+{
+    if (qb.nq == 0)
+        return;
+    if (k == 0 || k > kMaxK)
+        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
+    uint32_t const kr = (k + 1 + 3) / 4 * 4, mc = min_count_for(k);
+    dim3 const grid(grid_for(qb.nq, kQBlock));
+    PCPX_DISPATCH_K(kr, (normals_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
+                            ix.grid, qb, k, eps, mc, centroids, normals, tie_counter)));
+    PCPX_CHECK_LAUNCH();
+}
+
+void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long long* stats4)
+{
+    if (k == 0 || k > kMaxK)
+        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
+    QueryBatch qb{nullptr, 3u, nullptr, (uint32_t)ix.n_input};
+    if (qb.nq == 0)
+        return;
+    uint32_t const kr = (k + 3) / 4 * 4, mc = min_count_for(k);
+    dim3 const grid(grid_for(qb.nq, kQBlock));
+    PCPX_DISPATCH_K(kr, (knn_stats_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
+                            ix.grid, qb, k, eps, mc, stats4)));
+    PCPX_CHECK_LAUNCH();
+}
+
+void launch_radius_count(const pcpx_index& ix, const QueryBatch& qb, const float* radii, float r,
+                         uint32_t* count)
+{
+    if (qb.nq == 0)
+        return;
+    radius_count_kernel<<<grid_for(qb.nq, kQBlock), kQBlock, 0, ix.stream>>>(ix.grid, qb, radii, r,
+                                                                              count);
+    PCPX_CHECK_LAUNCH();
+}
+
+void launch_radius_fill(const pcpx_index& ix, const QueryBatch& qb, const float* radii, float r,
+                        const uint64_t* offsets, uint32_t* idx)
+{
+    if (qb.nq == 0)
+        return;
+    radius_fill_kernel<<<grid_for(qb.nq, kQBlock), kQBlock, 0, ix.stream>>>(ix.grid, qb, radii, r,
+                                                                             offsets, idx);
+    PCPX_CHECK_LAUNCH();
+}
+
+void launch_density_keep(const pcpx_index& ix, float r, uint32_t threshold, uint8_t* keep)
+{
+    uint32_t const n = (uint32_t)ix.n_input;
+    if (n == 0)
+        return;
+    density_keep_kernel<<<grid_for(n, kQBlock), kQBlock, 0, ix.stream>>>(ix.grid, n, r, threshold,
+                                                                          keep);
+    PCPX_CHECK_LAUNCH();
+}
+
+template <typename T>
+static void exclusive_scan(const pcpx_index& ix, const T* in, uint32_t n, uint64_t* out)
+{
+    if (n == 0)
+    {
+        PCPX_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t), ix.stream));
+        return;
+    }
+    uint32_t const n_tiles = (n + kScanTile - 1) / kScanTile;
+    DevBuf<uint64_t> sums(n_tiles + 1);
+    tile_sums_kernel<T><<<n_tiles, kScanBlock, 0, ix.stream>>>(in, n, sums.get());
+    PCPX_CHECK_LAUNCH();
+    scan_tile_sums_kernel<<<1, kScanBlock, 0, ix.stream>>>(sums.get(), n_tiles);
+    PCPX_CHECK_LAUNCH();
+    tile_scan_kernel<T><<<n_tiles, kScanBlock, 0, ix.stream>>>(in, n, sums.get(), n_tiles, out);
+    PCPX_CHECK_LAUNCH();
+    PCPX_CUDA(cudaStreamSynchronize(ix.stream)); // `sums` is freed on return
+}
+
+void launch_exclusive_scan_u32(const pcpx_index& ix, const uint32_t* in, uint32_t n, uint64_t* out)
+{
+    exclusive_scan<uint32_t>(ix, in, n, out);
+}
+void launch_exclusive_scan_u8(const pcpx_index& ix, const uint8_t* in, uint32_t n, uint64_t* out)
+{
+    exclusive_scan<uint8_t>(ix, in, n, out);
+}
+
+void launch_compact_points(const pcpx_index& ix, const uint8_t* keep, const uint64_t* scan,
+                           float* out_xyz)
+{
+    uint32_t const n = (uint32_t)ix.n_input;
+    if (n == 0)
+        return;
+    compact_points_kernel<<<grid_for(n, kQBlock), kQBlock, 0, ix.stream>>>(ix.grid, n, keep, scan,
+                                                                            out_xyz);
+    PCPX_CHECK_LAUNCH();
+}
+
+void launch_mean_reduce(const pcpx_index& ix, const float* v, uint32_t n, double* out_sum,
+                        uint32_t* out_valid)
+{
+    DevBuf<double> partial(kRedBlocks);
+    DevBuf<uint32_t> pvalid(kRedBlocks);
+    mean_partial_kernel<<<kRedBlocks, 256, 0, ix.stream>>>(v, n, partial.get(), pvalid.get());
+    PCPX_CHECK_LAUNCH();
+    mean_final_kernel<<<1, 1, 0, ix.stream>>>(partial.get(), pvalid.get(), out_sum, out_valid);
+    PCPX_CHECK_LAUNCH();
+    PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+}
+
+} // namespace pcpx

@@ -1,0 +1,47 @@
+// Device-side launchers of the query kernels (query.cu).  All pointers are DEVICE pointers.
+#pragma once
+#include "index.hpp"
+
+namespace pcpx {
+
+// A batch of query points.  q == nullptr: the index's own points, thread t <-> sorted point t,
+// result row = original index.  Otherwise thread t handles query order[t] (Morton order of the
+// queries' cells) and writes result row order[t].
+struct QueryBatch
+{
+    const float* q;
+    uint32_t stride_f;
+    const uint32_t* order;
+    uint32_t nq;
+};
+
+struct Tuning
+{
+    float level_factor = 0.5f; // start level: finest whose own cell holds >= level_factor * k points
+    int block_threads  = 128;
+};
+Tuning& tuning();
+
+constexpr uint32_t kMaxK = 32; // register-resident list; larger k is not supported yet
+
+void launch_knn(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps, uint32_t* idx,
+                float* d2, uint32_t* count);
+void launch_normals(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
+                    float* centroids, float* normals, uint32_t* tie_counter);
+void launch_mean_distance(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
+                          float* means);
+void launch_radius_count(const pcpx_index& ix, const QueryBatch& qb, const float* radii, float r,
+                         uint32_t* count);
+void launch_radius_fill(const pcpx_index& ix, const QueryBatch& qb, const float* radii, float r,
+                        const uint64_t* offsets, uint32_t* idx);
+void launch_density_keep(const pcpx_index& ix, float r, uint32_t threshold, uint8_t* keep);
+// exclusive scan of `in` (n values) into `out` (n + 1 values, out[n] = total); 64-bit sums
+void launch_exclusive_scan_u32(const pcpx_index& ix, const uint32_t* in, uint32_t n, uint64_t* out);
+void launch_exclusive_scan_u8(const pcpx_index& ix, const uint8_t* in, uint32_t n, uint64_t* out);
+void launch_compact_points(const pcpx_index& ix, const uint8_t* keep, const uint64_t* scan,
+                           float* out_xyz);
+void launch_mean_reduce(const pcpx_index& ix, const float* v, uint32_t n, double* out_sum,
+                        uint32_t* out_valid);
+void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long long* stats4);
+
+} // namespace pcpx

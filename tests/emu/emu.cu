@@ -1,0 +1,343 @@
+// TEST HARNESS ONLY — not part of libpcpx.so and never a product path.
+//
+// Runs the SAME __host__ __device__ traversal code the CUDA kernels call (grid_core.cuh,
+// knn_core.cuh, radius_core.cuh, normals_core.cuh, eig3.cuh) on the CPU, over an index built by
+// a small host re-statement of the device build, so that `-m "not gpu"` tests can compare the
+// search logic (pruning bounds, level walk, tie handling, exclusion box) with the oracle in a
+// container that has no GPU.  The device build itself (radix sort, hash insertion kernels,
+// scans) is only exercised by the `-m gpu` tests.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "normals_core.cuh"
+#include "radius_core.cuh"
+
+using namespace pcpx;
+
+struct EmuIndex
+{
+    GridView g{};
+    std::vector<float4> pts;
+    std::vector<HashSlot> table;
+    uint64_t n_input = 0;
+};
+
+static uint32_t host_claim(std::vector<HashSlot>& t, uint64_t key)
+{
+    uint32_t s = hash_slot(key, (uint32_t)t.size());
+    for (;;)
+    {
+        if (t[s].key_hi == kEmptyKeyHi)
+        {
+            t[s].key_lo = (uint32_t)key, t[s].key_hi = (uint32_t)(key >> 32);
+            return s;
+        }
+        if (t[s].key_lo == (uint32_t)key && t[s].key_hi == (uint32_t)(key >> 32))
+            return s;
+        s = s + 1 == t.size() ? 0u : s + 1;
+    }
+}
+
+extern "C" {
+
+void* emu_index_create(const float* xyz, size_t n, int use_box, const float* box6,
+                       uint32_t max_level, uint32_t min_occ_in)
+{
+    EmuIndex* ix = new EmuIndex();
+    ix->n_input  = n;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float maxabs = 0.f;
+    std::vector<uint8_t> inside(n, 1);
+    size_t n_inside = 0;
+    for (size_t i = 0; i < n; ++i)
+    {
+        for (int a = 0; a < 3; ++a)
+        {
+            float v = xyz[3 * i + a];
+            mn[a] = std::min(mn[a], v), mx[a] = std::max(mx[a], v);
+        }
+        if (use_box)
+            for (int a = 0; a < 3; ++a)
+                inside[i] &= xyz[3 * i + a] >= box6[a] && xyz[3 * i + a] <= box6[3 + a];
+        n_inside += inside[i];
+    }
+    if (use_box)
+        for (int a = 0; a < 3; ++a)
+            mn[a] = box6[a], mx[a] = box6[3 + a];
+    if (n == 0)
+        for (int a = 0; a < 3; ++a)
+            mn[a] = mx[a] = 0.f;
+    float extent = 0.f;
+    for (int a = 0; a < 3; ++a)
+    {
+        extent = std::max(extent, mx[a] - mn[a]);
+        maxabs = std::max(maxabs, std::max(std::fabs(mn[a]), std::fabs(mx[a])));
+    }
+    if (!(extent > 0.f) || !std::isfinite(extent))
+        extent = maxabs > 0.f && std::isfinite(maxabs) ? maxabs * 1e-3f : 1.f;
+    extent *= 1.0001f;
+    GridView& g = ix->g;
+    g.ox = mn[0], g.oy = mn[1], g.oz = mn[2];
+    g.extent = extent;
+    int lcap = (int)std::ceil(std::log2((double)std::max<size_t>(n_inside, 2)) / 2.0) + 1;
+    if (max_level)
+        lcap = (int)max_level;
+    double const ulp = std::max((double)maxabs, (double)extent) * std::ldexp(1.0, -23);
+    lcap = std::min(lcap, (int)std::floor(std::log2((double)extent / (64.0 * ulp))));
+    lcap = std::max(1, std::min(lcap, kMaxLevel));
+    g.lcap  = lcap;
+    g.scale = std::ldexp(1.f, lcap) / extent;
+    g.delta = 16.f * std::ldexp(std::max(extent, maxabs), -23);
+    g.n     = (uint32_t)n_inside;
+
+    std::vector<uint64_t> code(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        QueryCell c = query_cell(g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        code[i]     = inside[i] ? morton3(c.ux, c.uy, c.uz) : ~0ull;
+    }
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](uint32_t a, uint32_t b) { return code[a] < code[b]; });
+    ix->pts.resize(std::max<size_t>(n, 1));
+    for (size_t i = 0; i < n; ++i)
+    {
+        uint32_t o = order[i];
+        ix->pts[i] = make_float4(xyz[3 * o], xyz[3 * o + 1], xyz[3 * o + 2], u2f(o));
+    }
+    g.pts = ix->pts.data();
+
+    auto boundary = [&](uint32_t i) -> int {
+        if (i == 0)
+            return 0;
+        QueryCell a = query_cell(g, ix->pts[i - 1].x, ix->pts[i - 1].y, ix->pts[i - 1].z);
+        QueryCell b = query_cell(g, ix->pts[i].x, ix->pts[i].y, ix->pts[i].z);
+        uint32_t diff = (a.ux ^ b.ux) | (a.uy ^ b.uy) | (a.uz ^ b.uz);
+        if (!diff)
+            return g.lcap + 1;
+        int hb = 31 - __builtin_clz(diff);
+        return g.lcap - hb;
+    };
+    std::vector<uint64_t> lh(kMaxLevel + 2, 0);
+    for (uint32_t i = 0; i < g.n; ++i)
+        lh[boundary(i)]++;
+    double min_occ = min_occ_in ? (double)min_occ_in : 4.0;
+    uint64_t cells = 0, total = 0;
+    g.lfine = 0;
+    for (int l = 0; l <= g.lcap; ++l)
+    {
+        cells += lh[l];
+        if (l > 0 && (double)g.n / (double)std::max<uint64_t>(cells, 1) < min_occ)
+            break;
+        g.lfine = l;
+        total += cells;
+    }
+    size_t slots = std::max<uint64_t>(64, (uint64_t)((double)total * 2.5) + 1);
+    ix->table.assign(slots, HashSlot{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu});
+    g.table_size = (uint32_t)slots;
+    for (uint32_t i = 0; i < g.n; ++i)
+    {
+        int b = boundary(i);
+        QueryCell c = query_cell(g, ix->pts[i].x, ix->pts[i].y, ix->pts[i].z);
+        for (int l = b; l <= g.lfine; ++l)
+        {
+            int sh     = g.lcap - l;
+            uint32_t s = host_claim(ix->table, cell_key(l, c.ux >> sh, c.uy >> sh, c.uz >> sh));
+            ix->table[s].start = i;
+        }
+    }
+    for (uint32_t i = 1; i <= g.n; ++i)
+    {
+        int b = i == g.n ? 0 : boundary(i);
+        QueryCell c = query_cell(g, ix->pts[i - 1].x, ix->pts[i - 1].y, ix->pts[i - 1].z);
+        for (int l = b; l <= g.lfine; ++l)
+        {
+            int sh     = g.lcap - l;
+            uint32_t s = host_claim(ix->table, cell_key(l, c.ux >> sh, c.uy >> sh, c.uz >> sh));
+            ix->table[s].count = i - ix->table[s].start;
+        }
+    }
+    g.table = ix->table.data();
+    return ix;
+}
+
+void emu_index_destroy(void* h) { delete static_cast<EmuIndex*>(h); }
+
+void emu_index_info(void* h, uint64_t* n_indexed, int* lcap, int* lfine, uint64_t* slots)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    *n_indexed = ix->g.n, *lcap = ix->g.lcap, *lfine = ix->g.lfine, *slots = ix->table.size();
+}
+
+} // extern "C"
+
+static void fetch(EmuIndex* ix, const float* q, size_t i, float& x, float& y, float& z,
+                  size_t& row)
+{
+    if (!q)
+    {
+        float4 c = ix->pts[i];
+        x = c.x, y = c.y, z = c.z, row = f2u(c.w);
+    }
+    else
+        x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2], row = i;
+}
+
+template <int K>
+static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
+                     uint32_t min_count, uint32_t* idx, float* d2, uint32_t* cnt, uint64_t* st4)
+{
+    for (size_t i = 0; i < nq; ++i)
+    {
+        float x, y, z;
+        size_t row;
+        fetch(ix, q, i, x, y, z, row);
+        TopK<K> top;
+        SearchStats st;
+        knn_search<K, TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, min_count, top, &st);
+        uint32_t n = 0;
+        for (uint32_t j = 0; j < k; ++j)
+        {
+            bool valid       = top.a[j] != kEmptyEntry;
+            idx[row * k + j] = valid ? (uint32_t)top.a[j] : 0xFFFFFFFFu;
+            if (d2)
+                d2[row * k + j] = valid ? u2f((uint32_t)(top.a[j] >> 32)) : INFINITY;
+            n += valid;
+        }
+        if (cnt)
+            cnt[row] = n;
+        if (st4)
+            st4[0] += st.candidates, st4[1] += st.lookups, st4[2] += st.attempts,
+                st4[3] += st.attempts > 1;
+    }
+}
+
+#define EMU_DISPATCH(KR, CALL)                                                                 \
+    switch (KR)                                                                                \
+    {                                                                                          \
+    case 4: { constexpr int KK = 4; CALL; } break;                                             \
+    case 8: { constexpr int KK = 8; CALL; } break;                                             \
+    case 12: { constexpr int KK = 12; CALL; } break;                                           \
+    case 16: { constexpr int KK = 16; CALL; } break;                                           \
+    case 20: { constexpr int KK = 20; CALL; } break;                                           \
+    case 24: { constexpr int KK = 24; CALL; } break;                                           \
+    case 28: { constexpr int KK = 28; CALL; } break;                                           \
+    case 32: { constexpr int KK = 32; CALL; } break;                                           \
+    case 36: { constexpr int KK = 36; CALL; } break;                                           \
+    default: return -5;                                                                        \
+    }
+
+extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double eps, double level_factor,
+            uint32_t* idx, float* d2, uint32_t* cnt, uint64_t* st4)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    if (k == 0 || nq == 0)
+        return 0;
+    uint32_t mc = (uint32_t)std::max(1.0, std::ceil(level_factor * k));
+    uint32_t kr = (k + 3) / 4 * 4;
+    EMU_DISPATCH(kr, (knn_impl<KK>(ix, q, nq, k, (float)eps, mc, idx, d2, cnt, st4)));
+    return 0;
+}
+
+template <int K>
+static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
+                         uint32_t mc, float* ctr, float* nrm, float* means, uint32_t* ties)
+{
+    for (size_t i = 0; i < nq; ++i)
+    {
+        float x, y, z;
+        size_t row;
+        fetch(ix, q, i, x, y, z, row);
+        TopK<K> top;
+        int level = knn_search<K, TIE_SORTED_POSITION>(ix->g, x, y, z, k, eps, mc, top, nullptr);
+        float n3[3], c3[3];
+        uint64_t ek = top.kth(k), ek1 = top.kth(k + 1);
+        bool tie = ek1 != kEmptyEntry && (uint32_t)(ek >> 32) == (uint32_t)(ek1 >> 32);
+        if (!tie)
+            normal_from_positions(ix->g, top, k, n3, c3, nullptr);
+        else
+        {
+            TopK<K> ids;
+            knn_search<K, TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, mc, ids, nullptr);
+            normal_from_ids(ix->g, query_cell(ix->g, x, y, z), level, ids, k, n3, c3, nullptr);
+            if (ties)
+                ++*ties;
+        }
+        for (int a = 0; a < 3; ++a)
+        {
+            nrm[3 * row + a] = n3[a];
+            if (ctr)
+                ctr[3 * row + a] = c3[a];
+        }
+        if (means)
+        {
+            TopK<K> t2;
+            knn_search<K, TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, mc, t2, nullptr);
+            means[row] = mean_distance(t2, k);
+        }
+    }
+}
+
+extern "C" int emu_normals(void* h, const float* q, size_t nq, uint32_t k, double eps, double level_factor,
+                float* ctr, float* nrm, float* means, uint32_t* ties)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    if (k == 0 || nq == 0)
+        return 0;
+    uint32_t mc = (uint32_t)std::max(1.0, std::ceil(level_factor * k));
+    uint32_t kr = (k + 1 + 3) / 4 * 4;
+    EMU_DISPATCH(kr, (normals_impl<KK>(ix, q, nq, k, (float)eps, mc, ctr, nrm, means, ties)));
+    return 0;
+}
+
+extern "C" {
+
+int emu_radius(void* h, const float* q, size_t nq, const float* radii, float r, uint32_t* cnt,
+               const uint64_t* offsets, uint32_t* out_idx)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    for (size_t i = 0; i < nq; ++i)
+    {
+        float x, y, z;
+        size_t row;
+        fetch(ix, q, i, x, y, z, row);
+        uint32_t c = 0;
+        uint64_t w = offsets ? offsets[row] : 0;
+        radius_visit(ix->g, x, y, z, radii ? radii[row] : r, [&](float4 const& p, uint32_t) {
+            if (out_idx)
+                out_idx[w++] = f2u(p.w);
+            ++c;
+            return false;
+        });
+        if (cnt)
+            cnt[row] = c;
+    }
+    return 0;
+}
+
+int emu_density_keep(void* h, float r, uint32_t threshold, uint8_t* keep)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    for (size_t i = 0; i < ix->n_input; ++i)
+    {
+        float4 q = ix->pts[i];
+        uint32_t c = 0;
+        if (threshold)
+            radius_visit(ix->g, q.x, q.y, q.z, r,
+                         [&](float4 const&, uint32_t) { return ++c >= threshold; });
+        keep[f2u(q.w)] = c >= threshold;
+    }
+    return 0;
+}
+
+void emu_smallest_eigenvector(const float* cov6, float* n3, float* gap)
+{
+    Sym3 m{cov6[0], cov6[1], cov6[2], cov6[3], cov6[4], cov6[5]};
+    smallest_eigenvector(m, n3[0], n3[1], n3[2], gap);
+}
+
+} // extern "C"
