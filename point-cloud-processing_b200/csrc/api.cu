@@ -248,12 +248,18 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
         idx.prepare(out_idx, nq * (size_t)k);
         d2.prepare(out_d2, nq * (size_t)k);
         cnt.prepare(out_count, nq);
+        DevBuf<uint32_t> retries(1);
+        PCPX_CUDA(cudaMemsetAsync(retries.get(), 0, 4, ix.stream));
         timer.kernel_begin();
-        launch_knn(ix, batch.qb, k, (float)eps, idx.d, d2.d, cnt.d);
+        launch_knn(ix, batch.qb, k, (float)eps, idx.d, d2.d, cnt.d, retries.get());
         timer.kernel_end();
         ix.timings.kernel_launches = 1;
         idx.finish(ix.stream), d2.finish(ix.stream), cnt.finish(ix.stream);
+        uint32_t h_retries = 0;
+        PCPX_CUDA(cudaMemcpyAsync(&h_retries, retries.get(), 4, cudaMemcpyDeviceToHost,
+                                  ix.stream));
         timer.done();
+        ix.timings.retry_queries = h_retries;
     });
 }
 

@@ -195,4 +195,204 @@ PCPX_HD int knn_search(const GridView& g, float qx, float qy, float qz, uint32_t
     return l;
 }
 
+
+// =============================================================================================
+// Two-pass search (the fast path of every kNN-shaped kernel).
+//
+// Pass 1 keeps only the K smallest DISTANCES: a sorted fp32 list updated by a branch-free
+// min/max chain — a[j] = max(a[j-1], min(a[j], d)) is the sorted insert when d is new and the
+// identity when d >= a[K-1] — 2 instructions per slot and no divergence, against ~8 per slot for
+// the 64-bit (distance, id) list above.  Pass 2 walks the same block again with tau = the k-th
+// distance: every point with d2 <= tau is a neighbour; its rank is the number of list entries
+// strictly below d2.  Bit-equal distances (inside the list or across its boundary) make ranks
+// ambiguous; they are detected and such queries fall back to the exact 64-bit search, so the
+// (distance, original index) contract holds for every query.
+// =============================================================================================
+template <int K>
+struct TopD
+{
+    float a[K];
+
+    PCPX_HD void reset()
+    {
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            a[j] = INFINITY;
+    }
+    PCPX_HD float worst() const { return a[K - 1]; }
+    PCPX_HD float kth(uint32_t k) const // a[k - 1]; the launchers keep K - k <= 4
+    {
+        uint32_t const back = (uint32_t)K - k;
+        float r             = a[K - 1];
+#pragma unroll
+        for (int b = 1; b <= 4; ++b)
+            if (K - 1 - b >= 0)
+                r = back == (uint32_t)b ? a[K - 1 - b >= 0 ? K - 1 - b : 0] : r;
+        return r;
+    }
+    PCPX_HD void insert(float d)
+    {
+#pragma unroll
+        for (int j = K - 1; j > 0; --j)
+            a[j] = fmaxf(a[j - 1], fminf(a[j], d));
+        a[0] = fminf(a[0], d);
+    }
+    // number of entries strictly below d (= rank of a neighbour at distance d)
+    PCPX_HD uint32_t rank_of(float d) const
+    {
+        uint32_t r = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            r += a[j] < d;
+        return r;
+    }
+    // two of the first k entries are bit-equal (finite): ranks would collide
+    PCPX_HD bool has_internal_tie(uint32_t k) const
+    {
+        bool t = false;
+#pragma unroll
+        for (int j = 0; j + 1 < K; ++j)
+            t = t || ((uint32_t)(j + 1) < k && a[j] == a[j + 1] && a[j] < INFINITY);
+        return t;
+    }
+    PCPX_HD uint32_t count_finite(uint32_t k) const
+    {
+        uint32_t n = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            n += (uint32_t)j < k && a[j] < INFINITY;
+        return n;
+    }
+};
+
+PCPX_HD bool outside_block(const BlockGeom& b, int dx, int dy, int dz)
+{
+    return (dx < 0 && b.cx == 0u) || (dx > 0 && b.cx == b.last) || (dy < 0 && b.cy == 0u) ||
+           (dy > 0 && b.cy == b.last) || (dz < 0 && b.cz == 0u) || (dz > 0 && b.cz == b.last);
+}
+PCPX_HD float cell_lb2(const BlockGeom& b, int dx, int dy, int dz)
+{
+    float const sx = dx < 0 ? b.sm[0] : (dx > 0 ? b.sp[0] : 0.f);
+    float const sy = dy < 0 ? b.sm[1] : (dy > 0 ? b.sp[1] : 0.f);
+    float const sz = dz < 0 ? b.sm[2] : (dz > 0 ? b.sp[2] : 0.f);
+    return fadd_x(fadd_x(sx, sy), sz);
+}
+
+// The non-empty cells of one 3x3x3 block, in visiting order (own, faces, edges, corners), with
+// their conservative squared lower bounds.  Filled by ONE lock-step sweep of 27 table lookups
+// (every lane of a warp does the same thing at the same time); the candidate loops then run
+// FLAT per lane over these spans, so a warp's cost is max over lanes of (total candidates)
+// rather than the sum over cells of max over lanes of (cell size).  Lives in local memory
+// (dynamically indexed), which L1 caches.
+struct CellList
+{
+    uint32_t start[27], end[27];
+    float lb2[27];
+    int n;
+};
+
+PCPX_HD void collect_cells(const GridView& g, const BlockGeom& b, int level, CellList& cl,
+                           SearchStats* st)
+{
+    uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
+    int n               = 0;
+#pragma unroll 1
+    for (int i = 0; i < 27; ++i)
+    {
+        Offset3 const o = block27_offset(i);
+        if (outside_block(b, o.dx, o.dy, o.dz))
+            continue;
+        uint32_t start, count;
+        if (st)
+            st->lookups++;
+        if (!find_cell(g, key0 + key_delta(o.dx, o.dy, o.dz), start, count))
+            continue;
+        cl.start[n] = start;
+        cl.end[n]   = start + count;
+        cl.lb2[n]   = cell_lb2(b, o.dx, o.dy, o.dz);
+        ++n;
+    }
+    cl.n = n;
+}
+
+// Flat iteration over the spans of a CellList whose lower bound does not exceed `bound()`
+// (re-evaluated whenever a new span is entered).  body(p) is called once per point position.
+#define PCPX_FLAT_FOR_EACH(cl, bound_expr, p_var, ...)                                       \
+    {                                                                                          \
+        int e_ = 0;                                                                            \
+        uint32_t p_var = 0, pend_ = 0;                                                         \
+        for (;;)                                                                               \
+        {                                                                                      \
+            bool done_ = false;                                                                \
+            while (p_var == pend_)                                                             \
+            {                                                                                  \
+                if (e_ == (cl).n)                                                              \
+                {                                                                              \
+                    done_ = true;                                                              \
+                    break;                                                                     \
+                }                                                                              \
+                float const lb_     = (cl).lb2[e_];                                            \
+                uint32_t const s_   = (cl).start[e_];                                          \
+                uint32_t const en_  = (cl).end[e_];                                            \
+                ++e_;                                                                          \
+                if (lb_ > (bound_expr)) /* equal: a tie may hide there */                      \
+                    continue;                                                                  \
+                p_var = s_, pend_ = en_;                                                       \
+            }                                                                                  \
+            if (done_)                                                                         \
+                break;                                                                         \
+            __VA_ARGS__;                                                                       \
+            ++p_var;                                                                           \
+        }                                                                                      \
+    }
+
+// Pass 1.  Returns the level the answer was found at; `b` / `cl` describe that level's block.
+template <int K>
+PCPX_HD int knn_search_dist(const GridView& g, float qx, float qy, float qz, uint32_t k,
+                            float eps, uint32_t min_count, TopD<K>& top, BlockGeom& b,
+                            CellList& cl, SearchStats* st)
+{
+    QueryCell const qc = query_cell(g, qx, qy, qz);
+    int l              = select_level(g, qc, min_count, st);
+    for (;; --l)
+    {
+        top.reset();
+        if (st)
+            st->attempts++;
+        b = block_geom(g, qc, l, qx, qy, qz);
+        collect_cells(g, b, l, cl, st);
+        PCPX_FLAT_FOR_EACH(cl, top.worst(), p, {
+            float4 const c = load_pt(g.pts + p);
+            float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
+            float d2       = sqdist_x(dx, dy, dz);
+            // exclusion box, common/vector3d_queries.hpp:31-35,59-63 (strict <, all axes)
+            if (fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps)
+                d2 = INFINITY;
+            top.insert(d2);
+            if (st)
+                st->candidates++;
+        });
+        if (l == 0)
+            break;
+        if (top.kth(k) < b.block_lb2) // strictly closer than anything outside the block
+            break;
+    }
+    return l;
+}
+
+// Pass 2.  f(point, sorted position, d2, dx, dy, dz) for every eligible point with d2 <= tau.
+template <class F>
+PCPX_HD void for_each_within(const GridView& g, const CellList& cl, float qx, float qy, float qz,
+                             float tau, float eps, F&& f)
+{
+    PCPX_FLAT_FOR_EACH(cl, tau, p, {
+        float4 const c = load_pt(g.pts + p);
+        float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
+        float const d2 = sqdist_x(dx, dy, dz);
+        bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
+        if (!excluded && d2 <= tau)
+            f(c, p, d2, dx, dy, dz);
+    });
+}
+
 } // namespace pcpx

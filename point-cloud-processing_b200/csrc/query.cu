@@ -42,34 +42,60 @@ __device__ __forceinline__ bool fetch_query(const GridView& g, const QueryBatch&
     return true;
 }
 
-// ---- kNN -----------------------------------------------------------------------------------
+// ---- kNN-shaped kernels ----------------------------------------------------------------------
+// Fast path: two-pass search (knn_core.cuh).  Queries whose answer hinges on bit-equal
+// distances take the exact 64-bit (distance, original index) search in a separate noinline
+// function so that its register footprint does not tax the fast path.
+__host__ __device__ constexpr int exact_k(int K) { return (K + 3) / 4 * 4; }
+
+template <int K>
+__device__ __noinline__ void knn_exact_row(const GridView& g, float x, float y, float z,
+                                           uint32_t k, float eps, uint32_t min_count,
+                                           uint32_t* idx_row, float* d2_row, uint32_t* out_count)
+{
+    TopK<exact_k(K)> top;
+    knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, top, nullptr);
+    uint32_t n = 0;
+#pragma unroll
+    for (int j = 0; j < exact_k(K); ++j)
+        if ((uint32_t)j < k)
+        {
+            bool const valid = top.a[j] != kEmptyEntry;
+            idx_row[j]       = valid ? (uint32_t)top.a[j] : PCPX_NO_NEIGHBOUR;
+            if (d2_row)
+                d2_row[j] = valid ? __uint_as_float((uint32_t)(top.a[j] >> 32)) : INFINITY;
+            n += valid;
+        }
+    if (out_count)
+        *out_count = n;
+}
+
 template <int K>
 __global__ void __launch_bounds__(kQBlock) knn_kernel(
     GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
-    uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, uint32_t* __restrict__ out_count)
+    uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, uint32_t* __restrict__ out_count,
+    uint32_t* __restrict__ retry_counter)
 {
     float x, y, z;
     uint32_t row;
     if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
         return;
-    TopK<K> top;
-    knn_search<K, TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, top, nullptr);
-    uint32_t n = 0;
-    size_t const base = (size_t)row * k;
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-        if ((uint32_t)j < k)
-        {
-            bool const valid = top.a[j] != kEmptyEntry;
-            out_idx[base + j] = valid ? (uint32_t)top.a[j] : PCPX_NO_NEIGHBOUR;
-            if (out_d2)
-                out_d2[base + j] = valid ? __uint_as_float((uint32_t)(top.a[j] >> 32)) : INFINITY;
-            n += valid;
-        }
-    if (out_count)
-        out_count[row] = n;
+    TopD<K> top;
+    BlockGeom b;
+    CellList cl;
+    knn_search_dist<K>(g, x, y, z, k, eps, min_count, top, b, cl, nullptr);
+    uint32_t* idx_row = out_idx + (size_t)row * k;
+    float* d2_row     = out_d2 ? out_d2 + (size_t)row * k : nullptr;
+    uint32_t* cnt     = out_count ? out_count + row : nullptr;
+    if (!knn_two_pass_emit<K>(g, cl, x, y, z, top, k, eps, idx_row, d2_row, cnt))
+    {
+        knn_exact_row<K>(g, x, y, z, k, eps, min_count, idx_row, d2_row, cnt);
+        if (retry_counter)
+            atomicAdd(retry_counter, 1u);
+    }
 }
 
+// the per-point mean needs the k smallest distances only: one pass, no fallback
 template <int K>
 __global__ void __launch_bounds__(kQBlock) mean_distance_kernel(
     GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
@@ -79,48 +105,58 @@ __global__ void __launch_bounds__(kQBlock) mean_distance_kernel(
     uint32_t row;
     if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
         return;
-    TopK<K> top;
-    knn_search<K, TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, top, nullptr);
-    out_mean[row] = mean_distance(top, k);
+    TopD<K> top;
+    BlockGeom b;
+    CellList cl;
+    knn_search_dist<K>(g, x, y, z, k, eps, min_count, top, b, cl, nullptr);
+    out_mean[row] = mean_distance_d(top, k);
 }
 
 // ---- fused kNN + PCA normal ----------------------------------------------------------------
-// K >= k + 1 so that entry k exposes a distance tie across the neighbourhood boundary.
+template <int K>
+__device__ __noinline__ void normal_exact(const GridView& g, float x, float y, float z,
+                                          uint32_t k, float eps, uint32_t min_count,
+                                          float* out_normal_row, float* out_centroid_row)
+{
+    TopK<exact_k(K)> ids;
+    int const level =
+        knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, ids, nullptr);
+    float n3[3], c3[3];
+    normal_from_ids(g, query_cell(g, x, y, z), level, ids, k, n3, c3, nullptr);
+    out_normal_row[0] = n3[0], out_normal_row[1] = n3[1], out_normal_row[2] = n3[2];
+    if (out_centroid_row)
+        out_centroid_row[0] = c3[0], out_centroid_row[1] = c3[1], out_centroid_row[2] = c3[2];
+}
+
 template <int K>
 __global__ void __launch_bounds__(kQBlock) normals_kernel(
     GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
     float* __restrict__ out_centroid, float* __restrict__ out_normal,
-    uint32_t* __restrict__ tie_counter)
+    uint32_t* __restrict__ retry_counter)
 {
     float x, y, z;
     uint32_t row;
     if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
         return;
-    TopK<K> top;
-    int const level =
-        knn_search<K, TIE_SORTED_POSITION>(g, x, y, z, k, eps, min_count, top, nullptr);
+    float* nrow = out_normal + 3 * (size_t)row;
+    float* crow = out_centroid ? out_centroid + 3 * (size_t)row : nullptr;
+    TopD<K> top;
+    BlockGeom b;
+    CellList cl;
+    knn_search_dist<K>(g, x, y, z, k, eps, min_count, top, b, cl, nullptr);
     float n3[3], c3[3];
-    uint64_t const ek = top.kth(k), ek1 = top.kth(k + 1);
-    bool const tie = ek1 != kEmptyEntry && (uint32_t)(ek >> 32) == (uint32_t)(ek1 >> 32);
-    if (!tie)
-        normal_from_positions(g, top, k, n3, c3, nullptr);
+    if (normal_two_pass<K>(g, cl, x, y, z, top, k, eps, n3, c3, nullptr))
+    {
+        nrow[0] = n3[0], nrow[1] = n3[1], nrow[2] = n3[2];
+        if (crow)
+            crow[0] = c3[0], crow[1] = c3[1], crow[2] = c3[2];
+    }
     else
     {
         // which of the equidistant points is a neighbour is decided by the original index
-        TopK<K> ids;
-        knn_search<K, TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, ids, nullptr);
-        normal_from_ids(g, query_cell(g, x, y, z), level, ids, k, n3, c3, nullptr);
-        if (tie_counter)
-            atomicAdd(tie_counter, 1u);
-    }
-    out_normal[3 * (size_t)row]     = n3[0];
-    out_normal[3 * (size_t)row + 1] = n3[1];
-    out_normal[3 * (size_t)row + 2] = n3[2];
-    if (out_centroid)
-    {
-        out_centroid[3 * (size_t)row]     = c3[0];
-        out_centroid[3 * (size_t)row + 1] = c3[1];
-        out_centroid[3 * (size_t)row + 2] = c3[2];
+        normal_exact<K>(g, x, y, z, k, eps, min_count, nrow, crow);
+        if (retry_counter)
+            atomicAdd(retry_counter, 1u);
     }
 }
 
@@ -136,8 +172,10 @@ __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
     bool const live = fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row);
     if (live)
     {
-        TopK<K> top;
-        knn_search<K, TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, top, &st);
+        TopD<K> top;
+        BlockGeom b;
+        CellList cl;
+        knn_search_dist<K>(g, x, y, z, k, eps, min_count, top, b, cl, &st);
     }
     unsigned long long v[4] = {st.candidates, st.lookups, st.attempts,
                                (unsigned long long)(st.attempts > 1)};
@@ -386,32 +424,44 @@ uint32_t min_count_for(uint32_t k)
 
 } // namespace
 
+// register-list sizes that are compiled; a query with k neighbours runs with the smallest K >= k
+static int list_size_for(uint32_t k)
+{
+    static const int sizes[] = {4, 8, 10, 12, 15, 16, 20, 24, 28, 30, 32};
+    for (int s : sizes)
+        if ((uint32_t)s >= k)
+            return s;
+    return 0;
+}
+
 #define PCPX_DISPATCH_K(KR, CALL)                                                              \
     switch (KR)                                                                                \
     {                                                                                          \
     case 4: { constexpr int KK = 4; CALL; } break;                                             \
     case 8: { constexpr int KK = 8; CALL; } break;                                             \
+    case 10: { constexpr int KK = 10; CALL; } break;                                           \
     case 12: { constexpr int KK = 12; CALL; } break;                                           \
+    case 15: { constexpr int KK = 15; CALL; } break;                                           \
     case 16: { constexpr int KK = 16; CALL; } break;                                           \
     case 20: { constexpr int KK = 20; CALL; } break;                                           \
     case 24: { constexpr int KK = 24; CALL; } break;                                           \
     case 28: { constexpr int KK = 28; CALL; } break;                                           \
+    case 30: { constexpr int KK = 30; CALL; } break;                                           \
     case 32: { constexpr int KK = 32; CALL; } break;                                           \
-    case 36: { constexpr int KK = 36; CALL; } break;                                           \
     default: fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kMaxK);        \
     }
 
 void launch_knn(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps, uint32_t* idx,
-                float* d2, uint32_t* count)
+                float* d2, uint32_t* count, uint32_t* retry_counter)
 {
     if (qb.nq == 0 || k == 0)
         return;
     if (k > kMaxK)
         fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kMaxK);
-    uint32_t const kr = (k + 3) / 4 * 4, mc = min_count_for(k);
+    uint32_t const kr = (uint32_t)list_size_for(k), mc = min_count_for(k);
     dim3 const grid(grid_for(qb.nq, kQBlock));
-    PCPX_DISPATCH_K(kr, (knn_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(ix.grid, qb, k, eps, mc,
-                                                                         idx, d2, count)));
+    PCPX_DISPATCH_K(kr, (knn_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
+                            ix.grid, qb, k, eps, mc, idx, d2, count, retry_counter)));
     PCPX_CHECK_LAUNCH();
 }
 
@@ -422,7 +472,7 @@ void launch_mean_distance(const pcpx_index& ix, const QueryBatch& qb, uint32_t k
         return;
     if (k == 0 || k > kMaxK)
         fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
-    uint32_t const kr = (k + 3) / 4 * 4, mc = min_count_for(k);
+    uint32_t const kr = (uint32_t)list_size_for(k), mc = min_count_for(k);
     dim3 const grid(grid_for(qb.nq, kQBlock));
     PCPX_DISPATCH_K(kr, (mean_distance_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
                             ix.grid, qb, k, eps, mc, means)));
@@ -436,7 +486,7 @@ void launch_normals(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, floa
         return;
     if (k == 0 || k > kMaxK)
         fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
-    uint32_t const kr = (k + 1 + 3) / 4 * 4, mc = min_count_for(k);
+    uint32_t const kr = (uint32_t)list_size_for(k), mc = min_count_for(k);
     dim3 const grid(grid_for(qb.nq, kQBlock));
     PCPX_DISPATCH_K(kr, (normals_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
                             ix.grid, qb, k, eps, mc, centroids, normals, tie_counter)));
@@ -450,7 +500,7 @@ void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long
     QueryBatch qb{nullptr, 3u, nullptr, (uint32_t)ix.n_input};
     if (qb.nq == 0)
         return;
-    uint32_t const kr = (k + 3) / 4 * 4, mc = min_count_for(k);
+    uint32_t const kr = (uint32_t)list_size_for(k), mc = min_count_for(k);
     dim3 const grid(grid_for(qb.nq, kQBlock));
     PCPX_DISPATCH_K(kr, (knn_stats_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
                             ix.grid, qb, k, eps, mc, stats4)));

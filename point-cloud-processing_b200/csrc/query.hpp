@@ -25,7 +25,7 @@ Tuning& tuning();
 constexpr uint32_t kMaxK = 32; // register-resident list; larger k is not supported yet
 
 void launch_knn(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps, uint32_t* idx,
-                float* d2, uint32_t* count);
+                float* d2, uint32_t* count, uint32_t* retry_counter);
 void launch_normals(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
                     float* centroids, float* normals, uint32_t* tie_counter);
 void launch_mean_distance(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,

@@ -187,32 +187,62 @@ static void fetch(EmuIndex* ix, const float* q, size_t i, float& x, float& y, fl
         x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2], row = i;
 }
 
+static int list_size_for(uint32_t k)
+{
+    static const int sizes[] = {4, 8, 10, 12, 15, 16, 20, 24, 28, 30, 32};
+    for (int s : sizes)
+        if ((uint32_t)s >= k)
+            return s;
+    return 0;
+}
+constexpr int exact_k(int K) { return (K + 3) / 4 * 4; }
+
+// mirrors knn_kernel / knn_exact_row in query.cu; mode 0 = two-pass with fallback (the
+// product path), 1 = force the exact 64-bit search for every query
 template <int K>
 static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
-                     uint32_t min_count, uint32_t* idx, float* d2, uint32_t* cnt, uint64_t* st4)
+                     uint32_t min_count, int mode, uint32_t* idx, float* d2, uint32_t* cnt,
+                     uint64_t* st4, uint32_t* per_query_cand)
 {
     for (size_t i = 0; i < nq; ++i)
     {
         float x, y, z;
         size_t row;
         fetch(ix, q, i, x, y, z, row);
-        TopK<K> top;
         SearchStats st;
-        knn_search<K, TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, min_count, top, &st);
-        uint32_t n = 0;
-        for (uint32_t j = 0; j < k; ++j)
+        bool done = false;
+        if (mode == 0)
         {
-            bool valid       = top.a[j] != kEmptyEntry;
-            idx[row * k + j] = valid ? (uint32_t)top.a[j] : 0xFFFFFFFFu;
-            if (d2)
-                d2[row * k + j] = valid ? u2f((uint32_t)(top.a[j] >> 32)) : INFINITY;
-            n += valid;
+            TopD<K> top;
+            BlockGeom b;
+            CellList cl;
+            knn_search_dist<K>(ix->g, x, y, z, k, eps, min_count, top, b, cl, &st);
+            done = knn_two_pass_emit<K>(ix->g, cl, x, y, z, top, k, eps, idx + row * k,
+                                        d2 ? d2 + row * k : nullptr, cnt ? cnt + row : nullptr);
+            if (!done && st4)
+                st4[3] += 1; // retries
         }
-        if (cnt)
-            cnt[row] = n;
+        if (!done)
+        {
+            TopK<exact_k(K)> top;
+            knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, min_count, top,
+                                                       mode == 1 ? &st : nullptr);
+            uint32_t n = 0;
+            for (uint32_t j = 0; j < k; ++j)
+            {
+                bool valid       = top.a[j] != kEmptyEntry;
+                idx[row * k + j] = valid ? (uint32_t)top.a[j] : 0xFFFFFFFFu;
+                if (d2)
+                    d2[row * k + j] = valid ? u2f((uint32_t)(top.a[j] >> 32)) : INFINITY;
+                n += valid;
+            }
+            if (cnt)
+                cnt[row] = n;
+        }
         if (st4)
-            st4[0] += st.candidates, st4[1] += st.lookups, st4[2] += st.attempts,
-                st4[3] += st.attempts > 1;
+            st4[0] += st.candidates, st4[1] += st.lookups, st4[2] += st.attempts;
+        if (per_query_cand)
+            per_query_cand[i] = st.candidates; // processing order (Morton order for self-queries)
     }
 }
 
@@ -221,49 +251,55 @@ static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float 
     {                                                                                          \
     case 4: { constexpr int KK = 4; CALL; } break;                                             \
     case 8: { constexpr int KK = 8; CALL; } break;                                             \
+    case 10: { constexpr int KK = 10; CALL; } break;                                           \
     case 12: { constexpr int KK = 12; CALL; } break;                                           \
+    case 15: { constexpr int KK = 15; CALL; } break;                                           \
     case 16: { constexpr int KK = 16; CALL; } break;                                           \
     case 20: { constexpr int KK = 20; CALL; } break;                                           \
     case 24: { constexpr int KK = 24; CALL; } break;                                           \
     case 28: { constexpr int KK = 28; CALL; } break;                                           \
+    case 30: { constexpr int KK = 30; CALL; } break;                                           \
     case 32: { constexpr int KK = 32; CALL; } break;                                           \
-    case 36: { constexpr int KK = 36; CALL; } break;                                           \
     default: return -5;                                                                        \
     }
 
-extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double eps, double level_factor,
-            uint32_t* idx, float* d2, uint32_t* cnt, uint64_t* st4)
+extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double eps,
+                       double level_factor, int mode, uint32_t* idx, float* d2, uint32_t* cnt,
+                       uint64_t* st4, uint32_t* per_query_cand)
 {
     EmuIndex* ix = static_cast<EmuIndex*>(h);
     if (k == 0 || nq == 0)
         return 0;
     uint32_t mc = (uint32_t)std::max(1.0, std::ceil(level_factor * k));
-    uint32_t kr = (k + 3) / 4 * 4;
-    EMU_DISPATCH(kr, (knn_impl<KK>(ix, q, nq, k, (float)eps, mc, idx, d2, cnt, st4)));
+    EMU_DISPATCH(list_size_for(k),
+                 (knn_impl<KK>(ix, q, nq, k, (float)eps, mc, mode, idx, d2, cnt, st4,
+                               per_query_cand)));
     return 0;
 }
 
+// mirrors normals_kernel / normal_exact and mean_distance_kernel
 template <int K>
 static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
-                         uint32_t mc, float* ctr, float* nrm, float* means, uint32_t* ties)
+                         uint32_t mc, int mode, float* ctr, float* nrm, float* means,
+                         uint32_t* ties)
 {
     for (size_t i = 0; i < nq; ++i)
     {
         float x, y, z;
         size_t row;
         fetch(ix, q, i, x, y, z, row);
-        TopK<K> top;
-        int level = knn_search<K, TIE_SORTED_POSITION>(ix->g, x, y, z, k, eps, mc, top, nullptr);
         float n3[3], c3[3];
-        uint64_t ek = top.kth(k), ek1 = top.kth(k + 1);
-        bool tie = ek1 != kEmptyEntry && (uint32_t)(ek >> 32) == (uint32_t)(ek1 >> 32);
-        if (!tie)
-            normal_from_positions(ix->g, top, k, n3, c3, nullptr);
-        else
+        TopD<K> top;
+        BlockGeom b;
+        CellList cl;
+        knn_search_dist<K>(ix->g, x, y, z, k, eps, mc, top, b, cl, nullptr);
+        bool ok = mode == 0 && normal_two_pass<K>(ix->g, cl, x, y, z, top, k, eps, n3, c3, nullptr);
+        if (!ok)
         {
-            TopK<K> ids;
-            knn_search<K, TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, mc, ids, nullptr);
-            normal_from_ids(ix->g, query_cell(ix->g, x, y, z), level, ids, k, n3, c3, nullptr);
+            TopK<exact_k(K)> ids;
+            int lv = knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, mc, ids,
+                                                                nullptr);
+            normal_from_ids(ix->g, query_cell(ix->g, x, y, z), lv, ids, k, n3, c3, nullptr);
             if (ties)
                 ++*ties;
         }
@@ -274,23 +310,20 @@ static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, fl
                 ctr[3 * row + a] = c3[a];
         }
         if (means)
-        {
-            TopK<K> t2;
-            knn_search<K, TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, mc, t2, nullptr);
-            means[row] = mean_distance(t2, k);
-        }
+            means[row] = mean_distance_d(top, k);
     }
 }
 
-extern "C" int emu_normals(void* h, const float* q, size_t nq, uint32_t k, double eps, double level_factor,
-                float* ctr, float* nrm, float* means, uint32_t* ties)
+extern "C" int emu_normals(void* h, const float* q, size_t nq, uint32_t k, double eps,
+                           double level_factor, int mode, float* ctr, float* nrm, float* means,
+                           uint32_t* ties)
 {
     EmuIndex* ix = static_cast<EmuIndex*>(h);
     if (k == 0 || nq == 0)
         return 0;
     uint32_t mc = (uint32_t)std::max(1.0, std::ceil(level_factor * k));
-    uint32_t kr = (k + 1 + 3) / 4 * 4;
-    EMU_DISPATCH(kr, (normals_impl<KK>(ix, q, nq, k, (float)eps, mc, ctr, nrm, means, ties)));
+    EMU_DISPATCH(list_size_for(k),
+                 (normals_impl<KK>(ix, q, nq, k, (float)eps, mc, mode, ctr, nrm, means, ties)));
     return 0;
 }
 

@@ -52,9 +52,9 @@ class Emu:
         L.emu_index_info.argtypes = [C.c_void_p, _u64p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      _u64p]
         L.emu_knn.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_uint32, C.c_double, C.c_double,
-                              _u32p, _f32p, _u32p, _u64p]
+                              C.c_int, _u32p, _f32p, _u32p, _u64p, _u32p]
         L.emu_normals.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_uint32, C.c_double,
-                                  C.c_double, _f32p, _f32p, _f32p, _u32p]
+                                  C.c_double, C.c_int, _f32p, _f32p, _f32p, _u32p]
         L.emu_radius.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, C.c_float, _u32p, _u64p,
                                  _u32p]
         L.emu_density_keep.argtypes = [C.c_void_p, C.c_float, C.c_uint32, _u8p]
@@ -93,19 +93,26 @@ class EmuIndex:
         self.L.emu_index_info(self.h, C.byref(n), C.byref(lcap), C.byref(lfine), C.byref(slots))
         return dict(n_indexed=n.value, lcap=lcap.value, lfine=lfine.value, slots=slots.value)
 
-    def knn(self, queries, k, eps=1e-5, level_factor=0.5):
+    def knn(self, queries, k, eps=1e-5, level_factor=0.5, exact_only=False):
+        """exact_only=False mirrors the product kernel (two-pass + exact fallback); True forces
+        the 64-bit (distance, index) search for every query.  st = candidates, lookups,
+        attempts, fallbacks."""
         q = _f32(queries)
         nq = self.n if q is None else len(q)
         idx = np.full((nq, k), 0xFFFFFFFF, np.uint32)
         d2 = np.full((nq, k), np.inf, np.float32)
         cnt = np.zeros(nq, np.uint32)
         st = np.zeros(4, np.uint64)
-        rc = self.L.emu_knn(self.h, _ptr(q, _f32p), nq, k, eps, level_factor, _ptr(idx, _u32p),
-                            _ptr(d2, _f32p), _ptr(cnt, _u32p), _ptr(st, _u64p))
+        self.per_query_candidates = np.zeros(nq, np.uint32)
+        rc = self.L.emu_knn(self.h, _ptr(q, _f32p), nq, k, eps, level_factor,
+                            1 if exact_only else 0, _ptr(idx, _u32p),
+                            _ptr(d2, _f32p), _ptr(cnt, _u32p), _ptr(st, _u64p),
+                            _ptr(self.per_query_candidates, _u32p))
         assert rc == 0
         return idx, d2, cnt, st
 
-    def normals(self, queries, k, eps=1e-5, level_factor=0.5, want_means=False):
+    def normals(self, queries, k, eps=1e-5, level_factor=0.5, want_means=False,
+                exact_only=False):
         q = _f32(queries)
         nq = self.n if q is None else len(q)
         ctr = np.zeros((nq, 3), np.float32)
@@ -113,7 +120,7 @@ class EmuIndex:
         means = np.zeros(nq, np.float32) if want_means else None
         ties = np.zeros(1, np.uint32)
         rc = self.L.emu_normals(self.h, _ptr(q, _f32p), nq, k, eps, level_factor,
-                                _ptr(ctr, _f32p), _ptr(nrm, _f32p), _ptr(means, _f32p),
+                                1 if exact_only else 0, _ptr(ctr, _f32p), _ptr(nrm, _f32p), _ptr(means, _f32p),
                                 _ptr(ties, _u32p))
         assert rc == 0
         return nrm, ctr, means, int(ties[0])
