@@ -329,4 +329,35 @@ float ref_average_distance_to_neighbors(void* h, int tree, std::size_t k, float*
         knn_map);
 }
 
+// The per-element body of pcp::algorithm::estimate_normals (algorithm/estimate_normals.hpp:80-90)
+// for a sample of the cloud's own points: knn(v) through the reference's tree, then
+// pcp::estimate_normal.  The latter needs Eigen (absent), so the restatement in
+// oracle/pcp_oracle.c (oracle_estimate_normal, common/normals/normal_estimation.hpp:41-77) is
+// linked in for that one call; the neighbour search is the reference's own code.
+void oracle_estimate_normal(const float* pts, std::size_t n, float* out3, float* out_gap);
+
+void ref_estimate_normals_sample(
+    void* h,
+    int tree,
+    std::uint32_t const* sample,
+    std::size_t ns,
+    std::size_t k,
+    float* out_normals,
+    int nthreads)
+{
+    auto* c = static_cast<ref_cloud_t*>(h);
+    parallel_for(ns, nthreads, [&](std::size_t i) {
+        pcp::point_view_t const& v = c->views[sample[i]];
+        std::vector<pcp::point_view_t> nn;
+        if (tree == 0)
+            nn = c->octree->nearest_neighbours(v, k, view_map_t{});
+        else
+            nn = c->kdtree->nearest_neighbours(v, k);
+        std::vector<float> pts(3 * nn.size());
+        for (std::size_t j = 0; j < nn.size(); ++j)
+            pts[3 * j] = nn[j].x(), pts[3 * j + 1] = nn[j].y(), pts[3 * j + 2] = nn[j].z();
+        oracle_estimate_normal(pts.data(), nn.size(), out_normals + 3 * i, nullptr);
+    });
+}
+
 } // extern "C"

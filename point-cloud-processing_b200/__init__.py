@@ -20,4 +20,4 @@ from .capi import (  # noqa: F401
     lib,
     set_tuning,
 )
-from . import synth  # noqa: F401
+from . import sharding, synth  # noqa: F401

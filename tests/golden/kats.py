@@ -1,0 +1,83 @@
+"""Known-answer tests the reference itself holds for the hot path, restated as data
+(SURVEY.md §8c).  Each entry cites the reference test it comes from (paths relative to
+/root/reference/test/).  Pure data + tiny helpers: used against the oracle, the reference
+bridge, the host emulation and the CUDA path alike."""
+import numpy as np
+
+F = np.float32
+UNIT_BOX = (np.array([-1, -1, -1], F), np.array([1, 1, 1], F))
+
+# octree/octree_knn.cpp:13-60 and kdtree/knn.cpp (same data): one point per octant, k = 1
+OCTANT_POINTS = np.array([[-.5, -.5, -.5], [.5, -.5, -.5], [.5, .5, -.5], [-.5, .5, -.5],
+                          [-.5, -.5, .5], [.5, -.5, .5], [.5, .5, .5], [-.5, .5, .5]], F)
+OCTANT_QUERIES = np.array([[.51, .51, .51], [-.51, -.51, -.51], [.51, .51, -.51],
+                           [-.51, .51, .51]], F)
+OCTANT_EXPECTED = [6, 0, 2, 7]  # the reference only checks size == 1; the identity is implied
+
+# octree/octree_knn.cpp:61-88: the only point equals the target -> nothing is returned
+SELF_ONLY_POINTS = np.array([[-.5, -.5, -.5]], F)
+SELF_ONLY_QUERY = np.array([[-.5, -.5, -.5]], F)
+
+# octree/octree_knn.cpp:89-121: two points, one equal to the target, k = 2 -> one result
+SELF_PAIR_POINTS = np.array([[-.5, -.5, -.5], [-1., -1., -1.]], F)
+SELF_PAIR_QUERY = np.array([[-.5, -.5, -.5]], F)
+SELF_PAIR_EXPECTED = [1]
+
+# octree/octree_knn.cpp:123-183, kdtree/knn.cpp:117-176: ordering nearest -> furthest
+ORDER_POINTS = np.array([[-.5, -.5, -.5], [.5, -.5, -.5], [-.5, .5, -.5], [-.5, -.5, .5],
+                         [.5, -.5, .5], [.5, .5, .5], [-.5, .5, .5],
+                         [.51, .51, -.51], [.61, .51, -.51], [.41, .31, -.51],
+                         [.71, .21, -.51]], F)
+ORDER_QUERY = np.array([[.5, .5, -.5]], F)
+ORDER_EXPECTED_K4 = [7, 8, 9, 10]
+ORDER_EXPECTED_K3 = [7, 8, 9]
+
+# octree/octree_range_search.cpp:23-79, kdtree/kdtree_range_search.cpp:22-81
+RANGE_POINTS = np.array([[-.5, -.5, -.5], [.5, -.5, -.5], [.5, .5, -.5], [-.5, .5, -.5],
+                         [-.5, -.5, .5], [.5, -.5, .5], [.5, .5, .5], [-.5, .5, .5],
+                         [-.4, -.3, -.6], [.4, -.3, -.6], [.4, .3, -.6], [-.4, .3, -.6],
+                         [-.4, -.3, .6], [.4, -.3, .6], [.4, .3, .6], [-.4, .3, .6]], F)
+RANGE_SPHERES = [  # (centre, radius, expected original indices)
+    (np.array([0., 0., 0.], F), F(0.1), []),
+    (np.array([.9, .9, .9], F), F(1.0), [6, 14]),
+]
+
+# octree/octree_insertion.cpp:21-40,46-89: points outside the voxel grid are not inserted
+def insertion_points():
+    v = np.arange(1, 10, dtype=np.float64) / 10.0
+    pts = []
+    for sx, sy, sz in ((1, 1, 1), (-1, 1, 1), (1, -1, 1), (1, -1, -1)):
+        pts += [[sx * a, sy * a, sz * a] for a in v]
+    inside = np.array(pts, F)
+    outside = np.array([[-2, 0, 0], [0, -2, 0], [0, 0, -2], [2, 0, 0], [0, 2, 0], [0, 0, 2]], F)
+    return inside, outside
+
+
+# common/normal_estimation.cpp:12-37: axis cross -> +-(0, 0, 1), unit norm
+PCA_CROSS = np.array([[0, 0, 0], [-2, 0, 0], [2, 0, 0], [0, -2, 0], [0, 2, 0], [0, 0, -1],
+                      [0, 0, 1]], F)
+PCA_EXPECTED = np.array([0, 0, 1], F)
+
+# algorithm/average_distance_to_neighbors.cpp:35-78: 4 clusters of 3 collinear points
+def mean_distance_case():
+    d = F(0.1)
+    z = F(0.0)
+    one = F(1.0)
+    pts = np.array([[z, z, z], [z, z, z + d], [z, z, z - d],
+                    [one, z, z], [one, z + d, z], [one, z - d, z],
+                    [z, one, z], [z + d, one, z], [z - d, one, z],
+                    [z, z, one], [z + d, z, one], [z - d, z, one]], F)
+    return pts, 2, F(16.0 / 12.0) * d
+
+
+# octree/octree_knn.cpp:184-254 with a fixed seed in place of std::random_device
+def planted_corner_case(seed, size=None, k=None):
+    rng = np.random.default_rng(seed)
+    size = int(rng.integers(1_000, 20_000)) if size is None else size
+    k = int(rng.integers(1, 11)) if k is None else k
+    pts = rng.uniform(-0.95, 0.95, (size, 3)).astype(F)
+    planted = np.stack([rng.uniform(-.99, -.96, k), rng.uniform(.96, .99, k),
+                        rng.uniform(.96, .99, k)], 1).astype(F)
+    cloud = np.concatenate([pts, planted], 0)
+    box = (np.array([-2, -2, -2], F), np.array([2, 2, 2], F))
+    return cloud, np.array([[-1., 1., 1.]], F), k, set(range(size, size + k)), box

@@ -251,6 +251,8 @@ class RefBridge:
                                  _u32p, _u64p, _i64p, C.c_int]
         L.ref_average_distance_to_neighbors.restype = C.c_float
         L.ref_average_distance_to_neighbors.argtypes = [C.c_void_p, C.c_int, C.c_size_t, _f32p]
+        L.ref_estimate_normals_sample.argtypes = [C.c_void_p, C.c_int, _u32p, C.c_size_t,
+                                                  C.c_size_t, _f32p, C.c_int]
         self.L = L
 
     def cloud(self, xyz, which=2, bbox=None, node_capacity=0, max_depth=0, kd_adaptive=1):
@@ -327,3 +329,11 @@ class RefCloud:
         means = np.zeros(self.n, np.float32)
         mu = self.L.ref_average_distance_to_neighbors(self.h, tree, k, _ptr(means, _f32p))
         return means, np.float32(mu)
+
+    def normals_sample(self, tree, sample, k, nthreads=None):
+        """estimate_normals' per-element body for the cloud points listed in `sample`"""
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        out = np.zeros((len(sample), 3), np.float32)
+        self.L.ref_estimate_normals_sample(self.h, tree, _ptr(sample, _u32p), len(sample), k,
+                                           _ptr(out, _f32p), nthreads or nthreads_default())
+        return out
