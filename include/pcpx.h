@@ -257,8 +257,8 @@ typedef struct pcpx_timings
 int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
 
 /* Process-wide tunables (performance only, never results).  Known names:
- *   "level_factor"  start level of a kNN search = finest level whose own cell holds at least
- *                   level_factor * k points (default 0.5). */
+ *   "level_factor"  main level of a kNN-shaped call = finest stored level whose mean cell
+ *                   occupancy is at least level_factor * k (default 0.35). */
 int pcpx_set_tuning(const char* name, double value);
 
 /* Search work of a self-kNN over the whole cloud, summed over queries:

@@ -41,7 +41,14 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: build an experimental variant (e.g. -DPCPX_MIN_BLOCKS=8) next to the
+    product library; the product is always built with no extra defines."""
+    global LIB, OBJDIR
+    if out is not None:
+        LIB = os.path.join(LIBDIR, out)
+        OBJDIR = os.path.join(HERE, "build", out.replace(".so", ""))
+        force = True
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
@@ -50,7 +57,7 @@ def build(force=False, verbose=False):
 
     def compile_one(unit):
         obj = os.path.join(OBJDIR, unit.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        cmd = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, unit), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -69,4 +76,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs,
+                out=outs[0] if outs else None))

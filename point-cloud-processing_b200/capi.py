@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpcpx.so")
+LIB_PATH = os.environ.get("PCPX_LIB", os.path.join(HERE, "lib", "libpcpx.so"))  # PCPX_LIB: experimental builds
 NO_NEIGHBOUR = 0xFFFFFFFF
 
 

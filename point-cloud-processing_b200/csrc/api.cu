@@ -31,8 +31,12 @@ struct InBuf
             return;
         }
         staged.alloc(n * (size_t)width);
-        PCPX_CUDA(cudaMemcpy2DAsync(staged.get(), (size_t)width * 4, p, stride_bytes,
-                                    (size_t)width * 4, n, cudaMemcpyHostToDevice, s));
+        if (stride_bytes == (size_t)width * 4) // packed rows: one DMA, not one per row
+            PCPX_CUDA(cudaMemcpyAsync(staged.get(), p, n * (size_t)width * 4,
+                                      cudaMemcpyHostToDevice, s));
+        else
+            PCPX_CUDA(cudaMemcpy2DAsync(staged.get(), (size_t)width * 4, p, stride_bytes,
+                                        (size_t)width * 4, n, cudaMemcpyHostToDevice, s));
         d = staged.get(), stride_f = (uint32_t)width;
         h2d_bytes = n * (size_t)width * 4;
     }

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -48,7 +49,102 @@ inline std::string& last_error_storage()
 
 #define PCPX_CHECK_LAUNCH() PCPX_CUDA(cudaGetLastError())
 
-// Owning device allocation (stream-ordered free is not needed: the index outlives its calls).
+// Process-wide caching allocator for device memory.  cudaMalloc / cudaFree cost tens of
+// microseconds to milliseconds each and synchronise the device; an index build needs a dozen
+// temporaries and a serving loop rebuilds indices continuously, so freed blocks are kept per
+// device and handed out again (best fit, at most 25 % slack).  Blocks are only recycled after
+// the stream work that used them has been synchronised by the caller (every C-ABI call ends
+// with a stream synchronise before its buffers go out of scope).
+class DevicePool
+{
+  public:
+    static DevicePool& instance()
+    {
+        static DevicePool p;
+        return p;
+    }
+    void* acquire(size_t bytes)
+    {
+        if (bytes == 0)
+            return nullptr;
+        int dev = 0;
+        PCPX_CUDA(cudaGetDevice(&dev));
+        size_t const want = (bytes + 511) & ~size_t(511);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            auto& fl  = free_[dev];
+            auto best = fl.end();
+            for (auto it = fl.lower_bound(want); it != fl.end(); ++it)
+            {
+                if (it->first <= want + want / 4 + 4096)
+                    best = it;
+                break;
+            }
+            if (best != fl.end())
+            {
+                void* p = best->second;
+                size_[p] = best->first;
+                fl.erase(best);
+                return p;
+            }
+        }
+        void* p       = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaErrorMemoryAllocation)
+        {
+            cudaGetLastError();
+            trim(dev); // give cached blocks back and retry once
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess)
+            fail(e == cudaErrorMemoryAllocation ? PCPX_ERR_OUT_OF_MEMORY : PCPX_ERR_CUDA,
+                 "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        std::lock_guard<std::mutex> lock(m_);
+        size_[p] = want;
+        dev_[p]  = dev;
+        return p;
+    }
+    void release(void* p)
+    {
+        if (!p)
+            return;
+        std::lock_guard<std::mutex> lock(m_);
+        auto it = size_.find(p);
+        if (it == size_.end())
+        {
+            cudaFree(p);
+            return;
+        }
+        free_[dev_[p]].emplace(it->second, p);
+    }
+    // hand a block over to the caller (it will be freed with cudaFree by pcpx_free)
+    void forget(void* p)
+    {
+        std::lock_guard<std::mutex> lock(m_);
+        size_.erase(p);
+        dev_.erase(p);
+    }
+    void trim(int dev)
+    {
+        std::multimap<size_t, void*> blocks;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            blocks.swap(free_[dev]);
+            for (auto& b : blocks)
+                size_.erase(b.second), dev_.erase(b.second);
+        }
+        for (auto& b : blocks)
+            cudaFree(b.second);
+    }
+
+  private:
+    std::mutex m_;
+    std::map<int, std::multimap<size_t, void*>> free_;
+    std::map<void*, size_t> size_;
+    std::map<void*, int> dev_;
+};
+
+// Owning device allocation out of the pool.
 template <typename T>
 class DevBuf
 {
@@ -75,20 +171,23 @@ class DevBuf
         release();
         n_ = n;
         if (n)
-            PCPX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p_), n * sizeof(T)));
+            p_ = static_cast<T*>(DevicePool::instance().acquire(n * sizeof(T)));
     }
     void release()
     {
         if (p_)
-            cudaFree(p_);
+            DevicePool::instance().release(p_);
         p_ = nullptr, n_ = 0;
     }
     T* get() const { return p_; }
     size_t size() const { return n_; }
     size_t bytes() const { return n_ * sizeof(T); }
+    // ownership leaves the pool: the caller frees it with cudaFree
     T* detach()
     {
         T* p = p_;
+        if (p)
+            DevicePool::instance().forget(p);
         p_ = nullptr, n_ = 0;
         return p;
     }

@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kBlock) encode_kernel(
         inside = x >= bx0 && y >= by0 && z >= bz0 && x <= bx1 && y <= by1 && z <= bz1;
     QueryCell const c = query_cell(g, x, y, z);
     uint64_t const m  = morton3(c.ux, c.uy, c.uz);
-    keys[i]           = inside ? (KeyT)m : (KeyT)~(KeyT)0; // un-indexed points sort to the tail
+    // un-indexed points get the first code past the grid: they sort to the tail
+    keys[i] = inside ? (KeyT)m : (KeyT)((KeyT)1 << (3 * g.lcap));
     vals[i]           = i;
 }
 
@@ -217,26 +218,25 @@ __global__ void __launch_bounds__(kBlock) table_count_kernel(GridView g, HashSlo
 
 // ---- radix sort driver ---------------------------------------------------------------------
 // Sorts (keys, vals) on bits [0, n_bits); returns true when the result is in the alt buffers.
-template <typename KeyT>
+// `hold` keeps the histogram / offset tables alive until the caller synchronises the stream.
+template <typename KeyT, class Holder>
 bool sort_pairs(KeyT* keys, uint32_t* vals, KeyT* keys_alt, uint32_t* vals_alt, uint32_t n,
-                int n_bits, cudaStream_t stream, uint32_t* launches)
+                int n_bits, cudaStream_t stream, uint32_t* launches, Holder& hold)
 {
     using namespace rsort;
     int const n_passes = (n_bits + kRadixBits - 1) / kRadixBits;
     if (n == 0 || n_passes == 0)
         return false;
     uint32_t const n_tiles = (n + kTile - 1) / kTile;
-    DevBuf<uint32_t> hist((size_t)n_passes * kRadix);
-    DevBuf<uint32_t> counts((size_t)kRadix * n_tiles);
+    hold.hist.alloc((size_t)n_passes * kRadix);
+    hold.counts.alloc((size_t)kRadix * n_tiles);
+    DevBuf<uint32_t>& hist   = hold.hist;
+    DevBuf<uint32_t>& counts = hold.counts;
     PCPX_CUDA(cudaMemsetAsync(hist.get(), 0, hist.bytes(), stream));
     uint32_t const hist_blocks = std::min<uint32_t>(n_tiles, 148u * 8u);
     digit_histograms<KeyT><<<hist_blocks, kThreads, 0, stream>>>(keys, n, 0, n_passes, hist.get());
     PCPX_CHECK_LAUNCH();
     ++*launches;
-    std::vector<uint32_t> h_hist((size_t)n_passes * kRadix);
-    PCPX_CUDA(cudaMemcpyAsync(h_hist.data(), hist.get(), hist.bytes(), cudaMemcpyDeviceToHost,
-                              stream));
-    PCPX_CUDA(cudaStreamSynchronize(stream));
 
     size_t const smem = sizeof(ScatterSmem<KeyT>);
     PCPX_CUDA(cudaFuncSetAttribute(scatter<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -244,12 +244,6 @@ bool sort_pairs(KeyT* keys, uint32_t* vals, KeyT* keys_alt, uint32_t* vals_alt, 
     bool in_alt = false;
     for (int p = 0; p < n_passes; ++p)
     {
-        bool constant = false;
-        for (int d = 0; d < kRadix; ++d)
-            if (h_hist[(size_t)p * kRadix + d] == n)
-                constant = true;
-        if (constant)
-            continue; // every key has the same digit: the pass would be the identity
         KeyT* kin      = in_alt ? keys_alt : keys;
         uint32_t* vin  = in_alt ? vals_alt : vals;
         KeyT* kout     = in_alt ? keys : keys_alt;
@@ -266,7 +260,6 @@ bool sort_pairs(KeyT* keys, uint32_t* vals, KeyT* keys_alt, uint32_t* vals_alt, 
         *launches += 3;
         in_alt = !in_alt;
     }
-    PCPX_CUDA(cudaStreamSynchronize(stream)); // hist / counts are freed on return
     return in_alt;
 }
 
@@ -286,28 +279,38 @@ int auto_level_cap(uint64_t n, float extent, float maxabs, uint32_t user_max)
 } // namespace
 
 // --------------------------------------------------------------------------------------------
+// Temporaries of the sort; kept alive by the caller until the stream has been synchronised.
+struct SortScratch
+{
+    DevBuf<unsigned char> keys, keys_alt;
+    DevBuf<uint32_t> vals, vals_alt;
+    DevBuf<uint32_t> hist, counts;
+    bool in_alt = false;
+    uint32_t* order() { return in_alt ? vals_alt.get() : vals.get(); }
+};
+
 template <typename KeyT>
 static void encode_and_sort(pcpx_index& ix, const float* d_xyz, uint32_t n,
-                            const pcpx_index_params& prm, DevBuf<uint32_t>& order_out,
-                            uint32_t* launches, float* sort_ms)
+                            const pcpx_index_params& prm, SortScratch& sc, uint32_t* launches,
+                            Event& e0, Event& e1)
 {
-    DevBuf<KeyT> keys(n), keys_alt(n);
-    DevBuf<uint32_t> vals(n), vals_alt(n);
+    sc.keys.alloc((size_t)n * sizeof(KeyT));
+    sc.keys_alt.alloc((size_t)n * sizeof(KeyT));
+    sc.vals.alloc(n);
+    sc.vals_alt.alloc(n);
+    KeyT* keys     = reinterpret_cast<KeyT*>(sc.keys.get());
+    KeyT* keys_alt = reinterpret_cast<KeyT*>(sc.keys_alt.get());
     encode_kernel<KeyT><<<blocks_for(n, kBlock), kBlock, 0, ix.stream>>>(
         d_xyz, 3u, n, ix.grid, prm.use_voxel_grid, prm.voxel_min[0], prm.voxel_min[1],
-        prm.voxel_min[2], prm.voxel_max[0], prm.voxel_max[1], prm.voxel_max[2], keys.get(),
-        vals.get());
+        prm.voxel_min[2], prm.voxel_max[0], prm.voxel_max[1], prm.voxel_max[2], keys,
+        sc.vals.get());
     PCPX_CHECK_LAUNCH();
     ++*launches;
-    Event e0, e1;
     e0.record(ix.stream);
-    int const bits = prm.use_voxel_grid ? (int)(8 * sizeof(KeyT)) : 3 * ix.grid.lcap;
-    bool const alt = sort_pairs<KeyT>(keys.get(), vals.get(), keys_alt.get(), vals_alt.get(), n,
-                                      bits, ix.stream, launches);
+    int const bits = 3 * ix.grid.lcap + (prm.use_voxel_grid ? 1 : 0);
+    sc.in_alt = sort_pairs<KeyT>(keys, sc.vals.get(), keys_alt, sc.vals_alt.get(), n, bits,
+                                 ix.stream, launches, sc);
     e1.record(ix.stream);
-    PCPX_CUDA(cudaStreamSynchronize(ix.stream));
-    *sort_ms  = elapsed_ms(e0, e1);
-    order_out = alt ? std::move(vals_alt) : std::move(vals);
 }
 
 pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
@@ -354,9 +357,12 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
     else if (n)
     {
         staged.alloc(3 * n);
-        PCPX_CUDA(cudaMemcpy2DAsync(staged.get(), 12, xyz, stride_bytes, 12, n,
-                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                    ix.stream));
+        cudaMemcpyKind const kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (stride_bytes == 12) // packed rows: one DMA, not one per row
+            PCPX_CUDA(cudaMemcpyAsync(staged.get(), xyz, 12 * n, kind, ix.stream));
+        else
+            PCPX_CUDA(cudaMemcpy2DAsync(staged.get(), 12, xyz, stride_bytes, 12, n, kind,
+                                        ix.stream));
         d_xyz = staged.get();
     }
 
@@ -420,22 +426,20 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
 
     // 4. codes -> sort -> SoA
     ix.pts.alloc(std::max<size_t>(n, 1));
-    g.pts         = ix.pts.get();
-    float sort_ms = 0.f;
+    g.pts = ix.pts.get();
+    SortScratch sc;
+    Event ev_sort0, ev_sort1;
     if (n)
     {
-        DevBuf<uint32_t> order;
-        if (ix.code_bits <= 30)
-            encode_and_sort<uint32_t>(ix, d_xyz, n32, prm, order, &launches, &sort_ms);
+        if (ix.code_bits + 1 <= 32)
+            encode_and_sort<uint32_t>(ix, d_xyz, n32, prm, sc, &launches, ev_sort0, ev_sort1);
         else
-            encode_and_sort<uint64_t>(ix, d_xyz, n32, prm, order, &launches, &sort_ms);
-        reorder_kernel<<<blocks_for(n, kBlock), kBlock, 0, ix.stream>>>(d_xyz, order.get(), n32,
+            encode_and_sort<uint64_t>(ix, d_xyz, n32, prm, sc, &launches, ev_sort0, ev_sort1);
+        reorder_kernel<<<blocks_for(n, kBlock), kBlock, 0, ix.stream>>>(d_xyz, sc.order(), n32,
                                                                          ix.pts.get());
         PCPX_CHECK_LAUNCH();
         ++launches;
-        PCPX_CUDA(cudaStreamSynchronize(ix.stream)); // `order` is freed here
     }
-    staged.release();
 
     // 5. cells per level -> finest stored level
     std::vector<uint32_t> lh(kMaxLevel + 2, 0u);
@@ -451,6 +455,11 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
                                   ix.stream));
         PCPX_CUDA(cudaStreamSynchronize(ix.stream));
     }
+    else
+        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+    float const sort_ms = n ? elapsed_ms(ev_sort0, ev_sort1) : 0.f;
+    sc = SortScratch{}; // the stream is idle: the sort temporaries and the staged copy can go
+    staged.release();
     double const min_occ = prm.min_cell_occupancy ? (double)prm.min_cell_occupancy : 4.0;
     uint64_t cells = 0, total_cells = 0;
     for (int l = 0; l <= g.lcap; ++l)
@@ -459,6 +468,7 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
         if (l > 0 && (double)g.n / (double)std::max<uint64_t>(cells, 1) < min_occ)
             break;
         g.lfine = l;
+        ix.cells_per_level[l] = cells;
         total_cells += cells;
     }
     ix.n_cells = total_cells;
@@ -495,15 +505,19 @@ void sort_queries_by_cell(const pcpx_index& ix, const float* d_queries, uint32_t
     if (nq == 0)
         return;
     uint32_t launches = 0;
-    DevBuf<uint64_t> keys(nq), keys_alt(nq);
-    DevBuf<uint32_t> vals_alt(nq);
+    SortScratch sc;
+    sc.keys.alloc((size_t)nq * 8);
+    sc.keys_alt.alloc((size_t)nq * 8);
+    sc.vals_alt.alloc(nq);
+    uint64_t* keys     = reinterpret_cast<uint64_t*>(sc.keys.get());
+    uint64_t* keys_alt = reinterpret_cast<uint64_t*>(sc.keys_alt.get());
     encode_kernel<uint64_t><<<blocks_for(nq, kBlock), kBlock, 0, ix.stream>>>(
-        d_queries, stride_floats, nq, ix.grid, 0, 0, 0, 0, 0, 0, 0, keys.get(), d_order);
+        d_queries, stride_floats, nq, ix.grid, 0, 0, 0, 0, 0, 0, 0, keys, d_order);
     PCPX_CHECK_LAUNCH();
-    bool const alt = sort_pairs<uint64_t>(keys.get(), d_order, keys_alt.get(), vals_alt.get(), nq,
-                                          3 * ix.grid.lcap, ix.stream, &launches);
+    bool const alt = sort_pairs<uint64_t>(keys, d_order, keys_alt, sc.vals_alt.get(), nq,
+                                          3 * ix.grid.lcap, ix.stream, &launches, sc);
     if (alt)
-        PCPX_CUDA(cudaMemcpyAsync(d_order, vals_alt.get(), (size_t)nq * 4,
+        PCPX_CUDA(cudaMemcpyAsync(d_order, sc.vals_alt.get(), (size_t)nq * 4,
                                   cudaMemcpyDeviceToDevice, ix.stream));
     PCPX_CUDA(cudaStreamSynchronize(ix.stream));
 }

@@ -14,6 +14,7 @@ struct pcpx_index
     float bbox_min[3]{}, bbox_max[3]{};
     uint32_t code_bits = 0;
     uint64_t n_cells   = 0;
+    uint64_t cells_per_level[pcpx::kMaxLevel + 2] = {}; // occupied cells at each stored level
     pcpx::GridView grid{}; // device pointers into the buffers below
     pcpx::DevBuf<float4> pts;          // n_input entries, Morton order; w = original index
     pcpx::DevBuf<pcpx::HashSlot> table; // all levels

@@ -70,24 +70,6 @@ struct TopK
     }
 };
 
-// Finest level whose own cell holds at least `min_count` points (0 = root).
-PCPX_HD int select_level(const GridView& g, const QueryCell& c, uint32_t min_count,
-                         SearchStats* st)
-{
-    int l = g.lfine;
-    for (; l > 0; --l)
-    {
-        int const sh = g.lcap - l;
-        uint32_t start, count;
-        if (st)
-            st->lookups++;
-        if (find_cell(g, cell_key(l, c.ux >> sh, c.uy >> sh, c.uz >> sh), start, count) &&
-            count >= min_count)
-            break;
-    }
-    return l;
-}
-
 // Geometry of the query inside its own cell at one level: conservative distances to the six
 // faces of the cell (for per-cell bounds) and to the faces of the 3x3x3 block (termination).
 struct BlockGeom
@@ -145,15 +127,15 @@ PCPX_HD void offer(TopK<K>& top, const float4& c, uint32_t pos, float qx, float 
 }
 
 // The search proper.  On return `top` holds the K best entries (first k are the answer).
-// min_count steers the start level (cells with about k/2 points make the first 3x3x3 block
-// succeed for most queries); correctness does not depend on it.
+// start_level only steers the cost (a level whose cells hold a fraction of k points makes the
+// first 3x3x3 block succeed for most queries); correctness does not depend on it.
 // Returns the level at which the answer was found (every list entry lies in that level's block).
 template <int K, int TIE>
 PCPX_HD int knn_search(const GridView& g, float qx, float qy, float qz, uint32_t k, float eps,
-                       uint32_t min_count, TopK<K>& top, SearchStats* st)
+                       int start_level, TopK<K>& top, SearchStats* st)
 {
     QueryCell const qc = query_cell(g, qx, qy, qz);
-    int l              = select_level(g, qc, min_count, st);
+    int l              = start_level;
     for (;; --l)
     {
         top.reset();
@@ -237,6 +219,19 @@ struct TopD
             a[j] = fmaxf(a[j - 1], fminf(a[j], d));
         a[0] = fminf(a[0], d);
     }
+    // Two candidates at once: with lo <= hi, the j-th smallest of list + {lo, hi} is
+    // max(min(a[j], lo), min(a[j-1], hi), a[j-2]) — 2 min + one 3-input max per slot for TWO
+    // candidates (1.5 ALU ops per slot and candidate instead of 2).
+    PCPX_HD void insert2(float d0, float d1)
+    {
+        float const lo = fminf(d0, d1), hi = fmaxf(d0, d1);
+#pragma unroll
+        for (int j = K - 1; j >= 2; --j)
+            a[j] = fmaxf(fmaxf(fminf(a[j], lo), fminf(a[j - 1], hi)), a[j - 2]);
+        if (K >= 2)
+            a[K >= 2 ? 1 : 0] = fmaxf(fminf(a[K >= 2 ? 1 : 0], lo), fminf(a[0], hi));
+        a[0] = fminf(a[0], lo);
+    }
     // number of entries strictly below d (= rank of a neighbour at distance d)
     PCPX_HD uint32_t rank_of(float d) const
     {
@@ -315,78 +310,189 @@ PCPX_HD void collect_cells(const GridView& g, const BlockGeom& b, int level, Cel
     cl.n = n;
 }
 
-// Flat iteration over the spans of a CellList whose lower bound does not exceed `bound()`
-// (re-evaluated whenever a new span is entered).  body(p) is called once per point position.
-#define PCPX_FLAT_FOR_EACH(cl, bound_expr, p_var, ...)                                       \
+// Flat iteration over the spans of a CellList whose lower bound does not exceed `bound_expr`
+// (re-evaluated whenever a new span is entered).  The body sees `c_var` (the point at sorted
+// position `p_var`); the NEXT point of the span is already in flight while the body runs
+// (software prefetch: the ~40-cycle L1 latency hides behind the ~50 instructions of the body).
+#ifndef PCPX_PREFETCH
+#define PCPX_PREFETCH 1
+#endif
+#define PCPX_FLAT_FOR_EACH(g, cl, bound_expr, p_var, c_var, ...)                               \
     {                                                                                          \
         int e_ = 0;                                                                            \
         uint32_t p_var = 0, pend_ = 0;                                                         \
+        float4 next_ = make_float4(0.f, 0.f, 0.f, 0.f);                                        \
         for (;;)                                                                               \
         {                                                                                      \
             bool done_ = false;                                                                \
-            while (p_var == pend_)                                                             \
+            if (p_var == pend_)                                                                \
             {                                                                                  \
-                if (e_ == (cl).n)                                                              \
+                for (;;)                                                                       \
                 {                                                                              \
-                    done_ = true;                                                              \
+                    if (e_ == (cl).n)                                                          \
+                    {                                                                          \
+                        done_ = true;                                                          \
+                        break;                                                                 \
+                    }                                                                          \
+                    float const lb_    = (cl).lb2[e_];                                         \
+                    uint32_t const s_  = (cl).start[e_];                                       \
+                    uint32_t const en_ = (cl).end[e_];                                         \
+                    ++e_;                                                                      \
+                    if (lb_ > (bound_expr)) /* equal: a tie may hide there */                  \
+                        continue;                                                              \
+                    p_var = s_, pend_ = en_;                                                   \
+                    next_ = load_pt((g).pts + p_var);                                          \
                     break;                                                                     \
                 }                                                                              \
-                float const lb_     = (cl).lb2[e_];                                            \
-                uint32_t const s_   = (cl).start[e_];                                          \
-                uint32_t const en_  = (cl).end[e_];                                            \
-                ++e_;                                                                          \
-                if (lb_ > (bound_expr)) /* equal: a tie may hide there */                      \
-                    continue;                                                                  \
-                p_var = s_, pend_ = en_;                                                       \
             }                                                                                  \
             if (done_)                                                                         \
                 break;                                                                         \
+            float4 const c_var = next_;                                                        \
+            if (PCPX_PREFETCH && p_var + 1 < pend_)                                            \
+                next_ = load_pt((g).pts + p_var + 1);                                          \
             __VA_ARGS__;                                                                       \
             ++p_var;                                                                           \
+            if (!PCPX_PREFETCH && p_var < pend_)                                               \
+                next_ = load_pt((g).pts + p_var);                                              \
         }                                                                                      \
     }
 
-// Pass 1.  Returns the level the answer was found at; `b` / `cl` describe that level's block.
+// Candidates that were at or below the list's worst distance when pass 1 met them — a superset
+// of the final neighbours (the worst distance only shrinks) and typically ~k (1 + ln(n / k)) of
+// the n candidates, so pass 2 revisits about half of them.  Entry = (span index << 11) | offset
+// inside the span; spans longer than 2048 points or more than kShortMax entries set `overflow`
+// and pass 2 falls back to walking every span again.
+constexpr int kShortMax = 64;
+struct ShortList
+{
+    uint16_t code[kShortMax];
+    uint32_t n;
+    bool overflow;
+};
+
+PCPX_HD void shortlist_push(ShortList& sl, int span, uint32_t offset)
+{
+    if (sl.n < (uint32_t)kShortMax && offset < 2048u)
+        sl.code[sl.n] = (uint16_t)(((uint32_t)span << 11) | offset);
+    else
+        sl.overflow = true;
+    sl.n += 1;
+}
+
+PCPX_HD float candidate_d2(const float4& c, float qx, float qy, float qz, float eps)
+{
+    float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
+    float d2       = sqdist_x(dx, dy, dz);
+    // exclusion box, common/vector3d_queries.hpp:31-35,59-63 (strict <, all axes)
+    if (fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps)
+        d2 = INFINITY;
+    return d2;
+}
+
+// Pass 1 at ONE level: distances of every candidate of the level's 3x3x3 block go through the
+// sorted list, two at a time, with the next pair already in flight.  Returns true when the
+// answer is final: the k-th distance is strictly below the distance to anything outside the
+// block (or the level is the root, which holds every point).
+template <int K>
+PCPX_HD bool knn_attempt_dist(const GridView& g, const QueryCell& qc, int level, float qx,
+                              float qy, float qz, uint32_t k, float eps, TopD<K>& top,
+                              BlockGeom& b, CellList& cl, ShortList& sl, SearchStats* st)
+{
+    top.reset();
+    sl.n        = 0;
+    sl.overflow = false;
+    if (st)
+        st->attempts++;
+    b = block_geom(g, qc, level, qx, qy, qz);
+    collect_cells(g, b, level, cl, st);
+
+    int e = 0;                // next span to enter
+    uint32_t p = 0, pend = 0; // position inside the current span
+    uint32_t pstart = 0;
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+    for (;;)
+    {
+        bool done = false;
+        if (p >= pend)
+        {
+            for (;;)
+            {
+                if (e == cl.n)
+                {
+                    done = true;
+                    break;
+                }
+                float const lb    = cl.lb2[e];
+                uint32_t const s  = cl.start[e];
+                uint32_t const en = cl.end[e];
+                ++e;
+                if (lb > top.worst()) // equal: a tie may hide there
+                    continue;
+                p = pstart = s, pend = en;
+                c0 = load_pt(g.pts + p);
+                c1 = load_pt(g.pts + (p + 1 < pend ? p + 1 : p));
+                break;
+            }
+        }
+        if (done)
+            break;
+        bool const has1 = p + 1 < pend;
+        float4 const a0 = c0, a1 = c1;
+        if (p + 2 < pend) // prefetch the next pair
+        {
+            c0 = load_pt(g.pts + p + 2);
+            c1 = load_pt(g.pts + (p + 3 < pend ? p + 3 : p + 2));
+        }
+        float const d0 = candidate_d2(a0, qx, qy, qz, eps);
+        float const d1 = has1 ? candidate_d2(a1, qx, qy, qz, eps) : INFINITY;
+        float const w  = top.worst();
+        if (d0 <= w && d0 < INFINITY)
+            shortlist_push(sl, e - 1, p - pstart);
+        if (d1 <= w && d1 < INFINITY)
+            shortlist_push(sl, e - 1, p + 1 - pstart);
+        top.insert2(d0, d1);
+        if (st)
+            st->candidates += has1 ? 2 : 1;
+        p += 2;
+    }
+    return level == 0 || top.kth(k) < b.block_lb2;
+}
+
+// Pass 1 walking to coarser levels until the answer is final.  Returns the final level.
 template <int K>
 PCPX_HD int knn_search_dist(const GridView& g, float qx, float qy, float qz, uint32_t k,
-                            float eps, uint32_t min_count, TopD<K>& top, BlockGeom& b,
-                            CellList& cl, SearchStats* st)
+                            float eps, int start_level, TopD<K>& top, BlockGeom& b,
+                            CellList& cl, ShortList& sl, SearchStats* st)
 {
     QueryCell const qc = query_cell(g, qx, qy, qz);
-    int l              = select_level(g, qc, min_count, st);
-    for (;; --l)
-    {
-        top.reset();
-        if (st)
-            st->attempts++;
-        b = block_geom(g, qc, l, qx, qy, qz);
-        collect_cells(g, b, l, cl, st);
-        PCPX_FLAT_FOR_EACH(cl, top.worst(), p, {
-            float4 const c = load_pt(g.pts + p);
-            float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
-            float d2       = sqdist_x(dx, dy, dz);
-            // exclusion box, common/vector3d_queries.hpp:31-35,59-63 (strict <, all axes)
-            if (fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps)
-                d2 = INFINITY;
-            top.insert(d2);
-            if (st)
-                st->candidates++;
-        });
-        if (l == 0)
-            break;
-        if (top.kth(k) < b.block_lb2) // strictly closer than anything outside the block
-            break;
-    }
+    int l              = start_level;
+    while (!knn_attempt_dist<K>(g, qc, l, qx, qy, qz, k, eps, top, b, cl, sl, st))
+        --l;
     return l;
 }
 
-// Pass 2.  f(point, sorted position, d2, dx, dy, dz) for every eligible point with d2 <= tau.
+// Pass 2.  f(point, sorted position, d2, dx, dy, dz) for every eligible point with d2 <= tau:
+// over the short list when it is complete, else over every span again.
 template <class F>
-PCPX_HD void for_each_within(const GridView& g, const CellList& cl, float qx, float qy, float qz,
-                             float tau, float eps, F&& f)
+PCPX_HD void for_each_within(const GridView& g, const CellList& cl, const ShortList& sl, float qx,
+                             float qy, float qz, float tau, float eps, F&& f)
 {
-    PCPX_FLAT_FOR_EACH(cl, tau, p, {
-        float4 const c = load_pt(g.pts + p);
+    if (!sl.overflow)
+    {
+        for (uint32_t j = 0; j < sl.n; ++j)
+        {
+            uint32_t const code = sl.code[j];
+            uint32_t const p    = cl.start[code >> 11] + (code & 2047u);
+            float4 const c      = load_pt(g.pts + p);
+            float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
+            float const d2 = sqdist_x(dx, dy, dz);
+            bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
+            if (!excluded && d2 <= tau)
+                f(c, p, d2, dx, dy, dz);
+        }
+        return;
+    }
+    PCPX_FLAT_FOR_EACH(g, cl, tau, p, c, {
         float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
         float const d2 = sqdist_x(dx, dy, dz);
         bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;

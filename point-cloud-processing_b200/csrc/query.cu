@@ -19,6 +19,17 @@ Tuning& tuning()
 namespace {
 
 constexpr int kQBlock = 128;
+// The kNN kernels are latency-bound (dependent L1 / local-memory loads in the span walk), so
+// occupancy is bought with a register cap: 10 CTAs of 128 threads per SM (48 registers) for
+// lists up to 16 entries measured best on B200 (4.3 ms vs 6.2 ms uncapped at k = 15, 10 M
+// points); longer lists get proportionally more registers.
+#ifndef PCPX_MIN_BLOCKS_SMALL_K
+#define PCPX_MIN_BLOCKS_SMALL_K 10
+#endif
+__host__ __device__ constexpr int min_blocks_for(int K)
+{
+    return K <= 16 ? PCPX_MIN_BLOCKS_SMALL_K : (K <= 24 ? 9 : 7);
+}
 
 inline uint32_t grid_for(uint32_t n, int block) { return std::max(1u, (n + block - 1) / block); }
 
@@ -43,18 +54,43 @@ __device__ __forceinline__ bool fetch_query(const GridView& g, const QueryBatch&
 }
 
 // ---- kNN-shaped kernels ----------------------------------------------------------------------
-// Fast path: two-pass search (knn_core.cuh).  Queries whose answer hinges on bit-equal
-// distances take the exact 64-bit (distance, original index) search in a separate noinline
-// function so that its register footprint does not tax the fast path.
+// Main pass: every query makes ONE attempt at the call's main level (chosen on the host from
+// the per-level cell occupancy so that the level's 3x3x3 block holds a few times k points).
+// All lanes of a warp therefore do the same amount of structure work, and the few queries whose
+// neighbourhood reaches past their block (sparse regions, outliers) do not stall 31 other
+// lanes: they are appended to a retry queue and answered by a second launch that walks to
+// coarser levels.  Queries whose answer hinges on bit-equal distances take the exact 64-bit
+// (distance, original index) search in a noinline function (register footprint stays off the
+// fast path).
+enum KnnMode
+{
+    MODE_KNN     = 0, // index rows (+ distances, counts)
+    MODE_MEAN    = 1, // mean neighbour distance
+    MODE_NORMALS = 2  // fused PCA normal (+ centroid)
+};
+
+struct KnnOutputs
+{
+    uint32_t* idx;
+    float* d2;
+    uint32_t* count;
+    float* mean;
+    float* normal;
+    float* centroid;
+    uint32_t* exact_counter; // queries answered by the exact tie path
+    uint32_t* retry_items;   // queue of thread ids for the second launch
+    uint32_t* retry_count;
+};
+
 __host__ __device__ constexpr int exact_k(int K) { return (K + 3) / 4 * 4; }
 
 template <int K>
 __device__ __noinline__ void knn_exact_row(const GridView& g, float x, float y, float z,
-                                           uint32_t k, float eps, uint32_t min_count,
+                                           uint32_t k, float eps, int start_level,
                                            uint32_t* idx_row, float* d2_row, uint32_t* out_count)
 {
     TopK<exact_k(K)> top;
-    knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, top, nullptr);
+    knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, start_level, top, nullptr);
     uint32_t n = 0;
 #pragma unroll
     for (int j = 0; j < exact_k(K); ++j)
@@ -71,56 +107,13 @@ __device__ __noinline__ void knn_exact_row(const GridView& g, float x, float y, 
 }
 
 template <int K>
-__global__ void __launch_bounds__(kQBlock) knn_kernel(
-    GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
-    uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, uint32_t* __restrict__ out_count,
-    uint32_t* __restrict__ retry_counter)
-{
-    float x, y, z;
-    uint32_t row;
-    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
-        return;
-    TopD<K> top;
-    BlockGeom b;
-    CellList cl;
-    knn_search_dist<K>(g, x, y, z, k, eps, min_count, top, b, cl, nullptr);
-    uint32_t* idx_row = out_idx + (size_t)row * k;
-    float* d2_row     = out_d2 ? out_d2 + (size_t)row * k : nullptr;
-    uint32_t* cnt     = out_count ? out_count + row : nullptr;
-    if (!knn_two_pass_emit<K>(g, cl, x, y, z, top, k, eps, idx_row, d2_row, cnt))
-    {
-        knn_exact_row<K>(g, x, y, z, k, eps, min_count, idx_row, d2_row, cnt);
-        if (retry_counter)
-            atomicAdd(retry_counter, 1u);
-    }
-}
-
-// the per-point mean needs the k smallest distances only: one pass, no fallback
-template <int K>
-__global__ void __launch_bounds__(kQBlock) mean_distance_kernel(
-    GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
-    float* __restrict__ out_mean)
-{
-    float x, y, z;
-    uint32_t row;
-    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
-        return;
-    TopD<K> top;
-    BlockGeom b;
-    CellList cl;
-    knn_search_dist<K>(g, x, y, z, k, eps, min_count, top, b, cl, nullptr);
-    out_mean[row] = mean_distance_d(top, k);
-}
-
-// ---- fused kNN + PCA normal ----------------------------------------------------------------
-template <int K>
 __device__ __noinline__ void normal_exact(const GridView& g, float x, float y, float z,
-                                          uint32_t k, float eps, uint32_t min_count,
+                                          uint32_t k, float eps, int start_level,
                                           float* out_normal_row, float* out_centroid_row)
 {
     TopK<exact_k(K)> ids;
     int const level =
-        knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, min_count, ids, nullptr);
+        knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(g, x, y, z, k, eps, start_level, ids, nullptr);
     float n3[3], c3[3];
     normal_from_ids(g, query_cell(g, x, y, z), level, ids, k, n3, c3, nullptr);
     out_normal_row[0] = n3[0], out_normal_row[1] = n3[1], out_normal_row[2] = n3[2];
@@ -128,42 +121,94 @@ __device__ __noinline__ void normal_exact(const GridView& g, float x, float y, f
         out_centroid_row[0] = c3[0], out_centroid_row[1] = c3[1], out_centroid_row[2] = c3[2];
 }
 
-template <int K>
-__global__ void __launch_bounds__(kQBlock) normals_kernel(
-    GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
-    float* __restrict__ out_centroid, float* __restrict__ out_normal,
-    uint32_t* __restrict__ retry_counter)
+// second pass + output of one query whose first pass is final
+template <int K, int MODE>
+__device__ __forceinline__ void knn_finish(const GridView& g, const CellList& cl,
+                                           const ShortList& sl, float x, float y, float z,
+                                           const TopD<K>& top, uint32_t k, float eps, int level,
+                                           uint32_t row, const KnnOutputs& out)
 {
-    float x, y, z;
-    uint32_t row;
-    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
-        return;
-    float* nrow = out_normal + 3 * (size_t)row;
-    float* crow = out_centroid ? out_centroid + 3 * (size_t)row : nullptr;
-    TopD<K> top;
-    BlockGeom b;
-    CellList cl;
-    knn_search_dist<K>(g, x, y, z, k, eps, min_count, top, b, cl, nullptr);
-    float n3[3], c3[3];
-    if (normal_two_pass<K>(g, cl, x, y, z, top, k, eps, n3, c3, nullptr))
+    if (MODE == MODE_MEAN)
     {
-        nrow[0] = n3[0], nrow[1] = n3[1], nrow[2] = n3[2];
-        if (crow)
-            crow[0] = c3[0], crow[1] = c3[1], crow[2] = c3[2];
+        out.mean[row] = mean_distance_d(top, k);
+    }
+    else if (MODE == MODE_KNN)
+    {
+        uint32_t* idx_row = out.idx + (size_t)row * k;
+        float* d2_row     = out.d2 ? out.d2 + (size_t)row * k : nullptr;
+        uint32_t* cnt     = out.count ? out.count + row : nullptr;
+        if (!knn_two_pass_emit<K>(g, cl, sl, x, y, z, top, k, eps, idx_row, d2_row, cnt))
+        {
+            knn_exact_row<K>(g, x, y, z, k, eps, level, idx_row, d2_row, cnt);
+            if (out.exact_counter)
+                atomicAdd(out.exact_counter, 1u);
+        }
     }
     else
     {
-        // which of the equidistant points is a neighbour is decided by the original index
-        normal_exact<K>(g, x, y, z, k, eps, min_count, nrow, crow);
-        if (retry_counter)
-            atomicAdd(retry_counter, 1u);
+        float* nrow = out.normal + 3 * (size_t)row;
+        float* crow = out.centroid ? out.centroid + 3 * (size_t)row : nullptr;
+        float n3[3], c3[3];
+        if (normal_two_pass<K>(g, cl, sl, x, y, z, top, k, eps, n3, c3, nullptr))
+        {
+            nrow[0] = n3[0], nrow[1] = n3[1], nrow[2] = n3[2];
+            if (crow)
+                crow[0] = c3[0], crow[1] = c3[1], crow[2] = c3[2];
+        }
+        else
+        {
+            // which of the equidistant points is a neighbour is decided by the original index
+            normal_exact<K>(g, x, y, z, k, eps, level, nrow, crow);
+            if (out.exact_counter)
+                atomicAdd(out.exact_counter, 1u);
+        }
+    }
+}
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kQBlock, min_blocks_for(K)) knn_main_kernel(GridView g, QueryBatch qb, uint32_t k,
+                                                           float eps, int level, KnnOutputs out)
+{
+    uint32_t const t = blockIdx.x * kQBlock + threadIdx.x;
+    float x, y, z;
+    uint32_t row;
+    if (!fetch_query(g, qb, t, x, y, z, row))
+        return;
+    TopD<K> top;
+    BlockGeom b;
+    CellList cl;
+    ShortList sl;
+    QueryCell const qc = query_cell(g, x, y, z);
+    if (knn_attempt_dist<K>(g, qc, level, x, y, z, k, eps, top, b, cl, sl, nullptr))
+        knn_finish<K, MODE>(g, cl, sl, x, y, z, top, k, eps, level, row, out);
+    else
+        out.retry_items[atomicAdd(out.retry_count, 1u)] = t;
+}
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kQBlock) knn_retry_kernel(GridView g, QueryBatch qb, uint32_t k,
+                                                            float eps, int level, KnnOutputs out)
+{
+    uint32_t const n_retry = *out.retry_count;
+    for (uint32_t i = blockIdx.x * kQBlock + threadIdx.x; i < n_retry; i += gridDim.x * kQBlock)
+    {
+        float x, y, z;
+        uint32_t row;
+        fetch_query(g, qb, out.retry_items[i], x, y, z, row);
+        TopD<K> top;
+        BlockGeom b;
+        CellList cl;
+        ShortList sl;
+        int const found = knn_search_dist<K>(g, x, y, z, k, eps, level > 0 ? level - 1 : 0, top,
+                                             b, cl, sl, nullptr);
+        knn_finish<K, MODE>(g, cl, sl, x, y, z, top, k, eps, found, row, out);
     }
 }
 
 // ---- instrumentation: what the search does per query ---------------------------------------
 template <int K>
 __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
-    GridView g, QueryBatch qb, uint32_t k, float eps, uint32_t min_count,
+    GridView g, QueryBatch qb, uint32_t k, float eps, int level,
     unsigned long long* __restrict__ stats4)
 {
     float x, y, z;
@@ -175,10 +220,12 @@ __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
         TopD<K> top;
         BlockGeom b;
         CellList cl;
-        knn_search_dist<K>(g, x, y, z, k, eps, min_count, top, b, cl, &st);
+        ShortList sl;
+        knn_search_dist<K>(g, x, y, z, k, eps, level, top, b, cl, sl, &st);
     }
+    uint32_t const warp_max = __reduce_max_sync(0xFFFFFFFFu, st.candidates);
     unsigned long long v[4] = {st.candidates, st.lookups, st.attempts,
-                               (unsigned long long)(st.attempts > 1)};
+                               (threadIdx.x & 31) == 0 ? warp_max * 32ull : 0ull};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
@@ -416,12 +463,6 @@ __global__ void mean_final_kernel(const double* partial, const uint32_t* partial
     *out_sum = s, *out_valid = c;
 }
 
-uint32_t min_count_for(uint32_t k)
-{
-    float const t = tuning().level_factor * (float)k;
-    return (uint32_t)std::max(1.f, std::ceil(t));
-}
-
 } // namespace
 
 // register-list sizes that are compiled; a query with k neighbours runs with the smallest K >= k
@@ -451,18 +492,55 @@ static int list_size_for(uint32_t k)
     default: fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kMaxK);        \
     }
 
+// Main level of a kNN-shaped call: the finest stored level whose mean cell occupancy is at
+// least level_factor * k (its 3x3x3 block then holds a few times k points and succeeds for
+// nearly every query of a uniformly dense region).
+int main_level_for(const pcpx_index& ix, uint32_t k)
+{
+    double const want = std::max(1.0, (double)tuning().level_factor * (double)k);
+    int level         = 0;
+    for (int l = 0; l <= ix.grid.lfine; ++l)
+        if (ix.cells_per_level[l] > 0 &&
+            (double)ix.n_indexed / (double)ix.cells_per_level[l] >= want)
+            level = l;
+    return level;
+}
+
+template <int MODE>
+static void launch_knn_shaped(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
+                              KnnOutputs out, uint32_t* exact_counter, uint32_t* launches)
+{
+    if (k == 0 || k > kMaxK)
+        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
+    uint32_t const kr = (uint32_t)list_size_for(k);
+    int const level   = main_level_for(ix, k);
+    DevBuf<uint32_t> retry_items(qb.nq), retry_count(1);
+    PCPX_CUDA(cudaMemsetAsync(retry_count.get(), 0, 4, ix.stream));
+    out.exact_counter = exact_counter;
+    out.retry_items   = retry_items.get();
+    out.retry_count   = retry_count.get();
+    dim3 const grid(grid_for(qb.nq, kQBlock));
+    dim3 const retry_grid(std::min<uint32_t>(grid.x, 148u * 16u));
+    PCPX_DISPATCH_K(kr, (knn_main_kernel<KK, MODE><<<grid, kQBlock, 0, ix.stream>>>(
+                            ix.grid, qb, k, eps, level, out)));
+    PCPX_CHECK_LAUNCH();
+    PCPX_DISPATCH_K(kr, (knn_retry_kernel<KK, MODE><<<retry_grid, kQBlock, 0, ix.stream>>>(
+                            ix.grid, qb, k, eps, level, out)));
+    PCPX_CHECK_LAUNCH();
+    if (launches)
+        *launches += 2;
+    // the queue is read by the retry kernel: keep it until the stream is idle
+    PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+}
+
 void launch_knn(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps, uint32_t* idx,
-                float* d2, uint32_t* count, uint32_t* retry_counter)
+                float* d2, uint32_t* count, uint32_t* exact_counter)
 {
     if (qb.nq == 0 || k == 0)
         return;
-    if (k > kMaxK)
-        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kMaxK);
-    uint32_t const kr = (uint32_t)list_size_for(k), mc = min_count_for(k);
-    dim3 const grid(grid_for(qb.nq, kQBlock));
-    PCPX_DISPATCH_K(kr, (knn_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, mc, idx, d2, count, retry_counter)));
-    PCPX_CHECK_LAUNCH();
+    KnnOutputs out{};
+    out.idx = idx, out.d2 = d2, out.count = count;
+    launch_knn_shaped<MODE_KNN>(ix, qb, k, eps, out, exact_counter, nullptr);
 }
 
 void launch_mean_distance(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
@@ -470,27 +548,19 @@ void launch_mean_distance(const pcpx_index& ix, const QueryBatch& qb, uint32_t k
 {
     if (qb.nq == 0)
         return;
-    if (k == 0 || k > kMaxK)
-        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
-    uint32_t const kr = (uint32_t)list_size_for(k), mc = min_count_for(k);
-    dim3 const grid(grid_for(qb.nq, kQBlock));
-    PCPX_DISPATCH_K(kr, (mean_distance_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, mc, means)));
-    PCPX_CHECK_LAUNCH();
+    KnnOutputs out{};
+    out.mean = means;
+    launch_knn_shaped<MODE_MEAN>(ix, qb, k, eps, out, nullptr, nullptr);
 }
 
 void launch_normals(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
-                    float* centroids, float* normals, uint32_t* tie_counter)
+                    float* centroids, float* normals, uint32_t* exact_counter)
 {
     if (qb.nq == 0)
         return;
-    if (k == 0 || k > kMaxK)
-        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
-    uint32_t const kr = (uint32_t)list_size_for(k), mc = min_count_for(k);
-    dim3 const grid(grid_for(qb.nq, kQBlock));
-    PCPX_DISPATCH_K(kr, (normals_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, mc, centroids, normals, tie_counter)));
-    PCPX_CHECK_LAUNCH();
+    KnnOutputs out{};
+    out.normal = normals, out.centroid = centroids;
+    launch_knn_shaped<MODE_NORMALS>(ix, qb, k, eps, out, exact_counter, nullptr);
 }
 
 void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long long* stats4)
@@ -500,10 +570,11 @@ void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long
     QueryBatch qb{nullptr, 3u, nullptr, (uint32_t)ix.n_input};
     if (qb.nq == 0)
         return;
-    uint32_t const kr = (uint32_t)list_size_for(k), mc = min_count_for(k);
+    uint32_t const kr = (uint32_t)list_size_for(k);
+    int const level   = main_level_for(ix, k);
     dim3 const grid(grid_for(qb.nq, kQBlock));
     PCPX_DISPATCH_K(kr, (knn_stats_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, mc, stats4)));
+                            ix.grid, qb, k, eps, level, stats4)));
     PCPX_CHECK_LAUNCH();
 }
 

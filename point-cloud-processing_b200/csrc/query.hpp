@@ -17,7 +17,7 @@ struct QueryBatch
 
 struct Tuning
 {
-    float level_factor = 0.5f; // start level: finest whose own cell holds >= level_factor * k points
+    float level_factor = 0.35f; // main level: finest whose mean cell occupancy >= level_factor * k
     int block_threads  = 128;
 };
 Tuning& tuning();
@@ -25,9 +25,9 @@ Tuning& tuning();
 constexpr uint32_t kMaxK = 32; // register-resident list; larger k is not supported yet
 
 void launch_knn(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps, uint32_t* idx,
-                float* d2, uint32_t* count, uint32_t* retry_counter);
+                float* d2, uint32_t* count, uint32_t* exact_counter);
 void launch_normals(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
-                    float* centroids, float* normals, uint32_t* tie_counter);
+                    float* centroids, float* normals, uint32_t* exact_counter);
 void launch_mean_distance(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
                           float* means);
 void launch_radius_count(const pcpx_index& ix, const QueryBatch& qb, const float* radii, float r,

@@ -23,7 +23,20 @@ struct EmuIndex
     std::vector<float4> pts;
     std::vector<HashSlot> table;
     uint64_t n_input = 0;
+    uint64_t cells_per_level[kMaxLevel + 2] = {};
 };
+
+// mirrors main_level_for() in query.cu
+static int main_level_for(const EmuIndex* ix, uint32_t k, double level_factor)
+{
+    double const want = std::max(1.0, level_factor * (double)k);
+    int level         = 0;
+    for (int l = 0; l <= ix->g.lfine; ++l)
+        if (ix->cells_per_level[l] > 0 &&
+            (double)ix->g.n / (double)ix->cells_per_level[l] >= want)
+            level = l;
+    return level;
+}
 
 static uint32_t host_claim(std::vector<HashSlot>& t, uint64_t key)
 {
@@ -134,6 +147,7 @@ void* emu_index_create(const float* xyz, size_t n, int use_box, const float* box
         if (l > 0 && (double)g.n / (double)std::max<uint64_t>(cells, 1) < min_occ)
             break;
         g.lfine = l;
+        ix->cells_per_level[l] = cells;
         total += cells;
     }
     size_t slots = std::max<uint64_t>(64, (uint64_t)((double)total * 2.5) + 1);
@@ -201,7 +215,7 @@ constexpr int exact_k(int K) { return (K + 3) / 4 * 4; }
 // product path), 1 = force the exact 64-bit search for every query
 template <int K>
 static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
-                     uint32_t min_count, int mode, uint32_t* idx, float* d2, uint32_t* cnt,
+                     int level, int mode, uint32_t* idx, float* d2, uint32_t* cnt,
                      uint64_t* st4, uint32_t* per_query_cand)
 {
     for (size_t i = 0; i < nq; ++i)
@@ -216,8 +230,13 @@ static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float 
             TopD<K> top;
             BlockGeom b;
             CellList cl;
-            knn_search_dist<K>(ix->g, x, y, z, k, eps, min_count, top, b, cl, &st);
-            done = knn_two_pass_emit<K>(ix->g, cl, x, y, z, top, k, eps, idx + row * k,
+            ShortList sl;
+            // main pass: one attempt at the main level; otherwise the retry pass walks coarser
+            if (!knn_attempt_dist<K>(ix->g, query_cell(ix->g, x, y, z), level, x, y, z, k, eps,
+                                     top, b, cl, sl, &st))
+                knn_search_dist<K>(ix->g, x, y, z, k, eps, level > 0 ? level - 1 : 0, top, b, cl,
+                                   sl, &st);
+            done = knn_two_pass_emit<K>(ix->g, cl, sl, x, y, z, top, k, eps, idx + row * k,
                                         d2 ? d2 + row * k : nullptr, cnt ? cnt + row : nullptr);
             if (!done && st4)
                 st4[3] += 1; // retries
@@ -225,7 +244,7 @@ static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float 
         if (!done)
         {
             TopK<exact_k(K)> top;
-            knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, min_count, top,
+            knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, level, top,
                                                        mode == 1 ? &st : nullptr);
             uint32_t n = 0;
             for (uint32_t j = 0; j < k; ++j)
@@ -270,9 +289,9 @@ extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double ep
     EmuIndex* ix = static_cast<EmuIndex*>(h);
     if (k == 0 || nq == 0)
         return 0;
-    uint32_t mc = (uint32_t)std::max(1.0, std::ceil(level_factor * k));
+    int const level = main_level_for(ix, k, level_factor);
     EMU_DISPATCH(list_size_for(k),
-                 (knn_impl<KK>(ix, q, nq, k, (float)eps, mc, mode, idx, d2, cnt, st4,
+                 (knn_impl<KK>(ix, q, nq, k, (float)eps, level, mode, idx, d2, cnt, st4,
                                per_query_cand)));
     return 0;
 }
@@ -280,7 +299,7 @@ extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double ep
 // mirrors normals_kernel / normal_exact and mean_distance_kernel
 template <int K>
 static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
-                         uint32_t mc, int mode, float* ctr, float* nrm, float* means,
+                         int level, int mode, float* ctr, float* nrm, float* means,
                          uint32_t* ties)
 {
     for (size_t i = 0; i < nq; ++i)
@@ -292,12 +311,17 @@ static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, fl
         TopD<K> top;
         BlockGeom b;
         CellList cl;
-        knn_search_dist<K>(ix->g, x, y, z, k, eps, mc, top, b, cl, nullptr);
-        bool ok = mode == 0 && normal_two_pass<K>(ix->g, cl, x, y, z, top, k, eps, n3, c3, nullptr);
+        ShortList sl;
+        if (!knn_attempt_dist<K>(ix->g, query_cell(ix->g, x, y, z), level, x, y, z, k, eps, top, b,
+                                 cl, sl, nullptr))
+            knn_search_dist<K>(ix->g, x, y, z, k, eps, level > 0 ? level - 1 : 0, top, b, cl, sl,
+                               nullptr);
+        bool ok =
+            mode == 0 && normal_two_pass<K>(ix->g, cl, sl, x, y, z, top, k, eps, n3, c3, nullptr);
         if (!ok)
         {
             TopK<exact_k(K)> ids;
-            int lv = knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, mc, ids,
+            int lv = knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, level, ids,
                                                                 nullptr);
             normal_from_ids(ix->g, query_cell(ix->g, x, y, z), lv, ids, k, n3, c3, nullptr);
             if (ties)
@@ -321,9 +345,9 @@ extern "C" int emu_normals(void* h, const float* q, size_t nq, uint32_t k, doubl
     EmuIndex* ix = static_cast<EmuIndex*>(h);
     if (k == 0 || nq == 0)
         return 0;
-    uint32_t mc = (uint32_t)std::max(1.0, std::ceil(level_factor * k));
+    int const level = main_level_for(ix, k, level_factor);
     EMU_DISPATCH(list_size_for(k),
-                 (normals_impl<KK>(ix, q, nq, k, (float)eps, mc, mode, ctr, nrm, means, ties)));
+                 (normals_impl<KK>(ix, q, nq, k, (float)eps, level, mode, ctr, nrm, means, ties)));
     return 0;
 }
 
