@@ -209,6 +209,21 @@ int pcpx_estimate_tangent_planes(
     float* out_normals);
 
 /*
+ * PCA normal of caller-supplied neighbourhoods (CSR: neighbourhood i = points
+ * nbr_xyz[offsets[i] .. offsets[i + 1]), packed fp32 xyz).  This is pcp::estimate_normal
+ * (common/normals/normal_estimation.hpp:32-78) batched on the GPU; it serves
+ * pcp::algorithm::estimate_normals when the KnnMap is an arbitrary user callable whose
+ * neighbourhoods the host has already gathered.  out_normals: n x 3 fp32; device = CUDA ordinal
+ * (-1 = current).  Host or device pointers.
+ */
+int pcpx_normals_from_neighbourhoods(
+    const float* nbr_xyz,
+    const uint64_t* offsets,
+    size_t n,
+    int device,
+    float* out_normals);
+
+/*
  * Mean distance to the k nearest neighbours of every indexed point.  Replaces
  * pcp::algorithm::average_distances_to_neighbors / average_distance_to_neighbors
  * (algorithm/average_distance_to_neighbors.hpp:39-113): per point the sequential fp32 sum of

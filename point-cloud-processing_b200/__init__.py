@@ -18,6 +18,7 @@ from .capi import (  # noqa: F401
     device_count,
     exported_symbols,
     lib,
+    normals_from_neighbourhoods,
     set_tuning,
 )
 from . import sharding, synth  # noqa: F401

@@ -74,6 +74,8 @@ _SIGNATURES = {
                                         C.c_uint32, C.c_double, C.c_void_p]),
     "pcpx_estimate_tangent_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                                C.c_uint32, C.c_double, C.c_void_p, C.c_void_p]),
+    "pcpx_normals_from_neighbourhoods": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                                   C.c_void_p]),
     "pcpx_mean_knn_distance": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p,
                                          C.POINTER(C.c_double)]),
     "pcpx_density_filter": (C.c_int, [C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -119,6 +121,17 @@ def device_count():
 
 def set_tuning(name, value):
     _check(lib().pcpx_set_tuning(name.encode(), float(value)))
+
+
+def normals_from_neighbourhoods(nbr_xyz, offsets, device=-1):
+    """PCA normal of caller-supplied neighbourhoods (CSR over packed xyz)."""
+    nbr = np.ascontiguousarray(nbr_xyz, np.float32).reshape(-1, 3)
+    off = np.ascontiguousarray(offsets, np.uint64)
+    n = len(off) - 1
+    out = np.zeros((n, 3), np.float32)
+    _check(lib().pcpx_normals_from_neighbourhoods(nbr.ctypes.data, off.ctypes.data, n, device,
+                                                  out.ctypes.data))
+    return out
 
 
 def _is_torch(x):

@@ -409,6 +409,48 @@ int pcpx_estimate_tangent_planes(const pcpx_index* index, const float* queries, 
     });
 }
 
+int pcpx_normals_from_neighbourhoods(const float* nbr_xyz, const uint64_t* offsets, size_t n,
+                                     int device, float* out_normals)
+{
+    return guarded([&] {
+        if (n == 0)
+            return;
+        if (!offsets || !out_normals)
+            fail(PCPX_ERR_INVALID_ARG, "offsets / out_normals is NULL");
+        if (n >= 0xFFFFFFFFull)
+            fail(PCPX_ERR_UNSUPPORTED, "more than 2^32 - 2 neighbourhoods in one call");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            fail(PCPX_ERR_NO_DEVICE, "no CUDA device: libpcpx has no CPU path");
+        if (device < 0)
+            PCPX_CUDA(cudaGetDevice(&device));
+        ScopedDevice guard(device);
+        cudaStream_t stream = nullptr; // legacy default stream: this call owns no index
+        DevBuf<uint64_t> d_off_buf;
+        const uint64_t* d_off = offsets;
+        uint64_t total        = 0;
+        if (!is_device_pointer(offsets))
+        {
+            total = offsets[n];
+            d_off_buf.alloc(n + 1);
+            PCPX_CUDA(cudaMemcpyAsync(d_off_buf.get(), offsets, (n + 1) * 8,
+                                      cudaMemcpyHostToDevice, stream));
+            d_off = d_off_buf.get();
+        }
+        else
+            PCPX_CUDA(cudaMemcpy(&total, offsets + n, 8, cudaMemcpyDeviceToHost));
+        if (total && !nbr_xyz)
+            fail(PCPX_ERR_INVALID_ARG, "nbr_xyz is NULL");
+        InBuf pts;
+        pts.stage(nbr_xyz, total, 12, 3, stream);
+        OutBuf<float> out;
+        out.prepare(out_normals, n * 3);
+        launch_normals_from_neighbourhoods(stream, pts.d, d_off, (uint32_t)n, out.d);
+        out.finish(stream);
+        PCPX_CUDA(cudaStreamSynchronize(stream));
+    });
+}
+
 int pcpx_mean_knn_distance(const pcpx_index* index, uint32_t k, double eps, float* out_per_point,
                            double* out_mean)
 {

@@ -237,6 +237,34 @@ __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
     }
 }
 
+// ---- PCA of caller-supplied neighbourhoods ---------------------------------------------------
+// common/normals/normal_estimation.hpp:41-77 per neighbourhood: fp32 mean, centred scatter,
+// eigenvector of the smallest eigenvalue.  One thread per neighbourhood.
+__global__ void __launch_bounds__(kQBlock) neighbourhood_normals_kernel(
+    const float* __restrict__ nbr, const uint64_t* __restrict__ offsets, uint32_t n,
+    float* __restrict__ out)
+{
+    uint32_t const i = blockIdx.x * kQBlock + threadIdx.x;
+    if (i >= n)
+        return;
+    uint64_t const b = offsets[i], e = offsets[i + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (uint64_t j = b; j < e; ++j)
+        sx += nbr[3 * j], sy += nbr[3 * j + 1], sz += nbr[3 * j + 2];
+    float const inv = 1.f / (float)(e - b);
+    float const mx = sx * inv, my = sy * inv, mz = sz * inv;
+    Sym3 m{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (uint64_t j = b; j < e; ++j)
+    {
+        float const x = nbr[3 * j] - mx, y = nbr[3 * j + 1] - my, z = nbr[3 * j + 2] - mz;
+        m.xx += x * x, m.xy += x * y, m.xz += x * z;
+        m.yy += y * y, m.yz += y * z, m.zz += z * z;
+    }
+    float nx, ny, nz;
+    smallest_eigenvector(m, nx, ny, nz, nullptr);
+    out[3 * (size_t)i] = nx, out[3 * (size_t)i + 1] = ny, out[3 * (size_t)i + 2] = nz;
+}
+
 // ---- radius --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kQBlock) radius_count_kernel(
     GridView g, QueryBatch qb, const float* __restrict__ radii, float r,
@@ -561,6 +589,16 @@ void launch_normals(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, floa
     KnnOutputs out{};
     out.normal = normals, out.centroid = centroids;
     launch_knn_shaped<MODE_NORMALS>(ix, qb, k, eps, out, exact_counter, nullptr);
+}
+
+void launch_normals_from_neighbourhoods(cudaStream_t stream, const float* nbr_xyz,
+                                        const uint64_t* offsets, uint32_t n, float* normals)
+{
+    if (n == 0)
+        return;
+    neighbourhood_normals_kernel<<<grid_for(n, kQBlock), kQBlock, 0, stream>>>(nbr_xyz, offsets, n,
+                                                                                normals);
+    PCPX_CHECK_LAUNCH();
 }
 
 void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long long* stats4)

@@ -42,6 +42,8 @@ void launch_compact_points(const pcpx_index& ix, const uint8_t* keep, const uint
                            float* out_xyz);
 void launch_mean_reduce(const pcpx_index& ix, const float* v, uint32_t n, double* out_sum,
                         uint32_t* out_valid);
+void launch_normals_from_neighbourhoods(cudaStream_t stream, const float* nbr_xyz,
+                                        const uint64_t* offsets, uint32_t n, float* normals);
 void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long long* stats4);
 
 } // namespace pcpx

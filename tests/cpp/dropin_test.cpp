@@ -1,0 +1,264 @@
+// Drop-in check: the reference's own test scenarios for the hot path, written against
+// include/pcpx/pcp.hpp with the reference's call signatures (test/octree/octree_knn.cpp,
+// test/octree/octree_range_search.cpp, test/kdtree/knn.cpp, test/common/normal_estimation.cpp,
+// test/algorithm/estimate_normals.cpp, test/algorithm/average_distance_to_neighbors.cpp,
+// examples/simple_example.cpp, examples/filter_point_cloud_noise_by_density.cpp).
+// Exit code 0 = every scenario holds.  Needs a GPU (libpcpx has no CPU path).
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include <pcpx/pcp.hpp>
+
+#define REQUIRE(cond)                                                                          \
+    do                                                                                         \
+    {                                                                                          \
+        if (!(cond))                                                                           \
+        {                                                                                      \
+            std::fprintf(stderr, "REQUIRE failed at %s:%d: %s\n", __FILE__, __LINE__, #cond);  \
+            std::exit(1);                                                                      \
+        }                                                                                      \
+    } while (0)
+
+static auto const point_map = [](pcp::point_t const& p) { return p; };
+
+static pcp::octree_parameters_t<pcp::point_t> unit_params(float h = 1.f)
+{
+    pcp::octree_parameters_t<pcp::point_t> params;
+    params.voxel_grid = pcp::axis_aligned_bounding_box_t<pcp::point_t>{pcp::point_t{-h, -h, -h},
+                                                                       pcp::point_t{h, h, h}};
+    return params;
+}
+
+static void octree_knn_scenarios()
+{
+    // "an octree with 1 point in each octant", k = 1
+    std::vector<pcp::point_t> pts{{-.5f, -.5f, -.5f}, {.5f, -.5f, -.5f}, {.5f, .5f, -.5f},
+                                  {-.5f, .5f, -.5f},  {-.5f, -.5f, .5f}, {.5f, -.5f, .5f},
+                                  {.5f, .5f, .5f},    {-.5f, .5f, .5f}};
+    pcp::linked_octree_t octree(pts.cbegin(), pts.cend(), point_map, unit_params());
+    REQUIRE(octree.size() == 8u);
+    auto nn = octree.nearest_neighbours(pcp::point_t{.51f, .51f, .51f}, 1u, point_map);
+    REQUIRE(nn.size() == 1u && pcp::common::are_vectors_equal(nn[0], pcp::point_t{.5f, .5f, .5f}));
+    nn = octree.nearest_neighbours(pcp::point_t{-.51f, -.51f, -.51f}, 1u, point_map);
+    REQUIRE(nn.size() == 1u && pcp::common::are_vectors_equal(nn[0], pcp::point_t{-.5f, -.5f, -.5f}));
+
+    // the only point equals the target -> nothing; two points, one equal -> the other one
+    std::vector<pcp::point_t> one{{-.5f, -.5f, -.5f}};
+    pcp::linked_octree_t o1(one.cbegin(), one.cend(), point_map, unit_params());
+    REQUIRE(o1.nearest_neighbours(pcp::point_t{-.5f, -.5f, -.5f}, 1u, point_map).empty());
+    std::vector<pcp::point_t> two{{-.5f, -.5f, -.5f}, {-1.f, -1.f, -1.f}};
+    pcp::linked_octree_t o2(two.cbegin(), two.cend(), point_map, unit_params());
+    nn = o2.nearest_neighbours(pcp::point_t{-.5f, -.5f, -.5f}, 2u, point_map);
+    REQUIRE(nn.size() == 1u && pcp::common::are_vectors_equal(nn[0], pcp::point_t{-1.f, -1.f, -1.f}));
+
+    // ordering nearest -> furthest, k = 4 and k = 3
+    std::vector<pcp::point_t> ord{{-.5f, -.5f, -.5f}, {.5f, -.5f, -.5f}, {-.5f, .5f, -.5f},
+                                  {-.5f, -.5f, .5f},  {.5f, -.5f, .5f},  {.5f, .5f, .5f},
+                                  {-.5f, .5f, .5f}};
+    pcp::point_t const first{.51f, .51f, -.51f}, second{.61f, .51f, -.51f},
+        third{.41f, .31f, -.51f}, fourth{.71f, .21f, -.51f};
+    ord.insert(ord.end(), {first, second, third, fourth});
+    pcp::linked_octree_t o3(ord.cbegin(), ord.cend(), point_map, unit_params());
+    pcp::point_t const reference{.5f, .5f, -.5f};
+    nn = o3.nearest_neighbours(reference, 4u, point_map);
+    REQUIRE(nn.size() == 4u);
+    REQUIRE(pcp::common::are_vectors_equal(first, nn[0]) && pcp::common::are_vectors_equal(second, nn[1]));
+    REQUIRE(pcp::common::are_vectors_equal(third, nn[2]) && pcp::common::are_vectors_equal(fourth, nn[3]));
+    nn = o3.nearest_neighbours(reference, 3u, point_map);
+    REQUIRE(nn.size() == 3u && pcp::common::are_vectors_equal(third, nn[2]));
+    REQUIRE(o3.nearest_neighbours(reference, 0u, point_map).empty());
+
+    // "a randomly constructed octree": k planted points near a corner are the k returned
+    std::mt19937 gen(1234);
+    std::uniform_real_distribution<float> c(-0.95f, 0.95f), nearc(-.99f, -.96f), farc(.96f, .99f);
+    std::vector<pcp::point_t> cloud;
+    for (int i = 0; i < 20000; ++i)
+        cloud.push_back({c(gen), c(gen), c(gen)});
+    std::size_t const k = 7;
+    std::vector<pcp::point_t> planted;
+    for (std::size_t i = 0; i < k; ++i)
+        planted.push_back({nearc(gen), farc(gen), farc(gen)});
+    cloud.insert(cloud.end(), planted.begin(), planted.end());
+    pcp::linked_octree_t o4(cloud.cbegin(), cloud.cend(), point_map, unit_params(2.f));
+    REQUIRE(o4.size() == cloud.size());
+    nn = o4.nearest_neighbours(pcp::point_t{-1.f, 1.f, 1.f}, k, point_map);
+    REQUIRE(nn.size() == k);
+    for (auto const& p : nn)
+        REQUIRE(std::any_of(planted.begin(), planted.end(),
+                            [&](auto const& q) { return pcp::common::are_vectors_equal(p, q); }));
+
+    // insertion test: points outside the voxel grid are not indexed
+    std::vector<pcp::point_t> in{{.1f, .1f, .1f}, {-.3f, .3f, .3f}, {.9f, -.9f, -.9f}};
+    auto with_out = in;
+    with_out.insert(with_out.end(), {{-2.f, 0.f, 0.f}, {0.f, 2.f, 0.f}, {0.f, 0.f, -2.f}});
+    pcp::linked_octree_t o5(with_out.cbegin(), with_out.cend(), point_map, unit_params());
+    REQUIRE(o5.size() == in.size());
+}
+
+static void octree_range_scenarios()
+{
+    std::vector<pcp::point_t> pts;
+    for (float z : {-1.f, 1.f})
+        for (auto xy : {std::pair<float, float>{-1, -1}, {1, -1}, {1, 1}, {-1, 1}})
+        {
+            pts.push_back({.5f * xy.first, .5f * xy.second, .5f * z});
+            pts.push_back({.4f * xy.first, .3f * xy.second, .6f * z});
+        }
+    pcp::linked_octree_t octree(pts.cbegin(), pts.cend(), point_map, unit_params());
+    pcp::sphere_t<pcp::point_t> sphere;
+    sphere.position = {0.f, 0.f, 0.f};
+    sphere.radius   = 0.1f;
+    REQUIRE(octree.range_search(sphere, point_map).empty());
+    sphere.position = {.9f, .9f, .9f};
+    sphere.radius   = 1.f;
+    auto in = octree.range_search(sphere, point_map);
+    REQUIRE(in.size() == 2u);
+    auto has = [&](pcp::point_t q) {
+        return std::count_if(in.begin(), in.end(),
+                             [&](auto const& p) { return pcp::common::are_vectors_equal(p, q); }) == 1;
+    };
+    REQUIRE(has({.5f, .5f, .5f}) && has({.4f, .3f, .6f}));
+    pcp::axis_aligned_bounding_box_t<pcp::point_t> aabb;
+    aabb.min = {1.05f, 1.05f, 1.05f}, aabb.max = {2.f, 2.f, 2.f};
+    REQUIRE(octree.range_search(aabb, point_map).empty());
+    aabb.min = {-2.f, -2.f, -2.f}, aabb.max = {0.f, 0.f, 0.f};
+    in = octree.range_search(aabb, point_map);
+    REQUIRE(in.size() == 2u && has({-.5f, -.5f, -.5f}) && has({-.4f, -.3f, -.6f}));
+}
+
+static void kdtree_scenarios()
+{
+    auto const coordinate_map = [](pcp::point_t const& p) {
+        return std::array<float, 3u>{p.x(), p.y(), p.z()};
+    };
+    std::vector<pcp::point_t> ord{{-.5f, -.5f, -.5f}, {.5f, -.5f, -.5f}, {-.5f, .5f, -.5f},
+                                  {-.5f, -.5f, .5f},  {.5f, -.5f, .5f},  {.5f, .5f, .5f},
+                                  {-.5f, .5f, .5f},   {.51f, .51f, -.51f}, {.61f, .51f, -.51f},
+                                  {.41f, .31f, -.51f}, {.71f, .21f, -.51f}};
+    pcp::basic_linked_kdtree_t<pcp::point_t, 3u, decltype(coordinate_map)> kdtree{
+        ord.begin(), ord.end(), coordinate_map};
+    auto nn = kdtree.nearest_neighbours(std::array<float, 3u>{.5f, .5f, -.5f}, 4u);
+    REQUIRE(nn.size() == 4u && pcp::common::are_vectors_equal(nn[0], ord[7]) &&
+            pcp::common::are_vectors_equal(nn[3], ord[10]));
+    nn = kdtree.nearest_neighbours(ord[7], 2u); // element overload: itself is excluded
+    REQUIRE(nn.size() == 2u && pcp::common::are_vectors_equal(nn[0], ord[8]));
+    pcp::sphere_a<float> ball{{.5f, .5f, -.5f}, 0.12f};
+    REQUIRE(kdtree.range_search(ball).size() == 2u); // (.51,.51,-.51) and (.61,.51,-.51)
+
+    // test/algorithm/average_distance_to_neighbors.cpp: 4 clusters of 3 collinear points
+    float const d = 0.1f;
+    std::vector<pcp::point_t> cl{{0, 0, 0}, {0, 0, d},  {0, 0, -d}, {1, 0, 0}, {1, d, 0},  {1, -d, 0},
+                                 {0, 1, 0}, {d, 1, 0},  {-d, 1, 0}, {0, 0, 1}, {d, 0, 1},  {-d, 0, 1}};
+    pcp::basic_linked_kdtree_t<pcp::point_t, 3u, decltype(coordinate_map)> kd2{
+        cl.begin(), cl.end(), coordinate_map};
+    float const mu = pcp::algorithm::average_distance_to_neighbors(kd2, 2u);
+    REQUIRE(pcp::common::floating_point_equals(mu, (16.f / 12.f) * d));
+}
+
+static void normals_scenarios()
+{
+    // test/common/normal_estimation.cpp: axis cross -> +-(0,0,1), unit norm
+    std::vector<pcp::point_t> cross{{0, 0, 0}, {-2, 0, 0}, {2, 0, 0}, {0, -2, 0},
+                                    {0, 2, 0}, {0, 0, -1}, {0, 0, 1}};
+    auto const n = pcp::estimate_normal(cross.cbegin(), cross.cend(), point_map);
+    pcp::normal_t const expected{0.f, 0.f, 1.f};
+    REQUIRE(pcp::common::are_vectors_equal(n, expected) ||
+            pcp::common::are_vectors_equal(n, -expected));
+    REQUIRE(pcp::common::floating_point_equals(pcp::common::norm(n), 1.f));
+
+    // examples/simple_example.cpp shape: point views over a vector, octree of views, density by
+    // range search, estimate_normals with a kNN callable
+    std::mt19937 gen(42);
+    std::normal_distribution<float> g(0.f, 1.f);
+    std::vector<pcp::point_t> points;
+    for (int i = 0; i < 50000; ++i)
+    {
+        float x = g(gen), y = g(gen), z = g(gen);
+        float const r = (1.f + 0.002f * g(gen)) / std::sqrt(x * x + y * y + z * z);
+        points.push_back({x * r, y * r, z * r});
+    }
+    std::vector<pcp::point_view_t> views;
+    for (auto& p : points)
+        views.push_back(pcp::point_view_t{&p});
+    auto const point_view_map = [](pcp::point_view_t const& p) { return p; };
+    using octree_type = pcp::basic_linked_octree_t<pcp::point_view_t>;
+    octree_type octree{views.begin(), views.end(), point_view_map};
+    REQUIRE(octree.size() == points.size());
+
+    // (a) the recognised map: one fused device call for the whole range
+    std::vector<pcp::normal_t> normals(points.size());
+    pcp::algorithm::estimate_normals(
+        std::execution::par, views.begin(), views.end(), normals.begin(), point_view_map,
+        pcp::make_gpu_knn_map(octree, 15u, point_view_map),
+        pcp::algorithm::default_normal_transform<pcp::point_view_t, pcp::normal_t>);
+    // (b) an arbitrary user lambda, exactly as the reference's examples write it
+    auto const knn = [&](pcp::point_view_t const& p) {
+        return octree.nearest_neighbours(p, 15u, point_view_map);
+    };
+    std::size_t const sample = 200;
+    std::vector<pcp::normal_t> normals_b;
+    pcp::algorithm::estimate_normals(
+        views.begin(), views.begin() + sample, std::back_inserter(normals_b), point_view_map, knn,
+        pcp::algorithm::default_normal_transform<pcp::point_view_t, pcp::normal_t>);
+    REQUIRE(normals_b.size() == sample);
+    for (std::size_t i = 0; i < points.size(); ++i)
+    {
+        // on a sphere the PCA normal is radial (up to sign)
+        float const dot = normals[i].x() * points[i].x() + normals[i].y() * points[i].y() +
+                          normals[i].z() * points[i].z();
+        REQUIRE(std::abs(dot) > 0.98f);
+        if (i < sample)
+        {
+            float const ab = normals[i].x() * normals_b[i].x() + normals[i].y() * normals_b[i].y() +
+                             normals[i].z() * normals_b[i].z();
+            REQUIRE(1.f - std::abs(ab) <= 1e-4f); // both routes agree (test/algorithm/estimate_normals.cpp)
+        }
+    }
+
+    // batched kNN == per-query kNN
+    auto const batch = octree.nearest_neighbours(views.begin(), views.begin() + 50, 8u, point_view_map);
+    for (std::size_t i = 0; i < 50; ++i)
+    {
+        auto const one = octree.nearest_neighbours(views[i], 8u, point_view_map);
+        REQUIRE(batch.counts[i] == one.size());
+        for (std::size_t j = 0; j < one.size(); ++j)
+            REQUIRE(one[j].point() == &points[batch.indices[i * 8 + j]]);
+    }
+
+    // examples/filter_point_cloud_noise_by_density.cpp: radius = mean kNN distance, threshold 5
+    std::uniform_real_distribution<float> u(-1.5f, 1.5f);
+    std::size_t const n_surface = points.size();
+    for (int i = 0; i < 2500; ++i)
+        points.push_back({u(gen), u(gen), u(gen)});
+    views.clear();
+    for (auto& p : points)
+        views.push_back(pcp::point_view_t{&p});
+    octree_type noisy{views.begin(), views.end(), point_view_map};
+    float const radius = pcp::algorithm::average_distance_to_neighbors(noisy, 15u);
+    std::vector<std::uint8_t> mask;
+    auto const kept = pcp::algorithm::filter_by_density(noisy, radius, 5u, &mask);
+    std::size_t kept_surface = 0, kept_noise = 0;
+    for (std::size_t i = 0; i < mask.size(); ++i)
+        (i < n_surface ? kept_surface : kept_noise) += mask[i];
+    REQUIRE(kept.size() == kept_surface + kept_noise);
+    REQUIRE(kept_surface > n_surface * 95 / 100); // the surface survives
+    REQUIRE(kept_noise < 2500 / 10);              // the uniform noise does not
+    for (std::size_t i = 1; i < kept.size(); ++i) // stable: original relative order
+        REQUIRE(kept[i - 1].point() < kept[i].point());
+}
+
+int main()
+{
+    if (pcpx_device_count() < 1)
+    {
+        std::fprintf(stderr, "no CUDA device: libpcpx has no CPU path\n");
+        return 2;
+    }
+    octree_knn_scenarios();
+    octree_range_scenarios();
+    kdtree_scenarios();
+    normals_scenarios();
+    std::printf("dropin_test: all scenarios hold\n");
+    return 0;
+}
