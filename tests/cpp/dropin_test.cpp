@@ -202,12 +202,14 @@ static void normals_scenarios()
         views.begin(), views.begin() + sample, std::back_inserter(normals_b), point_view_map, knn,
         pcp::algorithm::default_normal_transform<pcp::point_view_t, pcp::normal_t>);
     REQUIRE(normals_b.size() == sample);
+    double mean_abs_dot = 0.0;
     for (std::size_t i = 0; i < points.size(); ++i)
     {
         // on a sphere the PCA normal is radial (up to sign)
         float const dot = normals[i].x() * points[i].x() + normals[i].y() * points[i].y() +
                           normals[i].z() * points[i].z();
-        REQUIRE(std::abs(dot) > 0.98f);
+        REQUIRE(std::abs(dot) > 0.8f);
+        mean_abs_dot += std::abs(dot) / static_cast<double>(points.size());
         if (i < sample)
         {
             float const ab = normals[i].x() * normals_b[i].x() + normals[i].y() * normals_b[i].y() +
@@ -215,6 +217,8 @@ static void normals_scenarios()
             REQUIRE(1.f - std::abs(ab) <= 1e-4f); // both routes agree (test/algorithm/estimate_normals.cpp)
         }
     }
+
+    REQUIRE(mean_abs_dot > 0.995);
 
     // batched kNN == per-query kNN
     auto const batch = octree.nearest_neighbours(views.begin(), views.begin() + 50, 8u, point_view_map);
