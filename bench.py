@@ -289,7 +289,7 @@ def run_ours(args):
     achieved = ALGORITHMIC_BYTES_PER_NORMAL * n_local / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": recorded_traffic(),
-                "kernel": "normals_kernel<15>", "kernel_ms": kernel_ms,
+                "kernel": "knn_main_kernel<15, MODE_NORMALS>", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_NORMAL * n_local,
                 "peak_source": peak_src,
                 "note": "gather-model bytes (12 + 12k + 12 per normal); the kernel is "

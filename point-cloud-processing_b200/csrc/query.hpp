@@ -17,7 +17,7 @@ struct QueryBatch
 
 struct Tuning
 {
-    float level_factor = 0.35f; // main level: finest whose mean cell occupancy >= level_factor * k
+    float level_factor = 0.3f;  // main level: finest whose mean cell occupancy >= level_factor * k
     int block_threads  = 128;
 };
 Tuning& tuning();

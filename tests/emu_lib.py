@@ -93,7 +93,7 @@ class EmuIndex:
         self.L.emu_index_info(self.h, C.byref(n), C.byref(lcap), C.byref(lfine), C.byref(slots))
         return dict(n_indexed=n.value, lcap=lcap.value, lfine=lfine.value, slots=slots.value)
 
-    def knn(self, queries, k, eps=1e-5, level_factor=0.35, exact_only=False):
+    def knn(self, queries, k, eps=1e-5, level_factor=0.3, exact_only=False):
         """exact_only=False mirrors the product kernel (two-pass + exact fallback); True forces
         the 64-bit (distance, index) search for every query.  st = candidates, lookups,
         attempts, fallbacks."""
@@ -111,7 +111,7 @@ class EmuIndex:
         assert rc == 0
         return idx, d2, cnt, st
 
-    def normals(self, queries, k, eps=1e-5, level_factor=0.35, want_means=False,
+    def normals(self, queries, k, eps=1e-5, level_factor=0.3, want_means=False,
                 exact_only=False):
         q = _f32(queries)
         nq = self.n if q is None else len(q)
