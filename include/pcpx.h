@@ -124,6 +124,8 @@ int pcpx_index_info_get(const pcpx_index* index, pcpx_index_info* out_info);
  *     (common/vector3d_queries.hpp:31-35,48-64 applied at octree/linked_octree_node.hpp:540),
  *     which also drops foreign near-duplicates; eps is cast to float like the reference does.
  *   - k == 0 -> nothing is written, returns PCPX_OK (octree/linked_octree_node.hpp:464).
+ *   - k <= 32 runs the register-list kernels, 32 < k <= 256 an exact heap kernel (slower per
+ *     neighbour); larger k returns PCPX_ERR_UNSUPPORTED.
  * out_d2 and out_count may be NULL.
  */
 int pcpx_knn(

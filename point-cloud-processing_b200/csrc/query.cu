@@ -4,6 +4,7 @@
 // compare-selects and cached 16-byte loads.
 #include <algorithm>
 
+#include "big_k.cuh"
 #include "normals_core.cuh"
 #include "query.hpp"
 #include "radius_core.cuh"
@@ -203,6 +204,89 @@ __global__ void __launch_bounds__(kQBlock) knn_retry_kernel(GridView g, QueryBat
                                              b, cl, sl, nullptr);
         knn_finish<K, MODE>(g, cl, sl, x, y, z, top, k, eps, found, row, out);
     }
+}
+
+// ---- k beyond the register list (big_k.cuh) --------------------------------------------------
+template <int CAP>
+__global__ void __launch_bounds__(kQBlock) knn_big_kernel(
+    GridView g, QueryBatch qb, uint32_t k, float eps, int level, uint32_t* __restrict__ out_idx,
+    float* __restrict__ out_d2, uint32_t* __restrict__ out_count)
+{
+    float x, y, z;
+    uint32_t row;
+    if (!fetch_query(g, qb, blockIdx.x * kQBlock + threadIdx.x, x, y, z, row))
+        return;
+    uint64_t keys[CAP];
+    BigHeap heap{keys, 0u, k};
+    knn_search_big(g, x, y, z, eps, level, heap);
+    size_t const base = (size_t)row * k;
+    for (uint32_t j = 0; j < k; ++j)
+    {
+        bool const valid = j < heap.n;
+        if (out_idx)
+            out_idx[base + j] = valid ? (uint32_t)keys[j] : PCPX_NO_NEIGHBOUR;
+        if (out_d2)
+            out_d2[base + j] = valid ? __uint_as_float((uint32_t)(keys[j] >> 32)) : INFINITY;
+    }
+    if (out_count)
+        out_count[row] = heap.n;
+}
+
+__global__ void __launch_bounds__(256) inverse_order_kernel(GridView g, uint32_t n_total,
+                                                            uint32_t* __restrict__ inv)
+{
+    uint32_t const i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n_total)
+        inv[__float_as_uint(g.pts[i].w)] = i;
+}
+
+// PCA normal / mean distance from finished index rows (any k)
+__global__ void __launch_bounds__(kQBlock) rows_to_normals_kernel(
+    GridView g, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ inv, uint32_t nq,
+    uint32_t k, float* __restrict__ out_centroid, float* __restrict__ out_normal)
+{
+    uint32_t const q = blockIdx.x * kQBlock + threadIdx.x;
+    if (q >= nq)
+        return;
+    const uint32_t* row = idx + (size_t)q * k;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    uint32_t n = 0;
+    for (uint32_t j = 0; j < k && row[j] != PCPX_NO_NEIGHBOUR; ++j, ++n)
+    {
+        float4 const c = __ldg(g.pts + inv[row[j]]);
+        sx += c.x, sy += c.y, sz += c.z;
+    }
+    float const inv_n = 1.f / (float)n;
+    float const mx = sx * inv_n, my = sy * inv_n, mz = sz * inv_n;
+    Sym3 m{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (uint32_t j = 0; j < n; ++j)
+    {
+        float4 const c = __ldg(g.pts + inv[row[j]]);
+        float const x = c.x - mx, y = c.y - my, z = c.z - mz;
+        m.xx += x * x, m.xy += x * y, m.xz += x * z;
+        m.yy += y * y, m.yz += y * z, m.zz += z * z;
+    }
+    float nx, ny, nz;
+    smallest_eigenvector(m, nx, ny, nz, nullptr);
+    out_normal[3 * (size_t)q] = nx, out_normal[3 * (size_t)q + 1] = ny,
+                           out_normal[3 * (size_t)q + 2] = nz;
+    if (out_centroid)
+        out_centroid[3 * (size_t)q] = mx, out_centroid[3 * (size_t)q + 1] = my,
+                                 out_centroid[3 * (size_t)q + 2] = mz;
+}
+
+__global__ void __launch_bounds__(kQBlock) rows_to_mean_kernel(
+    const float* __restrict__ d2, uint32_t nq, uint32_t k, float* __restrict__ out_mean)
+{
+    uint32_t const q = blockIdx.x * kQBlock + threadIdx.x;
+    if (q >= nq)
+        return;
+    const float* row = d2 + (size_t)q * k;
+    float sum        = 0.f;
+    uint32_t n       = 0;
+    for (uint32_t j = 0; j < k && row[j] < INFINITY; ++j, ++n)
+        sum = __fadd_rn(sum, __fsqrt_rn(row[j]));
+    out_mean[q] = __fdiv_rn(sum, (float)n);
 }
 
 // ---- instrumentation: what the search does per query ---------------------------------------
@@ -534,12 +618,60 @@ int main_level_for(const pcpx_index& ix, uint32_t k)
     return level;
 }
 
+// k > kMaxK: heap kernel -> index / distance rows -> (normals | means) from the rows
+static void launch_knn_big(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
+                           uint32_t* idx, float* d2, uint32_t* count)
+{
+    if (k > kBigKMax)
+        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kBigKMax);
+    int const level = main_level_for(ix, k);
+    dim3 const grid(grid_for(qb.nq, kQBlock));
+    if (k <= 64)
+        knn_big_kernel<64><<<grid, kQBlock, 0, ix.stream>>>(ix.grid, qb, k, eps, level, idx, d2,
+                                                            count);
+    else if (k <= 128)
+        knn_big_kernel<128><<<grid, kQBlock, 0, ix.stream>>>(ix.grid, qb, k, eps, level, idx, d2,
+                                                             count);
+    else
+        knn_big_kernel<256><<<grid, kQBlock, 0, ix.stream>>>(ix.grid, qb, k, eps, level, idx, d2,
+                                                             count);
+    PCPX_CHECK_LAUNCH();
+}
+
 template <int MODE>
 static void launch_knn_shaped(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps,
                               KnnOutputs out, uint32_t* exact_counter, uint32_t* launches)
 {
-    if (k == 0 || k > kMaxK)
-        fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
+    if (k == 0)
+        fail(PCPX_ERR_UNSUPPORTED, "k = 0 has no neighbourhood");
+    if (k > kMaxK)
+    {
+        // rows are written per QUERY ROW (original order), so the row-wise epilogues index by row
+        if (MODE == MODE_KNN)
+            launch_knn_big(ix, qb, k, eps, out.idx, out.d2, out.count);
+        else if (MODE == MODE_MEAN)
+        {
+            DevBuf<float> d2((size_t)qb.nq * k);
+            launch_knn_big(ix, qb, k, eps, nullptr, d2.get(), nullptr);
+            rows_to_mean_kernel<<<grid_for(qb.nq, kQBlock), kQBlock, 0, ix.stream>>>(
+                d2.get(), qb.nq, k, out.mean);
+            PCPX_CHECK_LAUNCH();
+            PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        }
+        else
+        {
+            DevBuf<uint32_t> idx((size_t)qb.nq * k), inv(std::max<uint64_t>(ix.n_input, 1));
+            launch_knn_big(ix, qb, k, eps, idx.get(), nullptr, nullptr);
+            inverse_order_kernel<<<grid_for((uint32_t)ix.n_input, 256), 256, 0, ix.stream>>>(
+                ix.grid, (uint32_t)ix.n_input, inv.get());
+            PCPX_CHECK_LAUNCH();
+            rows_to_normals_kernel<<<grid_for(qb.nq, kQBlock), kQBlock, 0, ix.stream>>>(
+                ix.grid, idx.get(), inv.get(), qb.nq, k, out.centroid, out.normal);
+            PCPX_CHECK_LAUNCH();
+            PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        }
+        return;
+    }
     uint32_t const kr = (uint32_t)list_size_for(k);
     int const level   = main_level_for(ix, k);
     DevBuf<uint32_t> retry_items(qb.nq), retry_count(1);
@@ -603,7 +735,7 @@ void launch_normals_from_neighbourhoods(cudaStream_t stream, const float* nbr_xy
 
 void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long long* stats4)
 {
-    if (k == 0 || k > kMaxK)
+    if (k == 0 || k > kMaxK) // instrumentation of the register-list path only
         fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (1 <= k <= %u)", k, kMaxK);
     QueryBatch qb{nullptr, 3u, nullptr, (uint32_t)ix.n_input};
     if (qb.nq == 0)

@@ -22,7 +22,7 @@ struct Tuning
 };
 Tuning& tuning();
 
-constexpr uint32_t kMaxK = 32; // register-resident list; larger k is not supported yet
+constexpr uint32_t kMaxK = 32; // register-resident list; 32 < k <= 256 takes the heap kernel (big_k.cuh)
 
 void launch_knn(const pcpx_index& ix, const QueryBatch& qb, uint32_t k, float eps, uint32_t* idx,
                 float* d2, uint32_t* count, uint32_t* exact_counter);

@@ -12,6 +12,7 @@
 #include <numeric>
 #include <vector>
 
+#include "big_k.cuh"
 #include "normals_core.cuh"
 #include "radius_core.cuh"
 
@@ -290,6 +291,30 @@ extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double ep
     if (k == 0 || nq == 0)
         return 0;
     int const level = main_level_for(ix, k, level_factor);
+    if (k > 32) // mirrors knn_big_kernel
+    {
+        if (k > kBigKMax)
+            return -5;
+        std::vector<uint64_t> keys(k);
+        for (size_t i = 0; i < nq; ++i)
+        {
+            float x, y, z;
+            size_t row;
+            fetch(ix, q, i, x, y, z, row);
+            BigHeap heap{keys.data(), 0u, k};
+            knn_search_big(ix->g, x, y, z, (float)eps, level, heap);
+            for (uint32_t j = 0; j < k; ++j)
+            {
+                bool valid       = j < heap.n;
+                idx[row * k + j] = valid ? (uint32_t)keys[j] : 0xFFFFFFFFu;
+                if (d2)
+                    d2[row * k + j] = valid ? u2f((uint32_t)(keys[j] >> 32)) : INFINITY;
+            }
+            if (cnt)
+                cnt[row] = heap.n;
+        }
+        return 0;
+    }
     EMU_DISPATCH(list_size_for(k),
                  (knn_impl<KK>(ix, q, nq, k, (float)eps, level, mode, idx, d2, cnt, st4,
                                per_query_cand)));

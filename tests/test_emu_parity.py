@@ -79,7 +79,7 @@ def test_against_reference_fixtures(emu, fix, name):
     assert np.array_equal(means, fix[name + "_mean15"], equal_nan=True)
 
 
-@pytest.mark.parametrize("k", [1, 4, 8, 10, 15, 16, 21, 30, 32])
+@pytest.mark.parametrize("k", [1, 4, 8, 10, 15, 16, 21, 30, 32, 33, 64, 100, 256])
 def test_knn_all_list_sizes(emu, oracle, k):
     rng = np.random.default_rng(k)
     xyz = rng.uniform(0, 1, (4000, 3)).astype(np.float32) * np.array([1, 1, 0.05], np.float32)

@@ -113,10 +113,30 @@ def test_knn_every_list_size(pcpx, oracle, k):
         assert np.array_equal(per, oc.mean_knn_distance(k)[0], equal_nan=True)
 
 
+@pytest.mark.parametrize("k", [33, 64, 100, 256])
+def test_knn_beyond_the_register_list(pcpx, oracle, k):
+    """32 < k <= 256 takes the heap kernel (csrc/big_k.cuh): exact, same contract."""
+    rng = np.random.default_rng(k)
+    xyz = rng.uniform(0, 1, (6_000, 3)).astype(np.float32) * np.array([1, 1, 0.05], np.float32)
+    xyz[:200] = xyz[200:400]  # duplicates
+    q = rng.uniform(-0.2, 1.2, (500, 3)).astype(np.float32)
+    oc = oracle.cloud(xyz)
+    with pcpx.Index(xyz) as ix:
+        assert same_knn(ix.knn(None, k), oc.knn(None, k))
+        assert same_knn(ix.knn(q, k), oc.knn(q, k))
+        nrm = ix.estimate_normals(None, k)
+        onrm, gap = oc.normals(None, k)
+        assert (1 - np.abs((nrm * onrm).sum(1)))[gap > 1e-3].max() <= 1e-4
+        per, _ = ix.mean_knn_distance(k)
+        assert np.array_equal(per, oc.mean_knn_distance(k)[0], equal_nan=True)
+    with pcpx.Index(xyz[:50]) as ix:  # k > n
+        assert same_knn(ix.knn(None, k), oracle.cloud(xyz[:50]).knn(None, k))
+
+
 def test_unsupported_k_fails_loudly(pcpx):
     with pcpx.Index(np.zeros((10, 3), np.float32)) as ix:
         with pytest.raises(pcpx.PcpxError) as e:
-            ix.knn(None, 33)
+            ix.knn(None, 257)
         assert e.value.code == -5
         idx, d2, cnt = ix.knn(None, 0)  # k == 0 -> {} (octree/linked_octree_node.hpp:464)
         assert idx.shape == (10, 0)
