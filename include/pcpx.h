@@ -274,8 +274,8 @@ typedef struct pcpx_timings
 int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
 
 /* Process-wide tunables (performance only, never results).  Known names:
- *   "level_factor"  main level of a kNN-shaped call = finest stored level whose mean cell
- *                   occupancy is at least level_factor * k (default 0.3). */
+ *   "success_margin"  a kNN-shaped call first tries the cheapest (level, rings) block whose ball
+ *                     is expected to hold success_margin * (k + 1) points (default 1.15). */
 int pcpx_set_tuning(const char* name, double value);
 
 /* Search work of a self-kNN over the whole cloud, summed over queries:

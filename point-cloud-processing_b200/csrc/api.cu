@@ -552,8 +552,8 @@ int pcpx_set_tuning(const char* name, double value)
     return guarded([&] {
         if (!name)
             fail(PCPX_ERR_INVALID_ARG, "name is NULL");
-        if (!std::strcmp(name, "level_factor"))
-            tuning().level_factor = (float)value;
+        if (!std::strcmp(name, "success_margin"))
+            tuning().success_margin = (float)value;
         else
             fail(PCPX_ERR_INVALID_ARG, "unknown tuning parameter '%s'", name);
     });

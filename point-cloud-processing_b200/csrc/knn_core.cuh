@@ -75,8 +75,10 @@ struct TopK
 struct BlockGeom
 {
     uint32_t cx, cy, cz, last; // cell coordinates, 2^l - 1
-    float sm[3], sp[3];        // squared conservative distance to the -/+ neighbour slab per axis
-    float block_lb2;           // squared lower bound on the distance to any point outside the block
+    float sm[3], sp[3];        // squared conservative distance to the slab of cells at offset -1 / +1
+    float sm2[3], sp2[3];      // ... at offset -2 / +2
+    float block_lb2;           // squared lower bound on the distance to anything outside the 3^3 block
+    float block_lb2_r2;        // ... outside the 5^3 block
 };
 
 PCPX_HD BlockGeom block_geom(const GridView& g, const QueryCell& c, int l, float qx, float qy,
@@ -91,7 +93,7 @@ PCPX_HD BlockGeom block_geom(const GridView& g, const QueryCell& c, int l, float
     float const q[3]  = {qx, qy, qz};
     float const o[3]  = {g.ox, g.oy, g.oz};
     uint32_t const cc[3] = {b.cx, b.cy, b.cz};
-    float lb = INFINITY;
+    float lb1 = INFINITY, lb2 = INFINITY;
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax)
     {
@@ -100,14 +102,19 @@ PCPX_HD BlockGeom block_geom(const GridView& g, const QueryCell& c, int l, float
         float fp       = ((lo + h) - q[ax]) - d2x; // to the high face
         fm             = fm > 0.f ? fm : 0.f;
         fp             = fp > 0.f ? fp : 0.f;
-        b.sm[ax]       = fmul_x(fm, fm);
-        b.sp[ax]       = fmul_x(fp, fp);
-        // block faces one cell further out; a face on the grid boundary constrains nothing
-        float const bm = cc[ax] == 0u ? INFINITY : fmaxf(fm + h - d2x, 0.f);
-        float const bp = cc[ax] == b.last ? INFINITY : fmaxf(fp + h - d2x, 0.f);
-        lb             = fminf(lb, fminf(bm, bp));
+        // one cell further out: the slabs at offset +-2 and the faces of the 3^3 block
+        float const gm = fmaxf(fm + h - d2x, 0.f), gp = fmaxf(fp + h - d2x, 0.f);
+        // two cells further out: the faces of the 5^3 block
+        float const hm = fmaxf(gm + h - d2x, 0.f), hp = fmaxf(gp + h - d2x, 0.f);
+        b.sm[ax] = fmul_x(fm, fm), b.sp[ax] = fmul_x(fp, fp);
+        b.sm2[ax] = fmul_x(gm, gm), b.sp2[ax] = fmul_x(gp, gp);
+        // a block face on (or beyond) the grid boundary constrains nothing
+        lb1 = fminf(lb1, fminf(cc[ax] == 0u ? INFINITY : gm, cc[ax] == b.last ? INFINITY : gp));
+        lb2 = fminf(lb2, fminf(cc[ax] <= 1u ? INFINITY : hm,
+                               cc[ax] + 1u >= b.last ? INFINITY : hp));
     }
-    b.block_lb2 = fmul_x(lb, lb);
+    b.block_lb2    = fmul_x(lb1, lb1);
+    b.block_lb2_r2 = fmul_x(lb2, lb2);
     return b;
 }
 
@@ -260,25 +267,52 @@ struct TopD
     }
 };
 
+PCPX_HD bool outside_axis(uint32_t c, uint32_t last, int d)
+{
+    return d < 0 ? c < (uint32_t)(-d) : c + (uint32_t)d > last;
+}
 PCPX_HD bool outside_block(const BlockGeom& b, int dx, int dy, int dz)
 {
-    return (dx < 0 && b.cx == 0u) || (dx > 0 && b.cx == b.last) || (dy < 0 && b.cy == 0u) ||
-           (dy > 0 && b.cy == b.last) || (dz < 0 && b.cz == 0u) || (dz > 0 && b.cz == b.last);
+    return outside_axis(b.cx, b.last, dx) || outside_axis(b.cy, b.last, dy) ||
+           outside_axis(b.cz, b.last, dz);
 }
+PCPX_HD float axis_lb2(const BlockGeom& b, int ax, int d)
+{
+    return d == 0 ? 0.f
+                  : (d == -1 ? b.sm[ax]
+                             : (d == 1 ? b.sp[ax] : (d < 0 ? b.sm2[ax] : b.sp2[ax])));
+}
+// conservative squared lower bound on the distance to any point of the cell at offset (dx,dy,dz)
 PCPX_HD float cell_lb2(const BlockGeom& b, int dx, int dy, int dz)
 {
-    float const sx = dx < 0 ? b.sm[0] : (dx > 0 ? b.sp[0] : 0.f);
-    float const sy = dy < 0 ? b.sm[1] : (dy > 0 ? b.sp[1] : 0.f);
-    float const sz = dz < 0 ? b.sm[2] : (dz > 0 ? b.sp[2] : 0.f);
-    return fadd_x(fadd_x(sx, sy), sz);
+    return fadd_x(fadd_x(axis_lb2(b, 0, dx), axis_lb2(b, 1, dy)), axis_lb2(b, 2, dz));
 }
 
-// The non-empty cells of one 3x3x3 block, in visiting order (own, faces, edges, corners), with
-// their conservative squared lower bounds.  Filled by ONE lock-step sweep of 27 table lookups
-// (every lane of a warp does the same thing at the same time); the candidate loops then run
-// FLAT per lane over these spans, so a warp's cost is max over lanes of (total candidates)
-// rather than the sum over cells of max over lanes of (cell size).  Lives in local memory
-// (dynamically indexed), which L1 caches.
+// Visiting order of the 5^3 block: own cell, ring 1 (6 face, 12 edge, 8 corner neighbours), then
+// the 98 cells of ring 2 by increasing lower bound.  Entry = (dx+2) | (dy+2) << 3 | (dz+2) << 6.
+#define PCPX_RING_CODES {146, 145, 147, 138, 154, 82, 210, 137, 139, 153, 155, 81, 83, 209, 211, 74, 90, 202, 218, 73, 75, 89, 91, 201, 203, 217, 219, 144, 130, 18, 274, 162, 148, 136, 80, 208, 152, 129, 17, 273, 161, 66, 194, 10, 266, 26, 282, 98, 226, 131, 19, 275, 163, 140, 84, 212, 156, 72, 200, 88, 216, 65, 193, 9, 265, 25, 281, 97, 225, 67, 195, 11, 267, 27, 283, 99, 227, 76, 204, 92, 220, 128, 16, 272, 160, 2, 258, 34, 290, 132, 20, 276, 164, 64, 192, 8, 264, 24, 280, 96, 224, 1, 257, 33, 289, 3, 259, 35, 291, 68, 196, 12, 268, 28, 284, 100, 228, 0, 256, 32, 288, 4, 260, 36, 292}
+static const uint16_t kRingCodesHost[125] = PCPX_RING_CODES;
+#ifdef __CUDACC__
+static __constant__ uint16_t kRingCodesDev[125] = PCPX_RING_CODES;
+#endif
+constexpr int kRing1End = 27, kRing2End = 125;
+PCPX_HD Offset3 ring_offset(int i)
+{
+#ifdef __CUDA_ARCH__
+    int const c = kRingCodesDev[i];
+#else
+    int const c = kRingCodesHost[i];
+#endif
+    Offset3 o;
+    o.dx = (c & 7) - 2, o.dy = ((c >> 3) & 7) - 2, o.dz = ((c >> 6) & 7) - 2;
+    return o;
+}
+
+// Up to 27 non-empty cells of a block, in visiting order, with their conservative squared lower
+// bounds.  Filled by a lock-step sweep of table lookups (every lane of a warp does the same thing
+// at the same time); the candidate loops then run FLAT per lane over these spans, so a warp's
+// cost is max over lanes of (total candidates) rather than the sum over cells of max over lanes
+// of (cell size).  Lives in local memory (dynamically indexed), which L1 caches.
 struct CellList
 {
     uint32_t start[27], end[27];
@@ -286,16 +320,21 @@ struct CellList
     int n;
 };
 
-PCPX_HD void collect_cells(const GridView& g, const BlockGeom& b, int level, CellList& cl,
-                           SearchStats* st)
+// Collects the next chunk of spans of the block, starting at ring offset `i` (advanced): cells
+// outside the grid, cells whose bound already exceeds `worst`, and empty cells are dropped.
+PCPX_HD void collect_cells(const GridView& g, const BlockGeom& b, int level, int& i, int i_end,
+                           float worst, CellList& cl, SearchStats* st)
 {
     uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
     int n               = 0;
 #pragma unroll 1
-    for (int i = 0; i < 27; ++i)
+    for (; i < i_end && n < 27; ++i)
     {
-        Offset3 const o = block27_offset(i);
+        Offset3 const o = ring_offset(i);
         if (outside_block(b, o.dx, o.dy, o.dz))
+            continue;
+        float const lb = cell_lb2(b, o.dx, o.dy, o.dz);
+        if (lb > worst) // equal: a tie may hide there
             continue;
         uint32_t start, count;
         if (st)
@@ -304,76 +343,28 @@ PCPX_HD void collect_cells(const GridView& g, const BlockGeom& b, int level, Cel
             continue;
         cl.start[n] = start;
         cl.end[n]   = start + count;
-        cl.lb2[n]   = cell_lb2(b, o.dx, o.dy, o.dz);
+        cl.lb2[n]   = lb;
         ++n;
     }
     cl.n = n;
 }
 
-// Flat iteration over the spans of a CellList whose lower bound does not exceed `bound_expr`
-// (re-evaluated whenever a new span is entered).  The body sees `c_var` (the point at sorted
-// position `p_var`); the NEXT point of the span is already in flight while the body runs
-// (software prefetch: the ~40-cycle L1 latency hides behind the ~50 instructions of the body).
-#ifndef PCPX_PREFETCH
-#define PCPX_PREFETCH 1
-#endif
-#define PCPX_FLAT_FOR_EACH(g, cl, bound_expr, p_var, c_var, ...)                               \
-    {                                                                                          \
-        int e_ = 0;                                                                            \
-        uint32_t p_var = 0, pend_ = 0;                                                         \
-        float4 next_ = make_float4(0.f, 0.f, 0.f, 0.f);                                        \
-        for (;;)                                                                               \
-        {                                                                                      \
-            bool done_ = false;                                                                \
-            if (p_var == pend_)                                                                \
-            {                                                                                  \
-                for (;;)                                                                       \
-                {                                                                              \
-                    if (e_ == (cl).n)                                                          \
-                    {                                                                          \
-                        done_ = true;                                                          \
-                        break;                                                                 \
-                    }                                                                          \
-                    float const lb_    = (cl).lb2[e_];                                         \
-                    uint32_t const s_  = (cl).start[e_];                                       \
-                    uint32_t const en_ = (cl).end[e_];                                         \
-                    ++e_;                                                                      \
-                    if (lb_ > (bound_expr)) /* equal: a tie may hide there */                  \
-                        continue;                                                              \
-                    p_var = s_, pend_ = en_;                                                   \
-                    next_ = load_pt((g).pts + p_var);                                          \
-                    break;                                                                     \
-                }                                                                              \
-            }                                                                                  \
-            if (done_)                                                                         \
-                break;                                                                         \
-            float4 const c_var = next_;                                                        \
-            if (PCPX_PREFETCH && p_var + 1 < pend_)                                            \
-                next_ = load_pt((g).pts + p_var + 1);                                          \
-            __VA_ARGS__;                                                                       \
-            ++p_var;                                                                           \
-            if (!PCPX_PREFETCH && p_var < pend_)                                               \
-                next_ = load_pt((g).pts + p_var);                                              \
-        }                                                                                      \
-    }
-
 // Candidates that were at or below the list's worst distance when pass 1 met them — a superset
 // of the final neighbours (the worst distance only shrinks) and typically ~k (1 + ln(n / k)) of
-// the n candidates, so pass 2 revisits about half of them.  Entry = (span index << 11) | offset
-// inside the span; spans longer than 2048 points or more than kShortMax entries set `overflow`
-// and pass 2 falls back to walking every span again.
+// the n candidates, so pass 2 revisits about half of them.  More than kShortMax entries set
+// `overflow` and pass 2 walks the block again.
 constexpr int kShortMax = 64;
 struct ShortList
 {
-    uint16_t code[kShortMax];
+    uint32_t pos[kShortMax]; // sorted positions
     uint32_t n;
     bool overflow;
 };
 
-PCPX_HD void shortlist_push(ShortList& sl, int span, uint32_t offset)
+PCPX_HD void shortlist_push(ShortList& sl, uint32_t p)
 {
-    if (sl.n < (uint32_t)kShortMax && offset < 2048u)
-        sl.code[sl.n] = (uint16_t)(((uint32_t)span << 11) | offset);
+    if (sl.n < (uint32_t)kShortMax)
+        sl.pos[sl.n] = p;
     else
         sl.overflow = true;
     sl.n += 1;
@@ -389,26 +380,15 @@ PCPX_HD float candidate_d2(const float4& c, float qx, float qy, float qz, float 
     return d2;
 }
 
-// Pass 1 at ONE level: distances of every candidate of the level's 3x3x3 block go through the
-// sorted list, two at a time, with the next pair already in flight.  Returns true when the
-// answer is final: the k-th distance is strictly below the distance to anything outside the
-// block (or the level is the root, which holds every point).
+// Pass 1 over one chunk of spans: distances of every candidate go through the sorted list, two
+// at a time, with the next pair already in flight; candidates at or below the running worst
+// distance are remembered for pass 2.  Spans whose bound exceeds the running worst are skipped.
 template <int K>
-PCPX_HD bool knn_attempt_dist(const GridView& g, const QueryCell& qc, int level, float qx,
-                              float qy, float qz, uint32_t k, float eps, TopD<K>& top,
-                              BlockGeom& b, CellList& cl, ShortList& sl, SearchStats* st)
+PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, float qy, float qz,
+                           float eps, TopD<K>& top, ShortList& sl, SearchStats* st)
 {
-    top.reset();
-    sl.n        = 0;
-    sl.overflow = false;
-    if (st)
-        st->attempts++;
-    b = block_geom(g, qc, level, qx, qy, qz);
-    collect_cells(g, b, level, cl, st);
-
     int e = 0;                // next span to enter
     uint32_t p = 0, pend = 0; // position inside the current span
-    uint32_t pstart = 0;
     float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
     for (;;)
     {
@@ -428,7 +408,7 @@ PCPX_HD bool knn_attempt_dist(const GridView& g, const QueryCell& qc, int level,
                 ++e;
                 if (lb > top.worst()) // equal: a tie may hide there
                     continue;
-                p = pstart = s, pend = en;
+                p = s, pend = en;
                 c0 = load_pt(g.pts + p);
                 c1 = load_pt(g.pts + (p + 1 < pend ? p + 1 : p));
                 break;
@@ -447,43 +427,77 @@ PCPX_HD bool knn_attempt_dist(const GridView& g, const QueryCell& qc, int level,
         float const d1 = has1 ? candidate_d2(a1, qx, qy, qz, eps) : INFINITY;
         float const w  = top.worst();
         if (d0 <= w && d0 < INFINITY)
-            shortlist_push(sl, e - 1, p - pstart);
+            shortlist_push(sl, p);
         if (d1 <= w && d1 < INFINITY)
-            shortlist_push(sl, e - 1, p + 1 - pstart);
+            shortlist_push(sl, p + 1);
         top.insert2(d0, d1);
         if (st)
             st->candidates += has1 ? 2 : 1;
         p += 2;
     }
-    return level == 0 || top.kth(k) < b.block_lb2;
+}
+
+// What a kNN-shaped call tries first: a (2 * rings + 1)^3 block at `level`.
+struct SearchPlan
+{
+    int level;
+    int rings; // 1 or 2
+};
+
+// One attempt: pass 1 over the block of `rings` rings at `level`.  Ring 2 is only collected
+// after rings 0-1 have gone through the list, so its cells are pruned against an already tight
+// worst distance BEFORE they cost a table lookup.  Returns true when the answer is final: the
+// k-th distance is strictly below the distance to anything outside the block (or the level is
+// the root, which holds every point).
+template <int K>
+PCPX_HD bool knn_attempt_dist(const GridView& g, const QueryCell& qc, int level, int rings,
+                              float qx, float qy, float qz, uint32_t k, float eps, TopD<K>& top,
+                              BlockGeom& b, CellList& cl, ShortList& sl, SearchStats* st)
+{
+    top.reset();
+    sl.n        = 0;
+    sl.overflow = false;
+    if (st)
+        st->attempts++;
+    b               = block_geom(g, qc, level, qx, qy, qz);
+    int const i_end = rings >= 2 ? kRing2End : kRing1End;
+    int i           = 0;
+    while (i < i_end)
+    {
+        // ring 2 starts a fresh chunk so that it sees the worst distance left by rings 0-1
+        int const chunk_end = i < kRing1End ? kRing1End : i_end;
+        collect_cells(g, b, level, i, chunk_end, top.worst(), cl, st);
+        knn_scan_dist<K>(g, cl, qx, qy, qz, eps, top, sl, st);
+    }
+    return level == 0 || top.kth(k) < (rings >= 2 ? b.block_lb2_r2 : b.block_lb2);
 }
 
 // Pass 1 walking to coarser levels until the answer is final.  Returns the final level.
 template <int K>
 PCPX_HD int knn_search_dist(const GridView& g, float qx, float qy, float qz, uint32_t k,
-                            float eps, int start_level, TopD<K>& top, BlockGeom& b,
+                            float eps, SearchPlan plan, TopD<K>& top, BlockGeom& b,
                             CellList& cl, ShortList& sl, SearchStats* st)
 {
     QueryCell const qc = query_cell(g, qx, qy, qz);
-    int l              = start_level;
-    while (!knn_attempt_dist<K>(g, qc, l, qx, qy, qz, k, eps, top, b, cl, sl, st))
+    int l              = plan.level;
+    while (!knn_attempt_dist<K>(g, qc, l, plan.rings, qx, qy, qz, k, eps, top, b, cl, sl, st))
         --l;
     return l;
 }
 
 // Pass 2.  f(point, sorted position, d2, dx, dy, dz) for every eligible point with d2 <= tau:
-// over the short list when it is complete, else over every span again.
+// over the short list when it is complete, else over the whole block again.
 template <class F>
-PCPX_HD void for_each_within(const GridView& g, const CellList& cl, const ShortList& sl, float qx,
-                             float qy, float qz, float tau, float eps, F&& f)
+PCPX_HD void for_each_within(const GridView& g, const BlockGeom& b, int level, int rings,
+                             const ShortList& sl, float qx, float qy, float qz, float tau,
+                             float eps, F&& f)
 {
     if (!sl.overflow)
     {
         for (uint32_t j = 0; j < sl.n; ++j)
         {
-            uint32_t const code = sl.code[j];
-            uint32_t const p    = cl.start[code >> 11] + (code & 2047u);
-            float4 const c      = load_pt(g.pts + p);
+            uint32_t const p = sl.pos[j];
+            float4 const c   = load_pt(g.pts + p);
             float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
             float const d2 = sqdist_x(dx, dy, dz);
             bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
@@ -492,13 +506,27 @@ PCPX_HD void for_each_within(const GridView& g, const CellList& cl, const ShortL
         }
         return;
     }
-    PCPX_FLAT_FOR_EACH(g, cl, tau, p, c, {
-        float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
-        float const d2 = sqdist_x(dx, dy, dz);
-        bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
-        if (!excluded && d2 <= tau)
-            f(c, p, d2, dx, dy, dz);
-    });
+    uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
+    int const i_end     = rings >= 2 ? kRing2End : kRing1End;
+#pragma unroll 1
+    for (int i = 0; i < i_end; ++i)
+    {
+        Offset3 const o = ring_offset(i);
+        if (outside_block(b, o.dx, o.dy, o.dz) || cell_lb2(b, o.dx, o.dy, o.dz) > tau)
+            continue;
+        uint32_t start, count;
+        if (!find_cell(g, key0 + key_delta(o.dx, o.dy, o.dz), start, count))
+            continue;
+        for (uint32_t p = start; p < start + count; ++p)
+        {
+            float4 const c = load_pt(g.pts + p);
+            float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
+            float const d2 = sqdist_x(dx, dy, dz);
+            bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
+            if (!excluded && d2 <= tau)
+                f(c, p, d2, dx, dy, dz);
+        }
+    }
 }
 
 } // namespace pcpx

@@ -6,6 +6,7 @@
 
 #include "big_k.cuh"
 #include "normals_core.cuh"
+#include "plan.hpp"
 #include "query.hpp"
 #include "radius_core.cuh"
 
@@ -124,9 +125,9 @@ __device__ __noinline__ void normal_exact(const GridView& g, float x, float y, f
 
 // second pass + output of one query whose first pass is final
 template <int K, int MODE>
-__device__ __forceinline__ void knn_finish(const GridView& g, const CellList& cl,
-                                           const ShortList& sl, float x, float y, float z,
-                                           const TopD<K>& top, uint32_t k, float eps, int level,
+__device__ __forceinline__ void knn_finish(const GridView& g, const BlockGeom& b, int level,
+                                           int rings, const ShortList& sl, float x, float y,
+                                           float z, const TopD<K>& top, uint32_t k, float eps,
                                            uint32_t row, const KnnOutputs& out)
 {
     if (MODE == MODE_MEAN)
@@ -138,7 +139,8 @@ __device__ __forceinline__ void knn_finish(const GridView& g, const CellList& cl
         uint32_t* idx_row = out.idx + (size_t)row * k;
         float* d2_row     = out.d2 ? out.d2 + (size_t)row * k : nullptr;
         uint32_t* cnt     = out.count ? out.count + row : nullptr;
-        if (!knn_two_pass_emit<K>(g, cl, sl, x, y, z, top, k, eps, idx_row, d2_row, cnt))
+        if (!knn_two_pass_emit<K>(g, b, level, rings, sl, x, y, z, top, k, eps, idx_row, d2_row,
+                                  cnt))
         {
             knn_exact_row<K>(g, x, y, z, k, eps, level, idx_row, d2_row, cnt);
             if (out.exact_counter)
@@ -150,7 +152,7 @@ __device__ __forceinline__ void knn_finish(const GridView& g, const CellList& cl
         float* nrow = out.normal + 3 * (size_t)row;
         float* crow = out.centroid ? out.centroid + 3 * (size_t)row : nullptr;
         float n3[3], c3[3];
-        if (normal_two_pass<K>(g, cl, sl, x, y, z, top, k, eps, n3, c3, nullptr))
+        if (normal_two_pass<K>(g, b, level, rings, sl, x, y, z, top, k, eps, n3, c3, nullptr))
         {
             nrow[0] = n3[0], nrow[1] = n3[1], nrow[2] = n3[2];
             if (crow)
@@ -167,8 +169,8 @@ __device__ __forceinline__ void knn_finish(const GridView& g, const CellList& cl
 }
 
 template <int K, int MODE>
-__global__ void __launch_bounds__(kQBlock, min_blocks_for(K)) knn_main_kernel(GridView g, QueryBatch qb, uint32_t k,
-                                                           float eps, int level, KnnOutputs out)
+__global__ void __launch_bounds__(kQBlock, min_blocks_for(K)) knn_main_kernel(
+    GridView g, QueryBatch qb, uint32_t k, float eps, SearchPlan plan, KnnOutputs out)
 {
     uint32_t const t = blockIdx.x * kQBlock + threadIdx.x;
     float x, y, z;
@@ -180,15 +182,17 @@ __global__ void __launch_bounds__(kQBlock, min_blocks_for(K)) knn_main_kernel(Gr
     CellList cl;
     ShortList sl;
     QueryCell const qc = query_cell(g, x, y, z);
-    if (knn_attempt_dist<K>(g, qc, level, x, y, z, k, eps, top, b, cl, sl, nullptr))
-        knn_finish<K, MODE>(g, cl, sl, x, y, z, top, k, eps, level, row, out);
+    if (knn_attempt_dist<K>(g, qc, plan.level, plan.rings, x, y, z, k, eps, top, b, cl, sl,
+                            nullptr))
+        knn_finish<K, MODE>(g, b, plan.level, plan.rings, sl, x, y, z, top, k, eps, row, out);
     else
         out.retry_items[atomicAdd(out.retry_count, 1u)] = t;
 }
 
 template <int K, int MODE>
 __global__ void __launch_bounds__(kQBlock) knn_retry_kernel(GridView g, QueryBatch qb, uint32_t k,
-                                                            float eps, int level, KnnOutputs out)
+                                                            float eps, SearchPlan plan,
+                                                            KnnOutputs out)
 {
     uint32_t const n_retry = *out.retry_count;
     for (uint32_t i = blockIdx.x * kQBlock + threadIdx.x; i < n_retry; i += gridDim.x * kQBlock)
@@ -200,9 +204,10 @@ __global__ void __launch_bounds__(kQBlock) knn_retry_kernel(GridView g, QueryBat
         BlockGeom b;
         CellList cl;
         ShortList sl;
-        int const found = knn_search_dist<K>(g, x, y, z, k, eps, level > 0 ? level - 1 : 0, top,
-                                             b, cl, sl, nullptr);
-        knn_finish<K, MODE>(g, cl, sl, x, y, z, top, k, eps, found, row, out);
+        // same ring count, one level coarser each time
+        SearchPlan const next{plan.level > 0 ? plan.level - 1 : 0, plan.rings};
+        int const found = knn_search_dist<K>(g, x, y, z, k, eps, next, top, b, cl, sl, nullptr);
+        knn_finish<K, MODE>(g, b, found, plan.rings, sl, x, y, z, top, k, eps, row, out);
     }
 }
 
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(kQBlock) rows_to_mean_kernel(
 // ---- instrumentation: what the search does per query ---------------------------------------
 template <int K>
 __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
-    GridView g, QueryBatch qb, uint32_t k, float eps, int level,
+    GridView g, QueryBatch qb, uint32_t k, float eps, SearchPlan plan,
     unsigned long long* __restrict__ stats4)
 {
     float x, y, z;
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
         BlockGeom b;
         CellList cl;
         ShortList sl;
-        knn_search_dist<K>(g, x, y, z, k, eps, level, top, b, cl, sl, &st);
+        knn_search_dist<K>(g, x, y, z, k, eps, plan, top, b, cl, sl, &st);
     }
     uint32_t const warp_max = __reduce_max_sync(0xFFFFFFFFu, st.candidates);
     unsigned long long v[4] = {st.candidates, st.lookups, st.attempts,
@@ -604,18 +609,12 @@ static int list_size_for(uint32_t k)
     default: fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kMaxK);        \
     }
 
-// Main level of a kNN-shaped call: the finest stored level whose mean cell occupancy is at
-// least level_factor * k (its 3x3x3 block then holds a few times k points and succeeds for
-// nearly every query of a uniformly dense region).
-int main_level_for(const pcpx_index& ix, uint32_t k)
+// What a kNN-shaped call tries first (plan.hpp).
+SearchPlan plan_for(const pcpx_index& ix, uint32_t k)
 {
-    double const want = std::max(1.0, (double)tuning().level_factor * (double)k);
-    int level         = 0;
-    for (int l = 0; l <= ix.grid.lfine; ++l)
-        if (ix.cells_per_level[l] > 0 &&
-            (double)ix.n_indexed / (double)ix.cells_per_level[l] >= want)
-            level = l;
-    return level;
+    PlanChoice const c = choose_plan(ix.n_indexed, ix.cells_per_level, ix.grid.lfine, k,
+                                     (double)tuning().success_margin);
+    return SearchPlan{c.level, c.rings};
 }
 
 // k > kMaxK: heap kernel -> index / distance rows -> (normals | means) from the rows
@@ -624,7 +623,7 @@ static void launch_knn_big(const pcpx_index& ix, const QueryBatch& qb, uint32_t 
 {
     if (k > kBigKMax)
         fail(PCPX_ERR_UNSUPPORTED, "k = %u is not supported (k <= %u)", k, kBigKMax);
-    int const level = main_level_for(ix, k);
+    int const level = plan_for(ix, k).level;
     dim3 const grid(grid_for(qb.nq, kQBlock));
     if (k <= 64)
         knn_big_kernel<64><<<grid, kQBlock, 0, ix.stream>>>(ix.grid, qb, k, eps, level, idx, d2,
@@ -672,8 +671,8 @@ static void launch_knn_shaped(const pcpx_index& ix, const QueryBatch& qb, uint32
         }
         return;
     }
-    uint32_t const kr = (uint32_t)list_size_for(k);
-    int const level   = main_level_for(ix, k);
+    uint32_t const kr     = (uint32_t)list_size_for(k);
+    SearchPlan const plan = plan_for(ix, k);
     DevBuf<uint32_t> retry_items(qb.nq), retry_count(1);
     PCPX_CUDA(cudaMemsetAsync(retry_count.get(), 0, 4, ix.stream));
     out.exact_counter = exact_counter;
@@ -682,10 +681,10 @@ static void launch_knn_shaped(const pcpx_index& ix, const QueryBatch& qb, uint32
     dim3 const grid(grid_for(qb.nq, kQBlock));
     dim3 const retry_grid(std::min<uint32_t>(grid.x, 148u * 16u));
     PCPX_DISPATCH_K(kr, (knn_main_kernel<KK, MODE><<<grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, level, out)));
+                            ix.grid, qb, k, eps, plan, out)));
     PCPX_CHECK_LAUNCH();
     PCPX_DISPATCH_K(kr, (knn_retry_kernel<KK, MODE><<<retry_grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, level, out)));
+                            ix.grid, qb, k, eps, plan, out)));
     PCPX_CHECK_LAUNCH();
     if (launches)
         *launches += 2;
@@ -740,11 +739,11 @@ void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long
     QueryBatch qb{nullptr, 3u, nullptr, (uint32_t)ix.n_input};
     if (qb.nq == 0)
         return;
-    uint32_t const kr = (uint32_t)list_size_for(k);
-    int const level   = main_level_for(ix, k);
+    uint32_t const kr     = (uint32_t)list_size_for(k);
+    SearchPlan const plan = plan_for(ix, k);
     dim3 const grid(grid_for(qb.nq, kQBlock));
     PCPX_DISPATCH_K(kr, (knn_stats_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, level, stats4)));
+                            ix.grid, qb, k, eps, plan, stats4)));
     PCPX_CHECK_LAUNCH();
 }
 

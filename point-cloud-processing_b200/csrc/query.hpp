@@ -17,7 +17,7 @@ struct QueryBatch
 
 struct Tuning
 {
-    float level_factor = 0.3f;  // main level: finest whose mean cell occupancy >= level_factor * k
+    float success_margin = 1.15f; // a block is tried when its ball should hold margin * (k + 1) points
     int block_threads  = 128;
 };
 Tuning& tuning();

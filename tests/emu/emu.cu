@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "big_k.cuh"
+#include "plan.hpp"
 #include "normals_core.cuh"
 #include "radius_core.cuh"
 
@@ -27,16 +28,11 @@ struct EmuIndex
     uint64_t cells_per_level[kMaxLevel + 2] = {};
 };
 
-// mirrors main_level_for() in query.cu
-static int main_level_for(const EmuIndex* ix, uint32_t k, double level_factor)
+// mirrors plan_for() in query.cu
+static SearchPlan plan_for(const EmuIndex* ix, uint32_t k, double margin)
 {
-    double const want = std::max(1.0, level_factor * (double)k);
-    int level         = 0;
-    for (int l = 0; l <= ix->g.lfine; ++l)
-        if (ix->cells_per_level[l] > 0 &&
-            (double)ix->g.n / (double)ix->cells_per_level[l] >= want)
-            level = l;
-    return level;
+    PlanChoice const c = choose_plan(ix->g.n, ix->cells_per_level, ix->g.lfine, k, margin);
+    return SearchPlan{c.level, c.rings};
 }
 
 static uint32_t host_claim(std::vector<HashSlot>& t, uint64_t key)
@@ -139,7 +135,7 @@ void* emu_index_create(const float* xyz, size_t n, int use_box, const float* box
     std::vector<uint64_t> lh(kMaxLevel + 2, 0);
     for (uint32_t i = 0; i < g.n; ++i)
         lh[boundary(i)]++;
-    double min_occ = min_occ_in ? (double)min_occ_in : 4.0;
+    double min_occ = min_occ_in ? (double)min_occ_in : 2.0;
     uint64_t cells = 0, total = 0;
     g.lfine = 0;
     for (int l = 0; l <= g.lcap; ++l)
@@ -182,6 +178,17 @@ void* emu_index_create(const float* xyz, size_t n, int use_box, const float* box
 
 void emu_index_destroy(void* h) { delete static_cast<EmuIndex*>(h); }
 
+void emu_plan(void* h, uint32_t k, double margin, int* level, int* rings, double* occupancy)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    PlanChoice const c =
+        choose_plan(ix->g.n, ix->cells_per_level, ix->g.lfine, k, margin);
+    *level = c.level, *rings = c.rings;
+    *occupancy = ix->cells_per_level[c.level]
+                     ? (double)ix->g.n / (double)ix->cells_per_level[c.level]
+                     : 0.0;
+}
+
 void emu_index_info(void* h, uint64_t* n_indexed, int* lcap, int* lfine, uint64_t* slots)
 {
     EmuIndex* ix = static_cast<EmuIndex*>(h);
@@ -216,7 +223,7 @@ constexpr int exact_k(int K) { return (K + 3) / 4 * 4; }
 // product path), 1 = force the exact 64-bit search for every query
 template <int K>
 static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
-                     int level, int mode, uint32_t* idx, float* d2, uint32_t* cnt,
+                     SearchPlan plan, int mode, uint32_t* idx, float* d2, uint32_t* cnt,
                      uint64_t* st4, uint32_t* per_query_cand)
 {
     for (size_t i = 0; i < nq; ++i)
@@ -232,20 +239,24 @@ static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float 
             BlockGeom b;
             CellList cl;
             ShortList sl;
-            // main pass: one attempt at the main level; otherwise the retry pass walks coarser
-            if (!knn_attempt_dist<K>(ix->g, query_cell(ix->g, x, y, z), level, x, y, z, k, eps,
-                                     top, b, cl, sl, &st))
-                knn_search_dist<K>(ix->g, x, y, z, k, eps, level > 0 ? level - 1 : 0, top, b, cl,
-                                   sl, &st);
-            done = knn_two_pass_emit<K>(ix->g, cl, sl, x, y, z, top, k, eps, idx + row * k,
-                                        d2 ? d2 + row * k : nullptr, cnt ? cnt + row : nullptr);
+            // main pass: one attempt of the plan; otherwise the retry pass walks coarser
+            int level = plan.level;
+            if (!knn_attempt_dist<K>(ix->g, query_cell(ix->g, x, y, z), plan.level, plan.rings, x,
+                                     y, z, k, eps, top, b, cl, sl, &st))
+                level = knn_search_dist<K>(ix->g, x, y, z, k, eps,
+                                           SearchPlan{plan.level > 0 ? plan.level - 1 : 0,
+                                                      plan.rings},
+                                           top, b, cl, sl, &st);
+            done = knn_two_pass_emit<K>(ix->g, b, level, plan.rings, sl, x, y, z, top, k, eps,
+                                        idx + row * k, d2 ? d2 + row * k : nullptr,
+                                        cnt ? cnt + row : nullptr);
             if (!done && st4)
                 st4[3] += 1; // retries
         }
         if (!done)
         {
             TopK<exact_k(K)> top;
-            knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, level, top,
+            knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, plan.level, top,
                                                        mode == 1 ? &st : nullptr);
             uint32_t n = 0;
             for (uint32_t j = 0; j < k; ++j)
@@ -290,7 +301,8 @@ extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double ep
     EmuIndex* ix = static_cast<EmuIndex*>(h);
     if (k == 0 || nq == 0)
         return 0;
-    int const level = main_level_for(ix, k, level_factor);
+    SearchPlan const plan = plan_for(ix, k, level_factor);
+    int const level       = plan.level;
     if (k > 32) // mirrors knn_big_kernel
     {
         if (k > kBigKMax)
@@ -316,7 +328,7 @@ extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double ep
         return 0;
     }
     EMU_DISPATCH(list_size_for(k),
-                 (knn_impl<KK>(ix, q, nq, k, (float)eps, level, mode, idx, d2, cnt, st4,
+                 (knn_impl<KK>(ix, q, nq, k, (float)eps, plan, mode, idx, d2, cnt, st4,
                                per_query_cand)));
     return 0;
 }
@@ -324,7 +336,7 @@ extern "C" int emu_knn(void* h, const float* q, size_t nq, uint32_t k, double ep
 // mirrors normals_kernel / normal_exact and mean_distance_kernel
 template <int K>
 static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
-                         int level, int mode, float* ctr, float* nrm, float* means,
+                         SearchPlan plan, int mode, float* ctr, float* nrm, float* means,
                          uint32_t* ties)
 {
     for (size_t i = 0; i < nq; ++i)
@@ -337,17 +349,19 @@ static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, fl
         BlockGeom b;
         CellList cl;
         ShortList sl;
-        if (!knn_attempt_dist<K>(ix->g, query_cell(ix->g, x, y, z), level, x, y, z, k, eps, top, b,
-                                 cl, sl, nullptr))
-            knn_search_dist<K>(ix->g, x, y, z, k, eps, level > 0 ? level - 1 : 0, top, b, cl, sl,
-                               nullptr);
-        bool ok =
-            mode == 0 && normal_two_pass<K>(ix->g, cl, sl, x, y, z, top, k, eps, n3, c3, nullptr);
+        int level = plan.level;
+        if (!knn_attempt_dist<K>(ix->g, query_cell(ix->g, x, y, z), plan.level, plan.rings, x, y,
+                                 z, k, eps, top, b, cl, sl, nullptr))
+            level = knn_search_dist<K>(ix->g, x, y, z, k, eps,
+                                       SearchPlan{plan.level > 0 ? plan.level - 1 : 0, plan.rings},
+                                       top, b, cl, sl, nullptr);
+        bool ok = mode == 0 && normal_two_pass<K>(ix->g, b, level, plan.rings, sl, x, y, z, top, k,
+                                                  eps, n3, c3, nullptr);
         if (!ok)
         {
             TopK<exact_k(K)> ids;
-            int lv = knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, level, ids,
-                                                                nullptr);
+            int lv = knn_search<exact_k(K), TIE_ORIGINAL_INDEX>(ix->g, x, y, z, k, eps, plan.level,
+                                                                ids, nullptr);
             normal_from_ids(ix->g, query_cell(ix->g, x, y, z), lv, ids, k, n3, c3, nullptr);
             if (ties)
                 ++*ties;
@@ -370,9 +384,9 @@ extern "C" int emu_normals(void* h, const float* q, size_t nq, uint32_t k, doubl
     EmuIndex* ix = static_cast<EmuIndex*>(h);
     if (k == 0 || nq == 0)
         return 0;
-    int const level = main_level_for(ix, k, level_factor);
+    SearchPlan const plan = plan_for(ix, k, level_factor);
     EMU_DISPATCH(list_size_for(k),
-                 (normals_impl<KK>(ix, q, nq, k, (float)eps, level, mode, ctr, nrm, means, ties)));
+                 (normals_impl<KK>(ix, q, nq, k, (float)eps, plan, mode, ctr, nrm, means, ties)));
     return 0;
 }
 

@@ -51,6 +51,8 @@ class Emu:
         L.emu_index_destroy.argtypes = [C.c_void_p]
         L.emu_index_info.argtypes = [C.c_void_p, _u64p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      _u64p]
+        L.emu_plan.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.POINTER(C.c_int),
+                               C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.emu_knn.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_uint32, C.c_double, C.c_double,
                               C.c_int, _u32p, _f32p, _u32p, _u64p, _u32p]
         L.emu_normals.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_uint32, C.c_double,
@@ -93,7 +95,12 @@ class EmuIndex:
         self.L.emu_index_info(self.h, C.byref(n), C.byref(lcap), C.byref(lfine), C.byref(slots))
         return dict(n_indexed=n.value, lcap=lcap.value, lfine=lfine.value, slots=slots.value)
 
-    def knn(self, queries, k, eps=1e-5, level_factor=0.3, exact_only=False):
+    def plan(self, k, margin=1.15):
+        lv, rg, occ = C.c_int(), C.c_int(), C.c_double()
+        self.L.emu_plan(self.h, k, margin, C.byref(lv), C.byref(rg), C.byref(occ))
+        return dict(level=lv.value, rings=rg.value, occupancy=occ.value)
+
+    def knn(self, queries, k, eps=1e-5, level_factor=1.15, exact_only=False):
         """exact_only=False mirrors the product kernel (two-pass + exact fallback); True forces
         the 64-bit (distance, index) search for every query.  st = candidates, lookups,
         attempts, fallbacks."""
@@ -111,7 +118,7 @@ class EmuIndex:
         assert rc == 0
         return idx, d2, cnt, st
 
-    def normals(self, queries, k, eps=1e-5, level_factor=0.3, want_means=False,
+    def normals(self, queries, k, eps=1e-5, level_factor=1.15, want_means=False,
                 exact_only=False):
         q = _f32(queries)
         nq = self.n if q is None else len(q)

@@ -34,8 +34,8 @@ def main():
         d_nrm = torch.empty((n, 3), dtype=torch.float32, device="cuda")
         d_idx = torch.empty((n, k), dtype=torch.int32, device="cuda")
         d_cnt = torch.empty((n,), dtype=torch.int32, device="cuda")
-        for lf in (0.25, 0.5, 0.75):
-            pcpx.set_tuning("level_factor", lf)
+        for lf in (1.0, 1.15, 1.5):
+            pcpx.set_tuning("success_margin", lf)
             st = ix.knn_stats(k)
             res = {"stats_per_query": (st / n).tolist()}
             for rep in range(3):
@@ -45,7 +45,7 @@ def main():
                 ix.knn(None, k, out_idx=d_idx, out_d2=None, out_count=d_cnt, want_d2=False)
                 res.setdefault("knn_kernel_ms", []).append(ix.timings()["kernel_ms"])
             out["level_factor_%g" % lf] = res
-        pcpx.set_tuning("level_factor", 0.5)
+        pcpx.set_tuning("success_margin", 1.15)
         for rep in range(2):
             ix.radius_count(None, 0.01, out_count=d_cnt)
             out.setdefault("radius_count_kernel_ms", []).append(ix.timings()["kernel_ms"])

@@ -19,7 +19,7 @@ def main():
     what = sys.argv[3] if len(sys.argv) > 3 else "normals"
     lf = float(sys.argv[4]) if len(sys.argv) > 4 else None
     if lf is not None:
-        pcpx.set_tuning("level_factor", lf)
+        pcpx.set_tuning("success_margin", lf)
     xyz = pcpx.synth.noisy_plane(n)
     d_xyz = torch.from_numpy(xyz).cuda()
     torch.cuda.synchronize()
