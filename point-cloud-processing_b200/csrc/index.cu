@@ -460,7 +460,7 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
     float const sort_ms = n ? elapsed_ms(ev_sort0, ev_sort1) : 0.f;
     sc = SortScratch{}; // the stream is idle: the sort temporaries and the staged copy can go
     staged.release();
-    double const min_occ = prm.min_cell_occupancy ? (double)prm.min_cell_occupancy : 2.0;
+    double const min_occ = prm.min_cell_occupancy ? (double)prm.min_cell_occupancy : 4.0;
     uint64_t cells = 0, total_cells = 0;
     for (int l = 0; l <= g.lcap; ++l)
     {

@@ -276,6 +276,19 @@ PCPX_HD bool outside_block(const BlockGeom& b, int dx, int dy, int dz)
     return outside_axis(b.cx, b.last, dx) || outside_axis(b.cy, b.last, dy) ||
            outside_axis(b.cz, b.last, dz);
 }
+// |d| <= 1 fast paths (the 3^3 block): cheaper than the general forms below
+PCPX_HD bool outside_block_near(const BlockGeom& b, int dx, int dy, int dz)
+{
+    return (dx < 0 && b.cx == 0u) || (dx > 0 && b.cx == b.last) || (dy < 0 && b.cy == 0u) ||
+           (dy > 0 && b.cy == b.last) || (dz < 0 && b.cz == 0u) || (dz > 0 && b.cz == b.last);
+}
+PCPX_HD float cell_lb2_near(const BlockGeom& b, int dx, int dy, int dz)
+{
+    float const sx = dx < 0 ? b.sm[0] : (dx > 0 ? b.sp[0] : 0.f);
+    float const sy = dy < 0 ? b.sm[1] : (dy > 0 ? b.sp[1] : 0.f);
+    float const sz = dz < 0 ? b.sm[2] : (dz > 0 ? b.sp[2] : 0.f);
+    return fadd_x(fadd_x(sx, sy), sz);
+}
 PCPX_HD float axis_lb2(const BlockGeom& b, int ax, int d)
 {
     return d == 0 ? 0.f
@@ -320,15 +333,41 @@ struct CellList
     int n;
 };
 
-// Collects the next chunk of spans of the block, starting at ring offset `i` (advanced): cells
-// outside the grid, cells whose bound already exceeds `worst`, and empty cells are dropped.
-PCPX_HD void collect_cells(const GridView& g, const BlockGeom& b, int level, int& i, int i_end,
-                           float worst, CellList& cl, SearchStats* st)
+// Rings 0-1 (the 3^3 block): every in-grid cell is looked up, in visiting order.
+PCPX_HD void collect_block27(const GridView& g, const BlockGeom& b, int level, CellList& cl,
+                             SearchStats* st)
 {
     uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
     int n               = 0;
 #pragma unroll 1
-    for (; i < i_end && n < 27; ++i)
+    for (int i = 0; i < 27; ++i)
+    {
+        Offset3 const o = block27_offset(i);
+        if (outside_block_near(b, o.dx, o.dy, o.dz))
+            continue;
+        uint32_t start, count;
+        if (st)
+            st->lookups++;
+        if (!find_cell(g, key0 + key_delta(o.dx, o.dy, o.dz), start, count))
+            continue;
+        cl.start[n] = start;
+        cl.end[n]   = start + count;
+        cl.lb2[n]   = cell_lb2_near(b, o.dx, o.dy, o.dz);
+        ++n;
+    }
+    cl.n = n;
+}
+
+// Ring 2, in chunks of up to 27 spans starting at ring offset `i` (advanced): cells outside the
+// grid, cells whose bound already exceeds `worst`, and empty cells are dropped — most of the 98
+// cells never cost a table lookup because rings 0-1 have already tightened `worst`.
+PCPX_HD void collect_ring2(const GridView& g, const BlockGeom& b, int level, int& i, float worst,
+                           CellList& cl, SearchStats* st)
+{
+    uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
+    int n               = 0;
+#pragma unroll 1
+    for (; i < kRing2End && n < 27; ++i)
     {
         Offset3 const o = ring_offset(i);
         if (outside_block(b, o.dx, o.dy, o.dz))
@@ -353,22 +392,26 @@ PCPX_HD void collect_cells(const GridView& g, const BlockGeom& b, int level, int
 // of the final neighbours (the worst distance only shrinks) and typically ~k (1 + ln(n / k)) of
 // the n candidates, so pass 2 revisits about half of them.  More than kShortMax entries set
 // `overflow` and pass 2 walks the block again.
-constexpr int kShortMax = 64;
-struct ShortList
+template <int CAP>
+struct ShortListT
 {
-    uint32_t pos[kShortMax]; // sorted positions
+    static constexpr int capacity = CAP;
+    uint32_t pos[CAP]; // sorted positions
     uint32_t n;
     bool overflow;
-};
 
-PCPX_HD void shortlist_push(ShortList& sl, uint32_t p)
-{
-    if (sl.n < (uint32_t)kShortMax)
-        sl.pos[sl.n] = p;
-    else
-        sl.overflow = true;
-    sl.n += 1;
-}
+    PCPX_HD void push(uint32_t p)
+    {
+        if (n < (uint32_t)CAP)
+            pos[n] = p;
+        else
+            overflow = true;
+        n += 1;
+    }
+};
+// capacity for a K-entry list: ~3 K covers k (1 + ln(n / k)) for blocks of a few k candidates
+template <int K>
+using ShortListFor = ShortListT<(K <= 16 ? 48 : (K <= 24 ? 72 : 96))>;
 
 PCPX_HD float candidate_d2(const float4& c, float qx, float qy, float qz, float eps)
 {
@@ -383,9 +426,9 @@ PCPX_HD float candidate_d2(const float4& c, float qx, float qy, float qz, float 
 // Pass 1 over one chunk of spans: distances of every candidate go through the sorted list, two
 // at a time, with the next pair already in flight; candidates at or below the running worst
 // distance are remembered for pass 2.  Spans whose bound exceeds the running worst are skipped.
-template <int K>
+template <int K, class SL>
 PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, float qy, float qz,
-                           float eps, TopD<K>& top, ShortList& sl, SearchStats* st)
+                           float eps, TopD<K>& top, SL& sl, SearchStats* st)
 {
     int e = 0;                // next span to enter
     uint32_t p = 0, pend = 0; // position inside the current span
@@ -427,9 +470,9 @@ PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, floa
         float const d1 = has1 ? candidate_d2(a1, qx, qy, qz, eps) : INFINITY;
         float const w  = top.worst();
         if (d0 <= w && d0 < INFINITY)
-            shortlist_push(sl, p);
+            sl.push(p);
         if (d1 <= w && d1 < INFINITY)
-            shortlist_push(sl, p + 1);
+            sl.push(p + 1);
         top.insert2(d0, d1);
         if (st)
             st->candidates += has1 ? 2 : 1;
@@ -449,48 +492,50 @@ struct SearchPlan
 // worst distance BEFORE they cost a table lookup.  Returns true when the answer is final: the
 // k-th distance is strictly below the distance to anything outside the block (or the level is
 // the root, which holds every point).
-template <int K>
-PCPX_HD bool knn_attempt_dist(const GridView& g, const QueryCell& qc, int level, int rings,
-                              float qx, float qy, float qz, uint32_t k, float eps, TopD<K>& top,
-                              BlockGeom& b, CellList& cl, ShortList& sl, SearchStats* st)
+template <int K, int RINGS, class SL>
+PCPX_HD bool knn_attempt_dist(const GridView& g, const QueryCell& qc, int level, float qx,
+                              float qy, float qz, uint32_t k, float eps, TopD<K>& top,
+                              BlockGeom& b, CellList& cl, SL& sl, SearchStats* st)
 {
     top.reset();
     sl.n        = 0;
     sl.overflow = false;
     if (st)
         st->attempts++;
-    b               = block_geom(g, qc, level, qx, qy, qz);
-    int const i_end = rings >= 2 ? kRing2End : kRing1End;
-    int i           = 0;
-    while (i < i_end)
+    b = block_geom(g, qc, level, qx, qy, qz);
+    collect_block27(g, b, level, cl, st);
+    knn_scan_dist<K>(g, cl, qx, qy, qz, eps, top, sl, st);
+    if (RINGS >= 2)
     {
-        // ring 2 starts a fresh chunk so that it sees the worst distance left by rings 0-1
-        int const chunk_end = i < kRing1End ? kRing1End : i_end;
-        collect_cells(g, b, level, i, chunk_end, top.worst(), cl, st);
-        knn_scan_dist<K>(g, cl, qx, qy, qz, eps, top, sl, st);
+        // ring 2 is collected only now, so that it sees the worst distance left by rings 0-1
+        int i = kRing1End;
+        while (i < kRing2End)
+        {
+            collect_ring2(g, b, level, i, top.worst(), cl, st);
+            knn_scan_dist<K>(g, cl, qx, qy, qz, eps, top, sl, st);
+        }
     }
-    return level == 0 || top.kth(k) < (rings >= 2 ? b.block_lb2_r2 : b.block_lb2);
+    return level == 0 || top.kth(k) < (RINGS >= 2 ? b.block_lb2_r2 : b.block_lb2);
 }
 
 // Pass 1 walking to coarser levels until the answer is final.  Returns the final level.
-template <int K>
+template <int K, int RINGS, class SL>
 PCPX_HD int knn_search_dist(const GridView& g, float qx, float qy, float qz, uint32_t k,
-                            float eps, SearchPlan plan, TopD<K>& top, BlockGeom& b,
-                            CellList& cl, ShortList& sl, SearchStats* st)
+                            float eps, int start_level, TopD<K>& top, BlockGeom& b, CellList& cl,
+                            SL& sl, SearchStats* st)
 {
     QueryCell const qc = query_cell(g, qx, qy, qz);
-    int l              = plan.level;
-    while (!knn_attempt_dist<K>(g, qc, l, plan.rings, qx, qy, qz, k, eps, top, b, cl, sl, st))
+    int l              = start_level;
+    while (!knn_attempt_dist<K, RINGS>(g, qc, l, qx, qy, qz, k, eps, top, b, cl, sl, st))
         --l;
     return l;
 }
 
 // Pass 2.  f(point, sorted position, d2, dx, dy, dz) for every eligible point with d2 <= tau:
 // over the short list when it is complete, else over the whole block again.
-template <class F>
-PCPX_HD void for_each_within(const GridView& g, const BlockGeom& b, int level, int rings,
-                             const ShortList& sl, float qx, float qy, float qz, float tau,
-                             float eps, F&& f)
+template <int RINGS, class SL, class F>
+PCPX_HD void for_each_within(const GridView& g, const BlockGeom& b, int level, const SL& sl,
+                             float qx, float qy, float qz, float tau, float eps, F&& f)
 {
     if (!sl.overflow)
     {
@@ -507,7 +552,7 @@ PCPX_HD void for_each_within(const GridView& g, const BlockGeom& b, int level, i
         return;
     }
     uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
-    int const i_end     = rings >= 2 ? kRing2End : kRing1End;
+    int const i_end     = RINGS >= 2 ? kRing2End : kRing1End;
 #pragma unroll 1
     for (int i = 0; i < i_end; ++i)
     {

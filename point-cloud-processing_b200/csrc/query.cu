@@ -124,10 +124,10 @@ __device__ __noinline__ void normal_exact(const GridView& g, float x, float y, f
 }
 
 // second pass + output of one query whose first pass is final
-template <int K, int MODE>
+template <int K, int MODE, int RINGS, class SL>
 __device__ __forceinline__ void knn_finish(const GridView& g, const BlockGeom& b, int level,
-                                           int rings, const ShortList& sl, float x, float y,
-                                           float z, const TopD<K>& top, uint32_t k, float eps,
+                                           const SL& sl, float x, float y, float z,
+                                           const TopD<K>& top, uint32_t k, float eps,
                                            uint32_t row, const KnnOutputs& out)
 {
     if (MODE == MODE_MEAN)
@@ -139,8 +139,8 @@ __device__ __forceinline__ void knn_finish(const GridView& g, const BlockGeom& b
         uint32_t* idx_row = out.idx + (size_t)row * k;
         float* d2_row     = out.d2 ? out.d2 + (size_t)row * k : nullptr;
         uint32_t* cnt     = out.count ? out.count + row : nullptr;
-        if (!knn_two_pass_emit<K>(g, b, level, rings, sl, x, y, z, top, k, eps, idx_row, d2_row,
-                                  cnt))
+        if (!knn_two_pass_emit<K, RINGS>(g, b, level, sl, x, y, z, top, k, eps, idx_row, d2_row,
+                                         cnt))
         {
             knn_exact_row<K>(g, x, y, z, k, eps, level, idx_row, d2_row, cnt);
             if (out.exact_counter)
@@ -152,7 +152,7 @@ __device__ __forceinline__ void knn_finish(const GridView& g, const BlockGeom& b
         float* nrow = out.normal + 3 * (size_t)row;
         float* crow = out.centroid ? out.centroid + 3 * (size_t)row : nullptr;
         float n3[3], c3[3];
-        if (normal_two_pass<K>(g, b, level, rings, sl, x, y, z, top, k, eps, n3, c3, nullptr))
+        if (normal_two_pass<K, RINGS>(g, b, level, sl, x, y, z, top, k, eps, n3, c3, nullptr))
         {
             nrow[0] = n3[0], nrow[1] = n3[1], nrow[2] = n3[2];
             if (crow)
@@ -168,9 +168,9 @@ __device__ __forceinline__ void knn_finish(const GridView& g, const BlockGeom& b
     }
 }
 
-template <int K, int MODE>
+template <int K, int MODE, int RINGS>
 __global__ void __launch_bounds__(kQBlock, min_blocks_for(K)) knn_main_kernel(
-    GridView g, QueryBatch qb, uint32_t k, float eps, SearchPlan plan, KnnOutputs out)
+    GridView g, QueryBatch qb, uint32_t k, float eps, int level, KnnOutputs out)
 {
     uint32_t const t = blockIdx.x * kQBlock + threadIdx.x;
     float x, y, z;
@@ -180,19 +180,17 @@ __global__ void __launch_bounds__(kQBlock, min_blocks_for(K)) knn_main_kernel(
     TopD<K> top;
     BlockGeom b;
     CellList cl;
-    ShortList sl;
+    ShortListFor<K> sl;
     QueryCell const qc = query_cell(g, x, y, z);
-    if (knn_attempt_dist<K>(g, qc, plan.level, plan.rings, x, y, z, k, eps, top, b, cl, sl,
-                            nullptr))
-        knn_finish<K, MODE>(g, b, plan.level, plan.rings, sl, x, y, z, top, k, eps, row, out);
+    if (knn_attempt_dist<K, RINGS>(g, qc, level, x, y, z, k, eps, top, b, cl, sl, nullptr))
+        knn_finish<K, MODE, RINGS>(g, b, level, sl, x, y, z, top, k, eps, row, out);
     else
         out.retry_items[atomicAdd(out.retry_count, 1u)] = t;
 }
 
-template <int K, int MODE>
+template <int K, int MODE, int RINGS>
 __global__ void __launch_bounds__(kQBlock) knn_retry_kernel(GridView g, QueryBatch qb, uint32_t k,
-                                                            float eps, SearchPlan plan,
-                                                            KnnOutputs out)
+                                                            float eps, int level, KnnOutputs out)
 {
     uint32_t const n_retry = *out.retry_count;
     for (uint32_t i = blockIdx.x * kQBlock + threadIdx.x; i < n_retry; i += gridDim.x * kQBlock)
@@ -203,11 +201,11 @@ __global__ void __launch_bounds__(kQBlock) knn_retry_kernel(GridView g, QueryBat
         TopD<K> top;
         BlockGeom b;
         CellList cl;
-        ShortList sl;
+        ShortListFor<K> sl;
         // same ring count, one level coarser each time
-        SearchPlan const next{plan.level > 0 ? plan.level - 1 : 0, plan.rings};
-        int const found = knn_search_dist<K>(g, x, y, z, k, eps, next, top, b, cl, sl, nullptr);
-        knn_finish<K, MODE>(g, b, found, plan.rings, sl, x, y, z, top, k, eps, row, out);
+        int const found = knn_search_dist<K, RINGS>(g, x, y, z, k, eps, level > 0 ? level - 1 : 0,
+                                                    top, b, cl, sl, nullptr);
+        knn_finish<K, MODE, RINGS>(g, b, found, sl, x, y, z, top, k, eps, row, out);
     }
 }
 
@@ -295,9 +293,9 @@ __global__ void __launch_bounds__(kQBlock) rows_to_mean_kernel(
 }
 
 // ---- instrumentation: what the search does per query ---------------------------------------
-template <int K>
+template <int K, int RINGS>
 __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
-    GridView g, QueryBatch qb, uint32_t k, float eps, SearchPlan plan,
+    GridView g, QueryBatch qb, uint32_t k, float eps, int level,
     unsigned long long* __restrict__ stats4)
 {
     float x, y, z;
@@ -309,8 +307,8 @@ __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
         TopD<K> top;
         BlockGeom b;
         CellList cl;
-        ShortList sl;
-        knn_search_dist<K>(g, x, y, z, k, eps, plan, top, b, cl, sl, &st);
+        ShortListFor<K> sl;
+        knn_search_dist<K, RINGS>(g, x, y, z, k, eps, level, top, b, cl, sl, &st);
     }
     uint32_t const warp_max = __reduce_max_sync(0xFFFFFFFFu, st.candidates);
     unsigned long long v[4] = {st.candidates, st.lookups, st.attempts,
@@ -680,11 +678,22 @@ static void launch_knn_shaped(const pcpx_index& ix, const QueryBatch& qb, uint32
     out.retry_count   = retry_count.get();
     dim3 const grid(grid_for(qb.nq, kQBlock));
     dim3 const retry_grid(std::min<uint32_t>(grid.x, 148u * 16u));
-    PCPX_DISPATCH_K(kr, (knn_main_kernel<KK, MODE><<<grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, plan, out)));
-    PCPX_CHECK_LAUNCH();
-    PCPX_DISPATCH_K(kr, (knn_retry_kernel<KK, MODE><<<retry_grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, plan, out)));
+    if (plan.rings >= 2)
+    {
+        PCPX_DISPATCH_K(kr, (knn_main_kernel<KK, MODE, 2><<<grid, kQBlock, 0, ix.stream>>>(
+                                ix.grid, qb, k, eps, plan.level, out)));
+        PCPX_CHECK_LAUNCH();
+        PCPX_DISPATCH_K(kr, (knn_retry_kernel<KK, MODE, 2><<<retry_grid, kQBlock, 0, ix.stream>>>(
+                                ix.grid, qb, k, eps, plan.level, out)));
+    }
+    else
+    {
+        PCPX_DISPATCH_K(kr, (knn_main_kernel<KK, MODE, 1><<<grid, kQBlock, 0, ix.stream>>>(
+                                ix.grid, qb, k, eps, plan.level, out)));
+        PCPX_CHECK_LAUNCH();
+        PCPX_DISPATCH_K(kr, (knn_retry_kernel<KK, MODE, 1><<<retry_grid, kQBlock, 0, ix.stream>>>(
+                                ix.grid, qb, k, eps, plan.level, out)));
+    }
     PCPX_CHECK_LAUNCH();
     if (launches)
         *launches += 2;
@@ -742,8 +751,16 @@ void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long
     uint32_t const kr     = (uint32_t)list_size_for(k);
     SearchPlan const plan = plan_for(ix, k);
     dim3 const grid(grid_for(qb.nq, kQBlock));
-    PCPX_DISPATCH_K(kr, (knn_stats_kernel<KK><<<grid, kQBlock, 0, ix.stream>>>(
-                            ix.grid, qb, k, eps, plan, stats4)));
+    if (plan.rings >= 2)
+    {
+        PCPX_DISPATCH_K(kr, (knn_stats_kernel<KK, 2><<<grid, kQBlock, 0, ix.stream>>>(
+                                ix.grid, qb, k, eps, plan.level, stats4)));
+    }
+    else
+    {
+        PCPX_DISPATCH_K(kr, (knn_stats_kernel<KK, 1><<<grid, kQBlock, 0, ix.stream>>>(
+                                ix.grid, qb, k, eps, plan.level, stats4)));
+    }
     PCPX_CHECK_LAUNCH();
 }
 

@@ -135,7 +135,7 @@ void* emu_index_create(const float* xyz, size_t n, int use_box, const float* box
     std::vector<uint64_t> lh(kMaxLevel + 2, 0);
     for (uint32_t i = 0; i < g.n; ++i)
         lh[boundary(i)]++;
-    double min_occ = min_occ_in ? (double)min_occ_in : 2.0;
+    double min_occ = min_occ_in ? (double)min_occ_in : 4.0;
     uint64_t cells = 0, total = 0;
     g.lfine = 0;
     for (int l = 0; l <= g.lcap; ++l)
@@ -235,21 +235,25 @@ static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float 
         bool done = false;
         if (mode == 0)
         {
-            TopD<K> top;
-            BlockGeom b;
-            CellList cl;
-            ShortList sl;
             // main pass: one attempt of the plan; otherwise the retry pass walks coarser
-            int level = plan.level;
-            if (!knn_attempt_dist<K>(ix->g, query_cell(ix->g, x, y, z), plan.level, plan.rings, x,
-                                     y, z, k, eps, top, b, cl, sl, &st))
-                level = knn_search_dist<K>(ix->g, x, y, z, k, eps,
-                                           SearchPlan{plan.level > 0 ? plan.level - 1 : 0,
-                                                      plan.rings},
-                                           top, b, cl, sl, &st);
-            done = knn_two_pass_emit<K>(ix->g, b, level, plan.rings, sl, x, y, z, top, k, eps,
-                                        idx + row * k, d2 ? d2 + row * k : nullptr,
-                                        cnt ? cnt + row : nullptr);
+            auto run = [&](auto rings_tag) {
+                constexpr int R = decltype(rings_tag)::value;
+                TopD<K> top;
+                BlockGeom b;
+                CellList cl;
+                ShortListFor<K> sl;
+                int level = plan.level;
+                if (!knn_attempt_dist<K, R>(ix->g, query_cell(ix->g, x, y, z), plan.level, x, y, z,
+                                            k, eps, top, b, cl, sl, &st))
+                    level = knn_search_dist<K, R>(ix->g, x, y, z, k, eps,
+                                                  plan.level > 0 ? plan.level - 1 : 0, top, b, cl,
+                                                  sl, &st);
+                return knn_two_pass_emit<K, R>(ix->g, b, level, sl, x, y, z, top, k, eps,
+                                               idx + row * k, d2 ? d2 + row * k : nullptr,
+                                               cnt ? cnt + row : nullptr);
+            };
+            done = plan.rings >= 2 ? run(std::integral_constant<int, 2>{})
+                                   : run(std::integral_constant<int, 1>{});
             if (!done && st4)
                 st4[3] += 1; // retries
         }
@@ -346,17 +350,22 @@ static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, fl
         fetch(ix, q, i, x, y, z, row);
         float n3[3], c3[3];
         TopD<K> top;
-        BlockGeom b;
-        CellList cl;
-        ShortList sl;
-        int level = plan.level;
-        if (!knn_attempt_dist<K>(ix->g, query_cell(ix->g, x, y, z), plan.level, plan.rings, x, y,
-                                 z, k, eps, top, b, cl, sl, nullptr))
-            level = knn_search_dist<K>(ix->g, x, y, z, k, eps,
-                                       SearchPlan{plan.level > 0 ? plan.level - 1 : 0, plan.rings},
-                                       top, b, cl, sl, nullptr);
-        bool ok = mode == 0 && normal_two_pass<K>(ix->g, b, level, plan.rings, sl, x, y, z, top, k,
-                                                  eps, n3, c3, nullptr);
+        auto run = [&](auto rings_tag) {
+            constexpr int R = decltype(rings_tag)::value;
+            BlockGeom b;
+            CellList cl;
+            ShortListFor<K> sl;
+            int level = plan.level;
+            if (!knn_attempt_dist<K, R>(ix->g, query_cell(ix->g, x, y, z), plan.level, x, y, z, k,
+                                        eps, top, b, cl, sl, nullptr))
+                level = knn_search_dist<K, R>(ix->g, x, y, z, k, eps,
+                                              plan.level > 0 ? plan.level - 1 : 0, top, b, cl, sl,
+                                              nullptr);
+            return mode == 0 &&
+                   normal_two_pass<K, R>(ix->g, b, level, sl, x, y, z, top, k, eps, n3, c3, nullptr);
+        };
+        bool ok = plan.rings >= 2 ? run(std::integral_constant<int, 2>{})
+                                  : run(std::integral_constant<int, 1>{});
         if (!ok)
         {
             TopK<exact_k(K)> ids;

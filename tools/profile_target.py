@@ -23,7 +23,8 @@ def main():
     xyz = pcpx.synth.noisy_plane(n)
     d_xyz = torch.from_numpy(xyz).cuda()
     torch.cuda.synchronize()
-    ix = pcpx.Index(d_xyz)
+    ix = pcpx.Index(d_xyz, min_cell_occupancy=int(os.environ.get('PCPX_MIN_OCC', '0')))
+    print('finest level', ix.info()['finest_level'], 'cells', ix.info()['n_cells'])
     d_nrm = torch.empty((n, 3), dtype=torch.float32, device="cuda")
     d_idx = torch.empty((n, k), dtype=torch.int32, device="cuda")
     d_cnt = torch.empty((n,), dtype=torch.int32, device="cuda")
