@@ -295,6 +295,28 @@ def run_ours(args):
                 "note": "gather-model bytes (12 + 12k + 12 per normal); the kernel is "
                         "instruction-issue bound, DRAM traffic sits far below this figure"}
 
+    # untimed: the halo is wide enough iff every owned point near an inner slab face has its k
+    # nearest neighbours inside the local cloud, i.e. at least k + 1 local points (itself
+    # included) within its distance to the outer face of the halo
+    halo_ok = True
+    if world > 1:
+        L = pcpx.synth.plane_extent(N_POINTS)
+        own = xyz[:n_owned]
+        lo_gap = own[:, 0] - np.float32(rank * L - HALO) if rank > 0 else None
+        hi_gap = np.float32((rank + 1) * L + HALO) - own[:, 0] if rank < world - 1 else None
+        gap = np.full(n_owned, np.inf, np.float32)
+        if lo_gap is not None:
+            gap = np.minimum(gap, lo_gap)
+        if hi_gap is not None:
+            gap = np.minimum(gap, hi_gap)
+        near = np.flatnonzero(gap < 4 * HALO)
+        with pcpx.Index(d_xyz, device=local_rank) as ix:
+            cnt = ix.radius_count(own[near], 0.0, radii=(gap[near] * np.float32(0.999)))
+        halo_ok = bool((cnt >= K + 1).all())
+        t = torch.tensor([1 if halo_ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        halo_ok = bool(t.item())
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_step(xyz, K, args.ref_sample)
@@ -326,6 +348,7 @@ def run_ours(args):
                              "sort": float(np.mean(stats["sort_ms"])),
                              "normals_kernel": float(np.mean(stats["kernel_ms"]))},
             "exact_fallback_queries_per_step": float(np.mean(stats["retries"])),
+            "halo_sufficient": halo_ok,
         }
         print(json.dumps(line))
     if world > 1:
