@@ -531,47 +531,62 @@ PCPX_HD int knn_search_dist(const GridView& g, float qx, float qy, float qz, uin
     return l;
 }
 
-// Pass 2.  f(point, sorted position, d2, dx, dy, dz) for every eligible point with d2 <= tau:
-// over the short list when it is complete, else over the whole block again.
-template <int RINGS, class SL, class F>
-PCPX_HD void for_each_within(const GridView& g, const BlockGeom& b, int level, const SL& sl,
-                             float qx, float qy, float qz, float tau, float eps, F&& f)
+// Where a finished pass 1 looked: pass 2 walks the same region again when the short list
+// overflowed.  walk(g, q, tau, eps, f) calls f(point, position, d2, dx, dy, dz) for every
+// eligible point of the region with d2 <= tau.
+template <class F>
+PCPX_HD void offer_within(const float4& c, uint32_t p, float qx, float qy, float qz, float tau,
+                          float eps, F&& f)
+{
+    float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
+    float const d2 = sqdist_x(dx, dy, dz);
+    bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
+    if (!excluded && d2 <= tau)
+        f(c, p, d2, dx, dy, dz);
+}
+
+template <int RINGS>
+struct BlockRegion
+{
+    BlockGeom b;
+    int level;
+
+    template <class F>
+    PCPX_HD void walk(const GridView& g, float qx, float qy, float qz, float tau, float eps,
+                      F&& f) const
+    {
+        uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
+        int const i_end     = RINGS >= 2 ? kRing2End : kRing1End;
+#pragma unroll 1
+        for (int i = 0; i < i_end; ++i)
+        {
+            Offset3 const o = ring_offset(i);
+            if (outside_block(b, o.dx, o.dy, o.dz) || cell_lb2(b, o.dx, o.dy, o.dz) > tau)
+                continue;
+            uint32_t start, count;
+            if (!find_cell(g, key0 + key_delta(o.dx, o.dy, o.dz), start, count))
+                continue;
+            for (uint32_t p = start; p < start + count; ++p)
+                offer_within(load_pt(g.pts + p), p, qx, qy, qz, tau, eps, f);
+        }
+    }
+};
+
+// Pass 2: over the short list when it is complete, else over the region again.
+template <class Region, class SL, class F>
+PCPX_HD void for_each_within(const GridView& g, const Region& region, const SL& sl, float qx,
+                             float qy, float qz, float tau, float eps, F&& f)
 {
     if (!sl.overflow)
     {
         for (uint32_t j = 0; j < sl.n; ++j)
         {
             uint32_t const p = sl.pos[j];
-            float4 const c   = load_pt(g.pts + p);
-            float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
-            float const d2 = sqdist_x(dx, dy, dz);
-            bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
-            if (!excluded && d2 <= tau)
-                f(c, p, d2, dx, dy, dz);
+            offer_within(load_pt(g.pts + p), p, qx, qy, qz, tau, eps, f);
         }
         return;
     }
-    uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
-    int const i_end     = RINGS >= 2 ? kRing2End : kRing1End;
-#pragma unroll 1
-    for (int i = 0; i < i_end; ++i)
-    {
-        Offset3 const o = ring_offset(i);
-        if (outside_block(b, o.dx, o.dy, o.dz) || cell_lb2(b, o.dx, o.dy, o.dz) > tau)
-            continue;
-        uint32_t start, count;
-        if (!find_cell(g, key0 + key_delta(o.dx, o.dy, o.dz), start, count))
-            continue;
-        for (uint32_t p = start; p < start + count; ++p)
-        {
-            float4 const c = load_pt(g.pts + p);
-            float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
-            float const d2 = sqdist_x(dx, dy, dz);
-            bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
-            if (!excluded && d2 <= tau)
-                f(c, p, d2, dx, dy, dz);
-        }
-    }
+    region.walk(g, qx, qy, qz, tau, eps, f);
 }
 
 } // namespace pcpx

@@ -142,8 +142,8 @@ PCPX_HD float mean_distance(const TopK<K>& top, uint32_t k)
 // (common/normals/normal_estimation.hpp:50-52) up to fp32 rounding — far inside the 1e-4
 // |cos| tolerance.  Returns false when more than k points lie within the k-th distance (a
 // bit-equal tie across the boundary): the caller then decides membership by original index.
-template <int K, int RINGS, class SL>
-PCPX_HD bool normal_two_pass(const GridView& g, const BlockGeom& b, int level, const SL& sl,
+template <int K, class Region, class SL>
+PCPX_HD bool normal_two_pass(const GridView& g, const Region& region, const SL& sl,
                              float qx, float qy, float qz,
                              const TopD<K>& top, uint32_t k, float eps, float* n3,
                              float* centroid3, float* gap)
@@ -152,8 +152,8 @@ PCPX_HD bool normal_two_pass(const GridView& g, const BlockGeom& b, int level, c
     uint32_t n      = 0;
     float s1x = 0.f, s1y = 0.f, s1z = 0.f;
     Sym3 s2{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for_each_within<RINGS>(g, b, level, sl, qx, qy, qz, tau, eps,
-                           [&](float4 const&, uint32_t, float, float dx, float dy, float dz) {
+    for_each_within(g, region, sl, qx, qy, qz, tau, eps,
+                    [&](float4 const&, uint32_t, float, float dx, float dy, float dz) {
                         ++n;
                         s1x += dx, s1y += dy, s1z += dz;
                         s2.xx += dx * dx, s2.xy += dx * dy, s2.xz += dx * dz;
@@ -176,8 +176,8 @@ PCPX_HD bool normal_two_pass(const GridView& g, const BlockGeom& b, int level, c
 
 // Second pass of the kNN kernel: every neighbour goes straight to its rank in the output row.
 // Returns false when ranks are ambiguous (bit-equal distances); nothing written then is final.
-template <int K, int RINGS, class SL>
-PCPX_HD bool knn_two_pass_emit(const GridView& g, const BlockGeom& b, int level, const SL& sl,
+template <int K, class Region, class SL>
+PCPX_HD bool knn_two_pass_emit(const GridView& g, const Region& region, const SL& sl,
                                float qx, float qy, float qz,
                                const TopD<K>& top, uint32_t k, float eps, uint32_t* idx_row,
                                float* d2_row, uint32_t* out_count)
@@ -186,8 +186,8 @@ PCPX_HD bool knn_two_pass_emit(const GridView& g, const BlockGeom& b, int level,
         return false;
     float const tau = top.kth(k);
     uint32_t n      = 0;
-    for_each_within<RINGS>(g, b, level, sl, qx, qy, qz, tau, eps,
-                           [&](float4 const& c, uint32_t, float d2, float, float, float) {
+    for_each_within(g, region, sl, qx, qy, qz, tau, eps,
+                    [&](float4 const& c, uint32_t, float d2, float, float, float) {
                         uint32_t const r = top.rank_of(d2);
                         if (r < k)
                         {

@@ -9,6 +9,7 @@
 #include "plan.hpp"
 #include "query.hpp"
 #include "radius_core.cuh"
+#include "tree_core.cuh"
 
 namespace pcpx {
 
@@ -124,8 +125,8 @@ __device__ __noinline__ void normal_exact(const GridView& g, float x, float y, f
 }
 
 // second pass + output of one query whose first pass is final
-template <int K, int MODE, int RINGS, class SL>
-__device__ __forceinline__ void knn_finish(const GridView& g, const BlockGeom& b, int level,
+template <int K, int MODE, class Region, class SL>
+__device__ __forceinline__ void knn_finish(const GridView& g, const Region& region, int level,
                                            const SL& sl, float x, float y, float z,
                                            const TopD<K>& top, uint32_t k, float eps,
                                            uint32_t row, const KnnOutputs& out)
@@ -139,8 +140,7 @@ __device__ __forceinline__ void knn_finish(const GridView& g, const BlockGeom& b
         uint32_t* idx_row = out.idx + (size_t)row * k;
         float* d2_row     = out.d2 ? out.d2 + (size_t)row * k : nullptr;
         uint32_t* cnt     = out.count ? out.count + row : nullptr;
-        if (!knn_two_pass_emit<K, RINGS>(g, b, level, sl, x, y, z, top, k, eps, idx_row, d2_row,
-                                         cnt))
+        if (!knn_two_pass_emit<K>(g, region, sl, x, y, z, top, k, eps, idx_row, d2_row, cnt))
         {
             knn_exact_row<K>(g, x, y, z, k, eps, level, idx_row, d2_row, cnt);
             if (out.exact_counter)
@@ -152,7 +152,7 @@ __device__ __forceinline__ void knn_finish(const GridView& g, const BlockGeom& b
         float* nrow = out.normal + 3 * (size_t)row;
         float* crow = out.centroid ? out.centroid + 3 * (size_t)row : nullptr;
         float n3[3], c3[3];
-        if (normal_two_pass<K, RINGS>(g, b, level, sl, x, y, z, top, k, eps, n3, c3, nullptr))
+        if (normal_two_pass<K>(g, region, sl, x, y, z, top, k, eps, n3, c3, nullptr))
         {
             nrow[0] = n3[0], nrow[1] = n3[1], nrow[2] = n3[2];
             if (crow)
@@ -183,11 +183,16 @@ __global__ void __launch_bounds__(kQBlock, min_blocks_for(K)) knn_main_kernel(
     ShortListFor<K> sl;
     QueryCell const qc = query_cell(g, x, y, z);
     if (knn_attempt_dist<K, RINGS>(g, qc, level, x, y, z, k, eps, top, b, cl, sl, nullptr))
-        knn_finish<K, MODE, RINGS>(g, b, level, sl, x, y, z, top, k, eps, row, out);
+        knn_finish<K, MODE>(g, BlockRegion<RINGS>{b, level}, level, sl, x, y, z, top, k, eps, row,
+                            out);
     else
         out.retry_items[atomicAdd(out.retry_count, 1u)] = t;
 }
 
+// The queries the main pass could not finish.  A near miss (the k-ball pokes just past the
+// block) is usually final one level coarser, which is cheap; what is still open after that —
+// sparse regions, outliers — descends the octree (tree_core.cuh) instead of trying ever coarser
+// blocks whose cells hold thousands of points.
 template <int K, int MODE, int RINGS>
 __global__ void __launch_bounds__(kQBlock) knn_retry_kernel(GridView g, QueryBatch qb, uint32_t k,
                                                             float eps, int level, KnnOutputs out)
@@ -199,13 +204,26 @@ __global__ void __launch_bounds__(kQBlock) knn_retry_kernel(GridView g, QueryBat
         uint32_t row;
         fetch_query(g, qb, out.retry_items[i], x, y, z, row);
         TopD<K> top;
-        BlockGeom b;
-        CellList cl;
         ShortListFor<K> sl;
-        // same ring count, one level coarser each time
-        int const found = knn_search_dist<K, RINGS>(g, x, y, z, k, eps, level > 0 ? level - 1 : 0,
-                                                    top, b, cl, sl, nullptr);
-        knn_finish<K, MODE, RINGS>(g, b, found, sl, x, y, z, top, k, eps, row, out);
+        bool done = false;
+        if (level > 0)
+        {
+            BlockGeom b;
+            CellList cl;
+            int const coarser = level - 1;
+            if (knn_attempt_dist<K, RINGS>(g, query_cell(g, x, y, z), coarser, x, y, z, k, eps,
+                                           top, b, cl, sl, nullptr))
+            {
+                knn_finish<K, MODE>(g, BlockRegion<RINGS>{b, coarser}, coarser, sl, x, y, z, top,
+                                    k, eps, row, out);
+                done = true;
+            }
+        }
+        if (!done)
+        {
+            knn_tree_dist<K>(g, x, y, z, eps, top, sl, nullptr);
+            knn_finish<K, MODE>(g, TreeRegion{}, level, sl, x, y, z, top, k, eps, row, out);
+        }
     }
 }
 
@@ -308,7 +326,11 @@ __global__ void __launch_bounds__(kQBlock) knn_stats_kernel(
         BlockGeom b;
         CellList cl;
         ShortListFor<K> sl;
-        knn_search_dist<K, RINGS>(g, x, y, z, k, eps, level, top, b, cl, sl, &st);
+        QueryCell const qc = query_cell(g, x, y, z);
+        if (!knn_attempt_dist<K, RINGS>(g, qc, level, x, y, z, k, eps, top, b, cl, sl, &st) &&
+            !(level > 0 &&
+              knn_attempt_dist<K, RINGS>(g, qc, level - 1, x, y, z, k, eps, top, b, cl, sl, &st)))
+            knn_tree_dist<K>(g, x, y, z, eps, top, sl, &st);
     }
     uint32_t const warp_max = __reduce_max_sync(0xFFFFFFFFu, st.candidates);
     unsigned long long v[4] = {st.candidates, st.lookups, st.attempts,
@@ -683,14 +705,20 @@ static void launch_knn_shaped(const pcpx_index& ix, const QueryBatch& qb, uint32
         PCPX_DISPATCH_K(kr, (knn_main_kernel<KK, MODE, 2><<<grid, kQBlock, 0, ix.stream>>>(
                                 ix.grid, qb, k, eps, plan.level, out)));
         PCPX_CHECK_LAUNCH();
-        PCPX_DISPATCH_K(kr, (knn_retry_kernel<KK, MODE, 2><<<retry_grid, kQBlock, 0, ix.stream>>>(
-                                ix.grid, qb, k, eps, plan.level, out)));
     }
     else
     {
         PCPX_DISPATCH_K(kr, (knn_main_kernel<KK, MODE, 1><<<grid, kQBlock, 0, ix.stream>>>(
                                 ix.grid, qb, k, eps, plan.level, out)));
         PCPX_CHECK_LAUNCH();
+    }
+    if (plan.rings >= 2)
+    {
+        PCPX_DISPATCH_K(kr, (knn_retry_kernel<KK, MODE, 2><<<retry_grid, kQBlock, 0, ix.stream>>>(
+                                ix.grid, qb, k, eps, plan.level, out)));
+    }
+    else
+    {
         PCPX_DISPATCH_K(kr, (knn_retry_kernel<KK, MODE, 1><<<retry_grid, kQBlock, 0, ix.stream>>>(
                                 ix.grid, qb, k, eps, plan.level, out)));
     }

@@ -16,6 +16,7 @@
 #include "plan.hpp"
 #include "normals_core.cuh"
 #include "radius_core.cuh"
+#include "tree_core.cuh"
 
 using namespace pcpx;
 
@@ -242,15 +243,22 @@ static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float 
                 BlockGeom b;
                 CellList cl;
                 ShortListFor<K> sl;
-                int level = plan.level;
-                if (!knn_attempt_dist<K, R>(ix->g, query_cell(ix->g, x, y, z), plan.level, x, y, z,
-                                            k, eps, top, b, cl, sl, &st))
-                    level = knn_search_dist<K, R>(ix->g, x, y, z, k, eps,
-                                                  plan.level > 0 ? plan.level - 1 : 0, top, b, cl,
-                                                  sl, &st);
-                return knn_two_pass_emit<K, R>(ix->g, b, level, sl, x, y, z, top, k, eps,
-                                               idx + row * k, d2 ? d2 + row * k : nullptr,
-                                               cnt ? cnt + row : nullptr);
+                uint32_t* irow = idx + row * k;
+                float* drow    = d2 ? d2 + row * k : nullptr;
+                uint32_t* crow = cnt ? cnt + row : nullptr;
+                if (knn_attempt_dist<K, R>(ix->g, query_cell(ix->g, x, y, z), plan.level, x, y, z,
+                                           k, eps, top, b, cl, sl, &st))
+                    return knn_two_pass_emit<K>(ix->g, BlockRegion<R>{b, plan.level}, sl, x, y, z,
+                                                top, k, eps, irow, drow, crow);
+                // the retry pass: one level coarser, then the octree descent
+                if (plan.level > 0 &&
+                    knn_attempt_dist<K, R>(ix->g, query_cell(ix->g, x, y, z), plan.level - 1, x, y,
+                                           z, k, eps, top, b, cl, sl, &st))
+                    return knn_two_pass_emit<K>(ix->g, BlockRegion<R>{b, plan.level - 1}, sl, x, y,
+                                                z, top, k, eps, irow, drow, crow);
+                knn_tree_dist<K>(ix->g, x, y, z, eps, top, sl, &st);
+                return knn_two_pass_emit<K>(ix->g, TreeRegion{}, sl, x, y, z, top, k, eps, irow,
+                                            drow, crow);
             };
             done = plan.rings >= 2 ? run(std::integral_constant<int, 2>{})
                                    : run(std::integral_constant<int, 1>{});
@@ -355,14 +363,18 @@ static void normals_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, fl
             BlockGeom b;
             CellList cl;
             ShortListFor<K> sl;
-            int level = plan.level;
-            if (!knn_attempt_dist<K, R>(ix->g, query_cell(ix->g, x, y, z), plan.level, x, y, z, k,
-                                        eps, top, b, cl, sl, nullptr))
-                level = knn_search_dist<K, R>(ix->g, x, y, z, k, eps,
-                                              plan.level > 0 ? plan.level - 1 : 0, top, b, cl, sl,
-                                              nullptr);
+            if (knn_attempt_dist<K, R>(ix->g, query_cell(ix->g, x, y, z), plan.level, x, y, z, k,
+                                       eps, top, b, cl, sl, nullptr))
+                return mode == 0 && normal_two_pass<K>(ix->g, BlockRegion<R>{b, plan.level}, sl, x,
+                                                       y, z, top, k, eps, n3, c3, nullptr);
+            if (plan.level > 0 &&
+                knn_attempt_dist<K, R>(ix->g, query_cell(ix->g, x, y, z), plan.level - 1, x, y, z,
+                                       k, eps, top, b, cl, sl, nullptr))
+                return mode == 0 && normal_two_pass<K>(ix->g, BlockRegion<R>{b, plan.level - 1}, sl,
+                                                       x, y, z, top, k, eps, n3, c3, nullptr);
+            knn_tree_dist<K>(ix->g, x, y, z, eps, top, sl, nullptr);
             return mode == 0 &&
-                   normal_two_pass<K, R>(ix->g, b, level, sl, x, y, z, top, k, eps, n3, c3, nullptr);
+                   normal_two_pass<K>(ix->g, TreeRegion{}, sl, x, y, z, top, k, eps, n3, c3, nullptr);
         };
         bool ok = plan.rings >= 2 ? run(std::integral_constant<int, 2>{})
                                   : run(std::integral_constant<int, 1>{});
