@@ -468,10 +468,10 @@ PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, floa
         }
         float const d0 = candidate_d2(a0, qx, qy, qz, eps);
         float const d1 = has1 ? candidate_d2(a1, qx, qy, qz, eps) : INFINITY;
-        float const w  = top.worst();
-        if (d0 <= w && d0 < INFINITY)
+        float const w = fminf(top.worst(), 3.402823466e+38f); // finite: +inf (excluded) never passes
+        if (d0 <= w)
             sl.push(p);
-        if (d1 <= w && d1 < INFINITY)
+        if (d1 <= w)
             sl.push(p + 1);
         top.insert2(d0, d1);
         if (st)
