@@ -70,7 +70,8 @@ def recorded_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region"""
+    """nvidia-smi clocks + throttle reasons DURING the timed region: one long-running
+    `nvidia-smi -lms 50` whose lines are collected while the context is open."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -79,32 +80,47 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.samples = []
-        self.stop = threading.Event()
-        self.t = threading.Thread(target=self.run, daemon=True)
+        self.proc = None
+        self.t = None
 
-    def run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) >= 9:
+                self.samples.append(f)
 
     def __enter__(self):
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+            time.sleep(0.3)  # let the first samples arrive before the load starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.t.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            if self.t is not None:
+                self.t.join(timeout=5)
 
     def summary(self):
-        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
-        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+
+        sm = [num(s[1]) for s in self.samples if num(s[1]) is not None]
+        mx = [num(s[2]) for s in self.samples if num(s[2]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:

@@ -433,6 +433,12 @@ PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, floa
     int e = 0;                // next span to enter
     uint32_t p = 0, pend = 0; // position inside the current span
     float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+    // the next span's record is fetched from local memory one span ahead, so that entering it
+    // does not wait on the load
+    float nlb    = 0.f;
+    uint32_t ns = 0, nen = 0;
+    if (cl.n > 0)
+        nlb = cl.lb2[0], ns = cl.start[0], nen = cl.end[0];
     for (;;)
     {
         bool done = false;
@@ -440,15 +446,17 @@ PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, floa
         {
             for (;;)
             {
-                if (e == cl.n)
+                if (e >= cl.n)
                 {
                     done = true;
                     break;
                 }
-                float const lb    = cl.lb2[e];
-                uint32_t const s  = cl.start[e];
-                uint32_t const en = cl.end[e];
+                float const lb    = nlb;
+                uint32_t const s  = ns;
+                uint32_t const en = nen;
                 ++e;
+                if (e < cl.n)
+                    nlb = cl.lb2[e], ns = cl.start[e], nen = cl.end[e];
                 if (lb > top.worst()) // equal: a tie may hide there
                     continue;
                 p = s, pend = en;
