@@ -21,8 +21,9 @@ sort -> cell tables) + the fused kNN -> PCA normal kernel over all of its points
           estimate_normal, on this box's host cores, on a bounded sample (rank 0, N = 1 only).
 
 N > 1 ("weak"): every rank owns one 10 M-point slab of an N x 10 M-point plane plus a 0.05-wide
-halo of its neighbours' points (point-cloud-processing_b200/sharding.py); no data-path
-collective; value = N x 10 M normals / max-over-ranks time.
+halo of its neighbours' points; the halo strips are exchanged between neighbouring ranks over
+NCCL inside every timed step (point-cloud-processing_b200/sharding.py: exchange_halo) — the one
+real exchange of the sharded path; value = N x 10 M normals / max-over-ranks time.
 
 --impl reference: times the reference's CPU implementation of the same step (full-size octree
 build + a bounded query sample, extrapolated linearly) on all host threads; rank 0 only.
@@ -157,26 +158,12 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
-def slab_cloud(pcpx, rank, world):
-    """this rank's slab of the world x 10 M plane (+ halo of the neighbouring slabs)"""
+def own_slab(pcpx, rank):
+    """this rank's 10 M-point slab of the world x 10 M plane: x in [rank L, (rank + 1) L)"""
     L = pcpx.synth.plane_extent(N_POINTS)
-
-    def slab(r):
-        pts = pcpx.synth.noisy_plane(N_POINTS, seed=7 + r, extent=L)
-        pts[:, 0] += np.float32(r * L)
-        return pts
-
-    own = slab(rank)
-    if world == 1:
-        return own, len(own)
-    parts = [own]
-    if rank > 0:
-        left = slab(rank - 1)
-        parts.append(left[left[:, 0] >= np.float32(rank * L - HALO)])
-    if rank < world - 1:
-        right = slab(rank + 1)
-        parts.append(right[right[:, 0] <= np.float32((rank + 1) * L + HALO)])
-    return np.ascontiguousarray(np.concatenate(parts, 0)), len(own)
+    pts = pcpx.synth.noisy_plane(N_POINTS, seed=7 + rank, extent=L)
+    pts[:, 0] += np.float32(rank * L)
+    return pts, L
 
 
 # ------------------------------------------------------------------------------------------
@@ -267,12 +254,23 @@ def run_ours(args):
     pcpx = importlib.import_module("point-cloud-processing_b200")
     pcpx.lib()  # fail loudly now if the CUDA library is missing
 
-    xyz, n_owned = slab_cloud(pcpx, rank, world)
-    n_local = len(xyz)
+    xyz, L = own_slab(pcpx, rank)
+    n_owned = len(xyz)
     h_xyz = torch.from_numpy(xyz).pin_memory()
-    d_xyz = h_xyz.cuda()
+    d_own = h_xyz.cuda()
+    slab_lo, slab_hi = float(rank * L), float((rank + 1) * L)
+
+    def local_cloud(d_points):
+        """N > 1: the exchange step — boundary strips go to the neighbouring ranks over NCCL"""
+        if world == 1:
+            return d_points
+        return pcpx.sharding.exchange_halo(d_points, 0, slab_lo, slab_hi, HALO, rank, world,
+                                           dist)[0]
+
+    n_local = int(local_cloud(d_own).shape[0])
     d_nrm = torch.empty((n_local, 3), dtype=torch.float32, device="cuda")
     h_nrm = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
+    d_stage = torch.empty((n_owned, 3), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
 
     def barrier():
@@ -281,6 +279,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_resident(stats=None):
+        d_xyz = local_cloud(d_own)
+        torch.cuda.synchronize()  # the library runs on its own stream
         ix = pcpx.Index(d_xyz, device=local_rank)
         tb = ix.timings()
         ix.estimate_normals(None, K, out=d_nrm)
@@ -294,8 +294,14 @@ def run_ours(args):
             stats["retries"].append(tq["retry_queries"])
 
     def step_e2e():
-        ix = pcpx.Index(h_xyz.numpy(), device=local_rank)  # host pointer: H2D inside
-        ix.estimate_normals(None, K, out=h_nrm.numpy())  # host pointer: D2H inside
+        if world == 1:
+            ix = pcpx.Index(h_xyz.numpy(), device=local_rank)  # host pointer: H2D inside
+        else:
+            d_stage.copy_(h_xyz, non_blocking=True)  # H2D of the owned slab, then the exchange
+            d_xyz = local_cloud(d_stage)
+            torch.cuda.synchronize()
+            ix = pcpx.Index(d_xyz, device=local_rank)
+        ix.estimate_normals(None, K, out=h_nrm.numpy()[: ix.n])  # host pointer: D2H inside
         ix.close()
 
     def timed(fn, steps, warmup, stats=None):
@@ -342,8 +348,9 @@ def run_ours(args):
     # included) within its distance to the outer face of the halo
     halo_ok = True
     if world > 1:
-        L = pcpx.synth.plane_extent(N_POINTS)
-        own = xyz[:n_owned]
+        own = xyz
+        d_xyz = local_cloud(d_own)
+        torch.cuda.synchronize()
         lo_gap = own[:, 0] - np.float32(rank * L - HALO) if rank > 0 else None
         hi_gap = np.float32((rank + 1) * L + HALO) - own[:, 0] if rank < world - 1 else None
         gap = np.full(n_owned, np.inf, np.float32)
@@ -377,11 +384,11 @@ def run_ours(args):
                 "local_points": n_local,
                 "cache": "inputs larger than L2 (160 MB sorted float4 SoA + cell table vs 126 MB "
                          "L2); the index is rebuilt from scratch every step",
-                "parallelism": "one process per GPU, spatial slabs + halo, no data-path collective",
+                "parallelism": "one process per GPU, spatial slabs; halo strips exchanged with the neighbouring ranks over NCCL (isend/irecv) inside the timed step",
                 "numa_node_rank0": numa_node,
             },
             "e2e": {"value": e2e_value, "unit": "normals/s",
-                    "h2d_bytes_per_step": int(n_local * 12), "d2h_bytes_per_step": int(n_local * 12),
+                    "h2d_bytes_per_step": int(n_owned * 12), "d2h_bytes_per_step": int(n_local * 12),
                     "ms_per_step": dt_e2e / args.steps * 1e3},
             "gpu_launches": int(np.sum(stats["launches"])),
             "roofline": roofline,

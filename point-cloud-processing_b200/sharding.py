@@ -46,3 +46,42 @@ def query_slice(n, rank, world):
     b = n * rank // world
     e = n * (rank + 1) // world
     return b, e
+
+
+def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None):
+    """The one exchange step of the sharded path: every rank sends the points of its slab that
+    lie within `halo` of an inner face to the neighbour across that face and receives the
+    neighbour's strip (torch tensors on any device; NCCL moves device tensors over NVLink, gloo
+    CPU tensors in the tests).  Returns the local cloud [own ; from the left ; from the right]
+    and the number of owned points.  Strip sizes are exchanged first (two 8-byte messages)."""
+    import torch
+
+    c = own_xyz[:, axis]
+    send = {}
+    if rank > 0:
+        send[rank - 1] = own_xyz[c < lo + halo].contiguous()
+    if rank < world - 1:
+        send[rank + 1] = own_xyz[c > hi - halo].contiguous()
+    dev = own_xyz.device
+    sizes_out = {p: torch.tensor([t.shape[0]], dtype=torch.int64, device=dev) for p, t in send.items()}
+    sizes_in = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in send}
+    ops = []
+    for p in send:
+        ops.append(dist.P2POp(dist.isend, sizes_out[p], p, group))
+        ops.append(dist.P2POp(dist.irecv, sizes_in[p], p, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    recv = {p: torch.empty((int(sizes_in[p].item()), 3), dtype=own_xyz.dtype, device=dev)
+            for p in send}
+    ops = []
+    for p in send:
+        if send[p].shape[0]:
+            ops.append(dist.P2POp(dist.isend, send[p], p, group))
+        if recv[p].shape[0]:
+            ops.append(dist.P2POp(dist.irecv, recv[p], p, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    parts = [own_xyz] + [recv[p] for p in sorted(recv)]
+    return torch.cat(parts, 0), own_xyz.shape[0]

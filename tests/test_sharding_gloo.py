@@ -41,6 +41,13 @@ def _worker(rank, world, port, ret):
         edges = sh.slab_edges(0.0, L, world)
         halo = 0.05
         local, owned, gidx = sh.local_cloud(xyz, 0, edges, rank, halo)
+        # the same local cloud through the exchange step (what bench.py does over NCCL)
+        own_mask = sh.owner_of(xyz[:, 0], edges) == rank
+        exch, n_own = sh.exchange_halo(torch.from_numpy(xyz[own_mask]), 0, float(edges[rank]),
+                                       float(edges[rank + 1]), halo, rank, world, dist)
+        exch = exch.numpy()
+        same_set = (n_own == int(owned.sum()) and len(exch) == len(local) and np.array_equal(
+            exch[np.lexsort(exch.T)], local[np.lexsort(local.T)]))
         o = Oracle()
         idx, d2, cnt = o.cloud(local).knn(None, k, nthreads=2)
         ok = sh.halo_is_sufficient(local, owned, d2[:, k - 1], 0, edges, rank, halo)
@@ -52,7 +59,7 @@ def _worker(rank, world, port, ret):
         sizes = [torch.zeros(1, dtype=torch.long) for _ in range(world)]
         dist.all_gather(sizes, n_own)
         total = int(sum(int(s) for s in sizes))
-        ok_t = torch.tensor([1 if ok else 0])
+        ok_t = torch.tensor([1 if (ok and same_set) else 0])
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         gathered = [None] * world
         dist.all_gather_object(gathered, (g_rows, g_nbrs))
