@@ -13,11 +13,10 @@ namespace pcpx {
 
 constexpr uint64_t kEmptyEntry = 0xFFFFFFFFFFFFFFFFull;
 
-// What the low 32 bits of a list entry carry (and therefore what breaks distance ties).
+// What the low 32 bits of a 64-bit list entry carry (and therefore what breaks distance ties).
 enum TieId
 {
-    TIE_ORIGINAL_INDEX = 0, // the parity contract: (d2, original index)
-    TIE_SORTED_POSITION = 1 // (d2, position in the Morton-sorted array): cheap gathers
+    TIE_ORIGINAL_INDEX = 0 // the parity contract: (d2, original index)
 };
 
 struct SearchStats
@@ -127,7 +126,8 @@ PCPX_HD void offer(TopK<K>& top, const float4& c, uint32_t pos, float qx, float 
     float const d2 = sqdist_x(dx, dy, dz);
     // common/vector3d_queries.hpp:31-35,59-63: strict <, all three axes
     bool const excluded = fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps;
-    uint32_t const id   = TIE == TIE_ORIGINAL_INDEX ? f2u(c.w) : pos;
+    uint32_t const id   = f2u(c.w);
+    (void)pos;
     uint64_t const key  = ((uint64_t)f2u(d2) << 32) | id;
     if (!excluded && key < top.last())
         top.insert(key);
@@ -256,14 +256,6 @@ struct TopD
         for (int j = 0; j + 1 < K; ++j)
             t = t || ((uint32_t)(j + 1) < k && a[j] == a[j + 1] && a[j] < INFINITY);
         return t;
-    }
-    PCPX_HD uint32_t count_finite(uint32_t k) const
-    {
-        uint32_t n = 0;
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-            n += (uint32_t)j < k && a[j] < INFINITY;
-        return n;
     }
 };
 
@@ -524,19 +516,6 @@ PCPX_HD bool knn_attempt_dist(const GridView& g, const QueryCell& qc, int level,
         }
     }
     return level == 0 || top.kth(k) < (RINGS >= 2 ? b.block_lb2_r2 : b.block_lb2);
-}
-
-// Pass 1 walking to coarser levels until the answer is final.  Returns the final level.
-template <int K, int RINGS, class SL>
-PCPX_HD int knn_search_dist(const GridView& g, float qx, float qy, float qz, uint32_t k,
-                            float eps, int start_level, TopD<K>& top, BlockGeom& b, CellList& cl,
-                            SL& sl, SearchStats* st)
-{
-    QueryCell const qc = query_cell(g, qx, qy, qz);
-    int l              = start_level;
-    while (!knn_attempt_dist<K, RINGS>(g, qc, l, qx, qy, qz, k, eps, top, b, cl, sl, st))
-        --l;
-    return l;
 }
 
 // Where a finished pass 1 looked: pass 2 walks the same region again when the short list

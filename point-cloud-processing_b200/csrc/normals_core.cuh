@@ -6,41 +6,6 @@
 
 namespace pcpx {
 
-// common/normals/normal_estimation.hpp:41-77 on the neighbours whose SORTED POSITIONS are the
-// low words of top.a[0..k): fp32 mean (sum / n), centred un-normalised scatter, eigenvector of
-// the smallest eigenvalue.  Returns the number of neighbours used.
-template <int K>
-PCPX_HD uint32_t normal_from_positions(const GridView& g, const TopK<K>& top, uint32_t k,
-                                       float* n3, float* centroid3, float* gap)
-{
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    uint32_t n = 0;
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-        if ((uint32_t)j < k && top.a[j] != kEmptyEntry)
-        {
-            float4 const c = load_pt(g.pts + (uint32_t)top.a[j]);
-            sx += c.x, sy += c.y, sz += c.z;
-            ++n;
-        }
-    float const inv = 1.f / (float)n; // n == 0 -> inf, mean NaN like Eigen's empty mean()
-    float const mx = sx * inv, my = sy * inv, mz = sz * inv;
-    Sym3 m{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-        if ((uint32_t)j < k && top.a[j] != kEmptyEntry)
-        {
-            float4 const c = load_pt(g.pts + (uint32_t)top.a[j]);
-            float const x = c.x - mx, y = c.y - my, z = c.z - mz;
-            m.xx += x * x, m.xy += x * y, m.xz += x * z;
-            m.yy += y * y, m.yz += y * z, m.zz += z * z;
-        }
-    smallest_eigenvector(m, n3[0], n3[1], n3[2], gap);
-    if (centroid3)
-        centroid3[0] = mx, centroid3[1] = my, centroid3[2] = mz;
-    return n;
-}
-
 // Rare path of the normals kernel: the k-th and (k+1)-th distances are bit-equal, so WHICH of
 // the tied points belongs to the neighbourhood is decided by the original index (the parity
 // contract), which the position-keyed list does not carry.  `ids` is the exact (d2, original
@@ -107,31 +72,6 @@ PCPX_HD uint32_t normal_from_ids(const GridView& g, const QueryCell& qc, int lev
     if (centroid3)
         centroid3[0] = mx, centroid3[1] = my, centroid3[2] = mz;
     return n;
-}
-
-// algorithm/average_distance_to_neighbors.hpp:56-70: sequential fp32 sum of sqrt(d2), nearest ->
-// furthest, divided by the neighbour count (0 neighbours -> 0/0 = NaN like the reference).
-template <int K>
-PCPX_HD float mean_distance(const TopK<K>& top, uint32_t k)
-{
-    float sum  = 0.f;
-    uint32_t n = 0;
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-        if ((uint32_t)j < k && top.a[j] != kEmptyEntry)
-        {
-#ifdef __CUDA_ARCH__
-            sum = __fadd_rn(sum, __fsqrt_rn(u2f((uint32_t)(top.a[j] >> 32))));
-#else
-            sum = sum + sqrtf(u2f((uint32_t)(top.a[j] >> 32)));
-#endif
-            ++n;
-        }
-#ifdef __CUDA_ARCH__
-    return __fdiv_rn(sum, (float)n);
-#else
-    return sum / (float)n;
-#endif
 }
 
 // ---- two-pass fast paths (see knn_core.cuh) ---------------------------------------------------
