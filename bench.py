@@ -257,20 +257,24 @@ def run_ours(args):
     xyz, L = own_slab(pcpx, rank)
     n_owned = len(xyz)
     h_xyz = torch.from_numpy(xyz).pin_memory()
-    d_own = h_xyz.cuda()
+    # room behind the owned slab for the neighbours' strips: they are received in place
+    slack = 0 if world == 1 else 1_000_000
+    d_buf = torch.empty((n_owned + slack, 3), dtype=torch.float32, device="cuda")
+    d_stage_buf = torch.empty((n_owned + slack, 3), dtype=torch.float32, device="cuda")
+    d_own, d_stage = d_buf[:n_owned], d_stage_buf[:n_owned]
+    d_own.copy_(h_xyz)
     slab_lo, slab_hi = float(rank * L), float((rank + 1) * L)
 
-    def local_cloud(d_points):
+    def local_cloud(d_points, d_buffer):
         """N > 1: the exchange step — boundary strips go to the neighbouring ranks over NCCL"""
         if world == 1:
             return d_points
         return pcpx.sharding.exchange_halo(d_points, 0, slab_lo, slab_hi, HALO, rank, world,
-                                           dist)[0]
+                                           dist, buffer=d_buffer)[0]
 
-    n_local = int(local_cloud(d_own).shape[0])
+    n_local = int(local_cloud(d_own, d_buf).shape[0])
     d_nrm = torch.empty((n_local, 3), dtype=torch.float32, device="cuda")
     h_nrm = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
-    d_stage = torch.empty((n_owned, 3), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
 
     def barrier():
@@ -279,7 +283,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_resident(stats=None):
-        d_xyz = local_cloud(d_own)
+        d_xyz = local_cloud(d_own, d_buf)
         torch.cuda.synchronize()  # the library runs on its own stream
         ix = pcpx.Index(d_xyz, device=local_rank)
         tb = ix.timings()
@@ -298,7 +302,7 @@ def run_ours(args):
             ix = pcpx.Index(h_xyz.numpy(), device=local_rank)  # host pointer: H2D inside
         else:
             d_stage.copy_(h_xyz, non_blocking=True)  # H2D of the owned slab, then the exchange
-            d_xyz = local_cloud(d_stage)
+            d_xyz = local_cloud(d_stage, d_stage_buf)
             torch.cuda.synchronize()
             ix = pcpx.Index(d_xyz, device=local_rank)
         ix.estimate_normals(None, K, out=h_nrm.numpy()[: ix.n])  # host pointer: D2H inside
@@ -349,7 +353,7 @@ def run_ours(args):
     halo_ok = True
     if world > 1:
         own = xyz
-        d_xyz = local_cloud(d_own)
+        d_xyz = local_cloud(d_own, d_buf)
         torch.cuda.synchronize()
         lo_gap = own[:, 0] - np.float32(rank * L - HALO) if rank > 0 else None
         hi_gap = np.float32((rank + 1) * L + HALO) - own[:, 0] if rank < world - 1 else None

@@ -48,12 +48,14 @@ def query_slice(n, rank, world):
     return b, e
 
 
-def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None):
+def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None, buffer=None):
     """The one exchange step of the sharded path: every rank sends the points of its slab that
     lie within `halo` of an inner face to the neighbour across that face and receives the
     neighbour's strip (torch tensors on any device; NCCL moves device tensors over NVLink, gloo
     CPU tensors in the tests).  Returns the local cloud [own ; from the left ; from the right]
-    and the number of owned points.  Strip sizes are exchanged first (two 8-byte messages)."""
+    and the number of owned points.  Strip sizes are exchanged first (two 8-byte messages).
+    When `own_xyz` is the leading rows of a larger `buffer`, the strips are received straight
+    into the rows behind it and the local cloud is a view of `buffer` (no concatenation copy)."""
     import torch
 
     c = own_xyz[:, axis]
@@ -72,8 +74,17 @@ def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None):
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    recv = {p: torch.empty((int(sizes_in[p].item()), 3), dtype=own_xyz.dtype, device=dev)
-            for p in send}
+    n_own = own_xyz.shape[0]
+    counts = {p: int(sizes_in[p].item()) for p in send}
+    in_place = (buffer is not None and buffer.data_ptr() == own_xyz.data_ptr()
+                and buffer.shape[0] >= n_own + sum(counts.values()))
+    recv, at = {}, n_own
+    for p in sorted(send):
+        if in_place:
+            recv[p] = buffer[at:at + counts[p]]
+            at += counts[p]
+        else:
+            recv[p] = torch.empty((counts[p], 3), dtype=own_xyz.dtype, device=dev)
     ops = []
     for p in send:
         if send[p].shape[0]:
@@ -83,5 +94,7 @@ def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None):
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
+    if in_place:
+        return buffer[:at], n_own
     parts = [own_xyz] + [recv[p] for p in sorted(recv)]
-    return torch.cat(parts, 0), own_xyz.shape[0]
+    return torch.cat(parts, 0), n_own

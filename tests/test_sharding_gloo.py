@@ -45,6 +45,12 @@ def _worker(rank, world, port, ret):
         own_mask = sh.owner_of(xyz[:, 0], edges) == rank
         exch, n_own = sh.exchange_halo(torch.from_numpy(xyz[own_mask]), 0, float(edges[rank]),
                                        float(edges[rank + 1]), halo, rank, world, dist)
+        # ... and the in-place variant (strips received into the rows behind the owned slab)
+        buf = torch.empty((int(own_mask.sum()) + 5000, 3), dtype=torch.float32)
+        buf[: int(own_mask.sum())] = torch.from_numpy(xyz[own_mask])
+        exch2, _ = sh.exchange_halo(buf[: int(own_mask.sum())], 0, float(edges[rank]),
+                                    float(edges[rank + 1]), halo, rank, world, dist, buffer=buf)
+        assert exch2.data_ptr() == buf.data_ptr() and torch.equal(exch2, exch)
         exch = exch.numpy()
         same_set = (n_own == int(owned.sum()) and len(exch) == len(local) and np.array_equal(
             exch[np.lexsort(exch.T)], local[np.lexsort(local.T)]))
