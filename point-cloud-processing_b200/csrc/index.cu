@@ -229,7 +229,8 @@ bool sort_pairs(KeyT* keys, uint32_t* vals, KeyT* keys_alt, uint32_t* vals_alt, 
         return false;
     uint32_t const n_tiles = (n + kTile - 1) / kTile;
     hold.hist.alloc((size_t)n_passes * kRadix);
-    hold.counts.alloc((size_t)kRadix * n_tiles);
+    if (n >= kLookbackMaxN)
+        hold.counts.alloc((size_t)kRadix * n_tiles);
     DevBuf<uint32_t>& hist   = hold.hist;
     DevBuf<uint32_t>& counts = hold.counts;
     PCPX_CUDA(cudaMemsetAsync(hist.get(), 0, hist.bytes(), stream));
@@ -241,6 +242,16 @@ bool sort_pairs(KeyT* keys, uint32_t* vals, KeyT* keys_alt, uint32_t* vals_alt, 
     size_t const smem = sizeof(ScatterSmem<KeyT>);
     PCPX_CUDA(cudaFuncSetAttribute(scatter<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
+    PCPX_CUDA(cudaFuncSetAttribute(scatter_lookback<KeyT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bool const lookback = n < kLookbackMaxN;
+    if (lookback)
+    {
+        // per pass: [n_tiles][256] state words + one ticket, all zero
+        size_t const per_pass = (size_t)n_tiles * kRadix + 1;
+        hold.counts.alloc(per_pass * (size_t)n_passes);
+        PCPX_CUDA(cudaMemsetAsync(hold.counts.get(), 0, hold.counts.bytes(), stream));
+    }
     bool in_alt = false;
     for (int p = 0; p < n_passes; ++p)
     {
@@ -249,6 +260,17 @@ bool sort_pairs(KeyT* keys, uint32_t* vals, KeyT* keys_alt, uint32_t* vals_alt, 
         KeyT* kout     = in_alt ? keys : keys_alt;
         uint32_t* vout = in_alt ? vals : vals_alt;
         int const shift = p * kRadixBits;
+        if (lookback)
+        {
+            uint32_t* state = hold.counts.get() + ((size_t)n_tiles * kRadix + 1) * (size_t)p;
+            scatter_lookback<KeyT><<<n_tiles, kThreads, smem, stream>>>(
+                kin, vin, kout, vout, n, shift, hist.get() + (size_t)p * kRadix, state,
+                state + (size_t)n_tiles * kRadix);
+            PCPX_CHECK_LAUNCH();
+            *launches += 1;
+            in_alt = !in_alt;
+            continue;
+        }
         tile_histogram<KeyT><<<n_tiles, kThreads, 0, stream>>>(kin, n, shift, n_tiles, counts.get());
         PCPX_CHECK_LAUNCH();
         tile_offsets<<<kRadix, kThreads, 0, stream>>>(counts.get(), n_tiles,
