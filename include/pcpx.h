@@ -256,6 +256,77 @@ int pcpx_density_filter(
     float* out_xyz,
     size_t* out_n);
 
+/* ---- radius-search callers: smoothing and resampling ---------------- */
+
+/*
+ * Bilateral filter of the points.  Replaces pcp::algorithm::bilateral_filter_points
+ * (algorithm/bilateral_filter.hpp:301-421; per point bilateral::detail::compute_pi, :47-100):
+ * `iterations` (the reference's params.K) times, every point moves to the weighted mean of its
+ * projections onto the tangent planes (p_j, n_j) of the points within 2*sigmaf, weights
+ * gaussian(sigmaf, |s - p_j|) * gaussian(sigmag, |proj_j(s) - s|); the index is rebuilt on the
+ * moved points each iteration, the normals stay those handed in.  fp32 as in the reference;
+ * neighbours are summed in index order, not kd-tree order, so results agree to rounding
+ * (tests: 1e-5 of the cloud extent).  xyz / normals / out_xyz: n rows, host or device; out_xyz
+ * packed (12 B rows).  out_device_ms (may be NULL): device time of the whole call.
+ */
+int pcpx_bilateral_filter_points(
+    const float* xyz,
+    size_t n,
+    size_t stride_bytes,
+    const float* normals,
+    size_t normal_stride_bytes,
+    double sigmaf,
+    double sigmag,
+    uint32_t iterations,
+    int device,
+    float* out_xyz,
+    float* out_device_ms);
+
+/*
+ * Bilateral "normal improvement".  Replaces pcp::algorithm::bilateral_filter_normals
+ * (algorithm/bilateral_filter.hpp:452-575; per point bilateral::detail::compute_ni, :113-267):
+ * the points stay fixed (one index), and `iterations` times every normal is mapped through the
+ * Jacobian of the bilateral filter at its point and renormalised.  Formula restated verbatim,
+ * including the sign convention of the reference's projection Jacobian.
+ */
+int pcpx_bilateral_filter_normals(
+    const float* xyz,
+    size_t n,
+    size_t stride_bytes,
+    const float* normals,
+    size_t normal_stride_bytes,
+    double sigmaf,
+    double sigmag,
+    uint32_t iterations,
+    int device,
+    float* out_normals,
+    float* out_device_ms);
+
+/*
+ * WLOP / LOP resampling.  Replaces pcp::algorithm::wlop::wlop (algorithm/wlop.hpp:278-438).
+ * n_out points (params.I) are drawn from the cloud and moved `iterations` (params.k) times by
+ * the local-median attraction of the cloud plus the mutual repulsion (mu) of the resampled
+ * points, both with support radius h; uniform != 0 applies the WLOP density weights v_j, w_i
+ * (:371-401), 0 gives plain LOP.  The reference draws the start set with std::random_device
+ * (:346-358), which cannot be reproduced: pass it as initial_idx (n_out indices into xyz, host
+ * or device), or NULL for the last n_out entries of a std::mt19937(seed) shuffle of 0..n-1.
+ * out_xyz: n_out packed rows in the order of initial_idx.
+ */
+int pcpx_wlop(
+    const float* xyz,
+    size_t n,
+    size_t stride_bytes,
+    const uint32_t* initial_idx,
+    size_t n_out,
+    double mu,
+    double h,
+    uint32_t iterations,
+    int uniform,
+    uint32_t seed,
+    int device,
+    float* out_xyz,
+    float* out_device_ms);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 
 /* Device time (CUDA events on the launching stream) of the last call of each kind made

@@ -856,3 +856,291 @@ void oracle_radius_count_bruteforce(
         out_count[i] = cnt;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Radius-search callers.  The reference gathers each ball with a kd-tree
+ * rebuilt per iteration; the restatement gathers it from the octree above (same predicate,
+ * sphere_a::contains, common/sphere.hpp:51-56) — the neighbour ORDER therefore differs from
+ * the reference's kd-tree DFS order and fp32 sums agree only to rounding.
+ *
+ * Parity status: bilateral_filter_points and the four WLOP bodies are PINNED against the
+ * unmodified reference (oracle/ref_bridge_smoothing.cpp, fixtures in tests/golden/) and the
+ * reference's own tests (test/algorithm/bilateral_filter.cpp, test/algorithm/wlop.cpp).
+ * bilateral_filter_normals is UNPINNED: compute_ni is written on Eigen types (Eigen 3.3.8,
+ * absent here) and the reference's test only checks the output size
+ * (test/algorithm/bilateral_filter.cpp:135-155); the formula is restated line by line.
+ * ---------------------------------------------------------------------------------------- */
+
+/* algorithm/bilateral_filter.hpp:359-367 */
+static float gaussian_f(float sigma, float r)
+{
+    float const s2    = sigma * sigma;
+    float const r2    = r * r;
+    float const power = -r2 / (2 * s2);
+    float const coeff = 1.f / (sigma * sqrtf(2.f * 3.14159265358979323846f));
+    return coeff * expf(power);
+}
+
+/* algorithm/bilateral_filter.hpp:511-519 */
+static float dgaussian_f(float sigma, float r)
+{
+    float const s2    = sigma * sigma;
+    float const s3    = sigma * s2;
+    float const r2    = r * r;
+    float const power = -r2 / (2 * s2);
+    float const coeff = -r / (s3 * sqrtf(2.f * 3.14159265358979323846f));
+    return coeff * expf(power);
+}
+
+static u32vec_t ball(const oracle_cloud* c, const float* ctr, float r)
+{
+    u32vec_t v = {0};
+    if (c->n_nodes)
+        radius_rec(c, 0, ctr, r, r * r, 1, &v);
+    return v;
+}
+
+/* bilateral::detail::compute_pi, algorithm/bilateral_filter.hpp:47-100 */
+static void bilateral_pi(const oracle_cloud* c, const float* nrm, size_t i, float sigmaf,
+                         float sigmag, float* out)
+{
+    const float* s = c->xyz + 3 * i;
+    u32vec_t nb    = ball(c, s, 2.f * sigmaf);
+    float k = 0.f, acc[3] = {0.f, 0.f, 0.f};
+    for (size_t j = 0; j < nb.n; ++j)
+    {
+        const float* p = c->xyz + 3 * (size_t)nb.a[j];
+        const float* n = nrm + 3 * (size_t)nb.a[j];
+        float sp[3]    = {p[0] - s[0], p[1] - s[1], p[2] - s[2]};      /* :372 */
+        float d        = sp[0] * n[0] + sp[1] * n[1] + sp[2] * n[2];  /* :374 */
+        float pj[3]    = {s[0] + d * n[0], s[1] + d * n[1], s[2] + d * n[2]};
+        float f[3]     = {s[0] - p[0], s[1] - p[1], s[2] - p[2]};
+        float g[3]     = {pj[0] - s[0], pj[1] - s[1], pj[2] - s[2]};
+        float rf       = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]); /* :83 */
+        float rg       = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]); /* :84 */
+        float w        = gaussian_f(sigmaf, rf) * gaussian_f(sigmag, rg);
+        k += w;
+        for (int a = 0; a < 3; ++a)
+            acc[a] = acc[a] + w * pj[a];
+    }
+    for (int a = 0; a < 3; ++a)
+        out[a] = acc[a] / k;
+    free(nb.a);
+}
+
+/* algorithm/bilateral_filter.hpp:301-421: K iterations, tree rebuilt on the moved points */
+void oracle_bilateral_filter_points(const float* xyz, const float* normals, size_t n, double sigmaf,
+                                    double sigmag, size_t K, float* out)
+{
+    float* cur = (float*)malloc((n ? n : 1) * 12);
+    memcpy(cur, xyz, n * 12);
+    for (size_t it = 0; it < K; ++it)
+    {
+        oracle_cloud* c = oracle_cloud_create(cur, n, NULL, 0, 0);
+        float* nxt      = (float*)malloc((n ? n : 1) * 12);
+        for (size_t i = 0; i < n; ++i)
+            bilateral_pi(c, normals, i, (float)sigmaf, (float)sigmag, nxt + 3 * i);
+        oracle_cloud_destroy(c);
+        free(cur);
+        cur = nxt;
+    }
+    memcpy(out, cur, n * 12);
+    free(cur);
+}
+
+static void normalized3(const float* v, float* u)
+{
+    /* Eigen 3.3 MatrixBase::normalized(): v itself unless its squared norm is positive */
+    float z = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    if (z > 0.f)
+    {
+        float s = sqrtf(z);
+        u[0] = v[0] / s, u[1] = v[1] / s, u[2] = v[2] / s;
+    }
+    else
+        u[0] = v[0], u[1] = v[1], u[2] = v[2];
+}
+
+/* bilateral::detail::compute_ni, algorithm/bilateral_filter.hpp:113-267 */
+static void bilateral_ni(const oracle_cloud* c, const float* nrm, size_t i, float sigmaf,
+                         float sigmag, float* out)
+{
+    const float* s = c->xyz + 3 * i;
+    u32vec_t nb    = ball(c, s, 2.f * sigmaf);
+    float J[3][3] = {{0}}, u[3] = {0}, gk[3] = {0}, k = 0.f;
+    for (size_t j = 0; j < nb.n; ++j)
+    {
+        const float* p = c->xyz + 3 * (size_t)nb.a[j];
+        const float* n = nrm + 3 * (size_t)nb.a[j];
+        float v[3]     = {p[0] - s[0], p[1] - s[1], p[2] - s[2]};
+        float d        = v[0] * n[0] + v[1] * n[1] + v[2] * n[2];
+        float pj[3]    = {s[0] + d * n[0], s[1] + d * n[1], s[2] + d * n[2]};
+        float sp[3]    = {s[0] - p[0], s[1] - p[1], s[2] - p[2]};       /* :184 */
+        float sps[3]   = {pj[0] - s[0], pj[1] - s[1], pj[2] - s[2]};    /* :185 */
+        float rf       = sqrtf(sp[0] * sp[0] + sp[1] * sp[1] + sp[2] * sp[2]);
+        float rg       = sqrtf(sps[0] * sps[0] + sps[1] * sps[1] + sps[2] * sps[2]);
+        float wf = gaussian_f(sigmaf, rf), wg = gaussian_f(sigmag, rg);
+        float w  = wf * wg;
+        k += w;
+        for (int a = 0; a < 3; ++a)
+            u[a] += w * pj[a];
+        float wdf = dgaussian_f(sigmaf, rf);
+        float su[3], gf[3];
+        normalized3(sp, su);
+        for (int a = 0; a < 3; ++a)
+            gf[a] = su[a] * wdf;
+        float P[3][3] = {{1 - n[0] * n[0], n[0] * n[1], n[0] * n[2]},   /* :213-222 */
+                         {n[0] * n[1], 1 - n[1] * n[1], n[1] * n[2]},
+                         {n[0] * n[2], n[1] * n[2], 1 - n[2] * n[2]}};
+        float wdg = dgaussian_f(sigmag, rg);
+        float pu[3], gg[3];
+        normalized3(sps, pu);
+        for (int a = 0; a < 3; ++a)                                      /* :234 */
+            gg[a] = ((pu[0] * P[0][a] + pu[1] * P[1][a] + pu[2] * P[2][a]) - pu[a]) * wdg;
+        for (int a = 0; a < 3; ++a)                                      /* :239 */
+            gk[a] += gf[a] * wg + wf * gg[a];
+        for (int r = 0; r < 3; ++r)                                      /* :243 */
+            for (int a = 0; a < 3; ++a)
+                J[r][a] += (P[r][a] * wf * wg + sps[r] * gf[a] * wg) + sps[r] * wf * gg[a];
+    }
+    float inv = 1.f / (k * k);                                           /* :249-250 */
+    const float* ns = nrm + 3 * i;
+    float o[3];
+    for (int r = 0; r < 3; ++r)
+    {
+        float acc = 0.f;
+        for (int a = 0; a < 3; ++a)
+            acc += (inv * (J[r][a] * k - u[r] * gk[a])) * ns[a];
+        o[r] = acc;
+    }
+    normalized3(o, out);                                                 /* :264-266 */
+    free(nb.a);
+}
+
+/* algorithm/bilateral_filter.hpp:452-575: one tree, K passes over the normals */
+void oracle_bilateral_filter_normals(const float* xyz, const float* normals, size_t n,
+                                     double sigmaf, double sigmag, size_t K, float* out)
+{
+    oracle_cloud* c = oracle_cloud_create(xyz, n, NULL, 0, 0);
+    float* cur      = (float*)malloc((n ? n : 1) * 12);
+    float* nxt      = (float*)malloc((n ? n : 1) * 12);
+    memcpy(cur, normals, n * 12);
+    for (size_t it = 0; it < K; ++it)
+    {
+        for (size_t i = 0; i < n; ++i)
+            bilateral_ni(c, cur, i, (float)sigmaf, (float)sigmag, nxt + 3 * i);
+        float* t = cur;
+        cur = nxt, nxt = t;
+    }
+    memcpy(out, cur, n * 12);
+    free(cur), free(nxt);
+    oracle_cloud_destroy(c);
+}
+
+/* ---- WLOP: algorithm/wlop.hpp ---- */
+static float theta_f(float r2, float h4sq) { return expf(-r2 / h4sq); } /* :326-328 */
+
+static int same_point(const float* a, const float* b) /* are_vectors_equal(a, b, 1e-9f) */
+{
+    float const eps = (float)1e-9;
+    return fp_equals(a[0], b[0], eps) && fp_equals(a[1], b[1], eps) && fp_equals(a[2], b[2], eps);
+}
+
+/* compute_vj / compute_wi, :28-104 */
+static float wlop_density(const oracle_cloud* c, const float* q, float h, float h4sq)
+{
+    u32vec_t nb = ball(c, q, h);
+    float v     = 1.0f;
+    for (size_t j = 0; j < nb.n; ++j)
+    {
+        const float* p = c->xyz + 3 * (size_t)nb.a[j];
+        if (same_point(q, p))
+            continue;
+        v += theta_f(sqdist3(q, p), h4sq);
+    }
+    free(nb.a);
+    return v;
+}
+
+/* initial: I indices into xyz (the reference draws them with std::random_device, :346-358) */
+void oracle_wlop(const float* xyz, size_t n, const uint32_t* initial, size_t I, double mu_d,
+                 double h_d, size_t K, int uniform, float* out)
+{
+    float const mu = (float)mu_d, h = (float)h_d;
+    float const h4sq = (h * h) / (float)(4.0 * 4.0); /* :322-324 */
+    float const eps = (float)1e-9, zero = 0.f;
+    float* x  = (float*)malloc((I ? I : 1) * 12);
+    float* xp = (float*)malloc((I ? I : 1) * 12);
+    float* vj = (float*)malloc((n ? n : 1) * 4);
+    float* wi = (float*)malloc((I ? I : 1) * 4);
+    for (size_t i = 0; i < I; ++i)
+        memcpy(x + 3 * i, xyz + 3 * (size_t)initial[i], 12);
+    memcpy(xp, x, I * 12);
+    for (size_t j = 0; j < n; ++j)
+        vj[j] = 1.0f;
+    for (size_t i = 0; i < I; ++i)
+        wi[i] = 1.0f;
+    oracle_cloud* cp = oracle_cloud_create(xyz, n, NULL, 0, 0);
+    if (uniform) /* :371-381 */
+        for (size_t j = 0; j < n; ++j)
+            vj[j] = wlop_density(cp, xyz + 3 * j, h, h4sq);
+    for (size_t it = 0; it < K; ++it)
+    {
+        oracle_cloud* cq = oracle_cloud_create(x, I, NULL, 0, 0); /* :385-389 */
+        if (uniform) /* :391-401 */
+            for (size_t i = 0; i < I; ++i)
+                wi[i] = wlop_density(cq, x + 3 * i, h, h4sq);
+        for (size_t i = 0; i < I; ++i)
+        {
+            const float* q = x + 3 * i;
+            /* solve_first_energy_median, :106-168 */
+            u32vec_t nb = ball(cp, q, h);
+            float sum = 0.f, med[3] = {0.f, 0.f, 0.f};
+            for (size_t j = 0; j < nb.n; ++j)
+            {
+                const float* p = xyz + 3 * (size_t)nb.a[j];
+                if (same_point(q, p))
+                    continue;
+                float r2    = sqdist3(q, p);
+                float r     = sqrtf(r2);
+                float v     = vj[nb.a[j]];
+                float alpha = fp_equals(r, zero, eps) ? zero : theta_f(r2, h4sq) / r;
+                float coeff = fp_equals(v, zero, eps) ? zero : alpha / v;
+                for (int a = 0; a < 3; ++a)
+                    med[a] = med[a] + coeff * p[a];
+                sum += coeff;
+            }
+            free(nb.a);
+            if (fp_equals(sum, zero, eps))
+                med[0] = q[0], med[1] = q[1], med[2] = q[2];
+            else
+                med[0] = med[0] / sum, med[1] = med[1] / sum, med[2] = med[2] / sum;
+            /* solve_second_energy_repulsion_force, :170-224 */
+            nb = ball(cq, q, h);
+            float rsum = 0.f, rep[3] = {0.f, 0.f, 0.f};
+            for (size_t j = 0; j < nb.n; ++j)
+            {
+                const float* qi = x + 3 * (size_t)nb.a[j];
+                if (same_point(qi, q))
+                    continue;
+                float d[3]  = {q[0] - qi[0], q[1] - qi[1], q[2] - qi[2]};
+                float r2    = sqdist3(q, qi);
+                float r     = sqrtf(r2);
+                float beta  = fp_equals(r, zero, eps) ? zero : theta_f(r2, h4sq) / r;
+                float coeff = wi[nb.a[j]] * beta;
+                for (int a = 0; a < 3; ++a)
+                    rep[a] = rep[a] + coeff * d[a];
+                rsum += coeff;
+            }
+            free(nb.a);
+            float s = fp_equals(rsum, zero, eps) ? zero : mu / rsum;
+            for (int a = 0; a < 3; ++a)
+                xp[3 * i + a] = med[a] + s * rep[a]; /* :428-431 */
+        }
+        oracle_cloud_destroy(cq);
+        memcpy(x, xp, I * 12); /* :434 */
+    }
+    memcpy(out, xp, I * 12);
+    oracle_cloud_destroy(cp);
+    free(x), free(xp), free(vj), free(wi);
+}

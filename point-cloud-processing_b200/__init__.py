@@ -15,10 +15,13 @@ from .capi import (  # noqa: F401
     NO_NEIGHBOUR,
     Index,
     PcpxError,
+    bilateral_filter_normals,
+    bilateral_filter_points,
     device_count,
     exported_symbols,
     lib,
     normals_from_neighbourhoods,
     set_tuning,
+    wlop,
 )
 from . import sharding, synth  # noqa: F401

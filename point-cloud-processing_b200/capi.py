@@ -80,6 +80,15 @@ _SIGNATURES = {
                                          C.POINTER(C.c_double)]),
     "pcpx_density_filter": (C.c_int, [C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_size_t)]),
+    "pcpx_bilateral_filter_points": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                               C.c_size_t, C.c_double, C.c_double, C.c_uint32,
+                                               C.c_int, C.c_void_p, C.POINTER(C.c_float)]),
+    "pcpx_bilateral_filter_normals": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                C.c_size_t, C.c_double, C.c_double, C.c_uint32,
+                                                C.c_int, C.c_void_p, C.POINTER(C.c_float)]),
+    "pcpx_wlop": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                            C.c_double, C.c_double, C.c_uint32, C.c_int, C.c_uint32, C.c_int,
+                            C.c_void_p, C.POINTER(C.c_float)]),
     "pcpx_last_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "pcpx_set_tuning": (C.c_int, [C.c_char_p, C.c_double]),
     "pcpx_debug_knn_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]),
@@ -136,6 +145,60 @@ def normals_from_neighbourhoods(nbr_xyz, offsets, device=-1):
 
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
+
+
+def _out_rows(like, n, out):
+    """result buffer of n xyz rows: `out` if given, else same kind (numpy / torch) as `like`"""
+    if out is not None:
+        return out
+    if _is_torch(like):
+        import torch
+        return torch.empty((n, 3), dtype=torch.float32, device=like.device)
+    return np.zeros((n, 3), np.float32)
+
+
+def _bilateral(fn, xyz, normals, sigmaf, sigmag, iterations, device, out):
+    n = _count(xyz)
+    bx, bn = _Buf(xyz, np.float32), _Buf(normals, np.float32)
+    res = _out_rows(xyz, n, out)
+    bo = _Buf(res, np.float32, writable=True)
+    ms = C.c_float(-1.0)
+    _check(fn(bx.ptr, n, 12, bn.ptr, 12, float(sigmaf), float(sigmag), int(iterations), device,
+              bo.ptr, C.byref(ms)))
+    return res, ms.value
+
+
+def bilateral_filter_points(xyz, normals, sigmaf, sigmag, iterations=1, device=-1, out=None,
+                            want_ms=False):
+    """pcp::algorithm::bilateral_filter_points on the GPU (include/pcpx.h)."""
+    res, ms = _bilateral(lib().pcpx_bilateral_filter_points, xyz, normals, sigmaf, sigmag,
+                         iterations, device, out)
+    return (res, ms) if want_ms else res
+
+
+def bilateral_filter_normals(xyz, normals, sigmaf, sigmag, iterations=1, device=-1, out=None,
+                             want_ms=False):
+    """pcp::algorithm::bilateral_filter_normals on the GPU (include/pcpx.h)."""
+    res, ms = _bilateral(lib().pcpx_bilateral_filter_normals, xyz, normals, sigmaf, sigmag,
+                         iterations, device, out)
+    return (res, ms) if want_ms else res
+
+
+def wlop(xyz, n_out, h, mu=0.45, iterations=10, uniform=True, initial=None, seed=0, device=-1,
+         out=None, want_ms=False):
+    """pcp::algorithm::wlop::wlop on the GPU; `initial` = the start set's indices into xyz."""
+    n = _count(xyz)
+    bx = _Buf(xyz, np.float32)
+    bi = _Buf(initial, np.uint32 if not _is_torch(initial) else None)
+    if initial is not None:
+        n_out = initial.numel() if _is_torch(initial) else len(bi.obj)
+    res = _out_rows(xyz, n_out, out)
+    bo = _Buf(res, np.float32, writable=True)
+    ms = C.c_float(-1.0)
+    _check(lib().pcpx_wlop(bx.ptr, n, 12, bi.ptr, int(n_out), float(mu), float(h),
+                           int(iterations), 1 if uniform else 0, int(seed), device, bo.ptr,
+                           C.byref(ms)))
+    return (res, ms.value) if want_ms else res
 
 
 class _Buf:

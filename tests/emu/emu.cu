@@ -16,6 +16,7 @@
 #include "plan.hpp"
 #include "normals_core.cuh"
 #include "radius_core.cuh"
+#include "smoothing_core.cuh"
 #include "tree_core.cuh"
 
 using namespace pcpx;
@@ -188,6 +189,14 @@ void emu_plan(void* h, uint32_t k, double margin, int* level, int* rings, double
     *occupancy = ix->cells_per_level[c.level]
                      ? (double)ix->g.n / (double)ix->cells_per_level[c.level]
                      : 0.0;
+}
+
+// original index of every sorted position (the processing order of self-queries)
+void emu_sorted_order(void* h, uint32_t* out)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    for (uint64_t i = 0; i < ix->g.n; ++i)
+        out[i] = f2u(ix->g.pts[i].w);
 }
 
 void emu_index_info(void* h, uint64_t* n_indexed, int* lcap, int* lfine, uint64_t* slots)
@@ -455,6 +464,70 @@ void emu_smallest_eigenvector(const float* cov6, float* n3, float* gap)
 {
     Sym3 m{cov6[0], cov6[1], cov6[2], cov6[3], cov6[4], cov6[5]};
     smallest_eigenvector(m, n3[0], n3[1], n3[2], gap);
+}
+
+// ---- radius-search callers (smoothing_core.cuh); one step each, mirroring the kernels of
+// smoothing.cu.  Attribute arrays come in ORIGINAL order and are gathered into the index's
+// order exactly as gather3_kernel does.
+static std::vector<float4> gather3(EmuIndex* ix, const float* in)
+{
+    std::vector<float4> out(ix->n_input);
+    for (size_t t = 0; t < ix->n_input; ++t)
+    {
+        const float* r = in + 3 * (size_t)f2u(ix->pts[t].w);
+        out[t]         = make_float4(r[0], r[1], r[2], 0.f);
+    }
+    return out;
+}
+
+void emu_bilateral_points_step(void* h, const float* normals, float sigmaf, float sigmag,
+                               float* out_xyz)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    auto nrm     = gather3(ix, normals);
+    for (size_t t = 0; t < ix->n_input; ++t)
+    {
+        float4 const s = ix->pts[t];
+        bilateral_point(ix->g, nrm.data(), s.x, s.y, s.z, sigmaf, sigmag,
+                        out_xyz + 3 * (size_t)f2u(s.w));
+    }
+}
+
+void emu_bilateral_normals_step(void* h, const float* normals, float sigmaf, float sigmag,
+                                float* out_normals)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    auto nrm     = gather3(ix, normals);
+    for (size_t t = 0; t < ix->n_input; ++t)
+    {
+        float4 const s = ix->pts[t];
+        float4 const n = nrm[t];
+        bilateral_normal(ix->g, nrm.data(), s.x, s.y, s.z, n.x, n.y, n.z, sigmaf, sigmag,
+                         out_normals + 3 * (size_t)f2u(s.w));
+    }
+}
+
+// densities in the index's SORTED order, like wlop_density_kernel
+void emu_wlop_density(void* h, float hh, float mu, float* out_sorted)
+{
+    EmuIndex* ix       = static_cast<EmuIndex*>(h);
+    WlopParams const w = wlop_params(hh, mu);
+    for (size_t t = 0; t < ix->n_input; ++t)
+        out_sorted[t] = wlop_density(ix->g, w, ix->pts[t].x, ix->pts[t].y, ix->pts[t].z);
+}
+
+void emu_wlop_step(void* hp, const float* vj_sorted, void* hq, const float* wi_sorted, float hh,
+                   float mu, float* out_xyz)
+{
+    EmuIndex* ip       = static_cast<EmuIndex*>(hp);
+    EmuIndex* iq       = static_cast<EmuIndex*>(hq);
+    WlopParams const w = wlop_params(hh, mu);
+    for (size_t t = 0; t < iq->n_input; ++t)
+    {
+        float4 const q = iq->pts[t];
+        wlop_step(ip->g, vj_sorted, iq->g, wi_sorted, w, q.x, q.y, q.z,
+                  out_xyz + 3 * (size_t)f2u(q.w));
+    }
 }
 
 } // extern "C"

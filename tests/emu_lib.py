@@ -61,10 +61,57 @@ class Emu:
                                  _u32p]
         L.emu_density_keep.argtypes = [C.c_void_p, C.c_float, C.c_uint32, _u8p]
         L.emu_smallest_eigenvector.argtypes = [_f32p, _f32p, _f32p]
+        L.emu_sorted_order.argtypes = [C.c_void_p, _u32p]
+        L.emu_bilateral_points_step.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_float, _f32p]
+        L.emu_bilateral_normals_step.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_float, _f32p]
+        L.emu_wlop_density.argtypes = [C.c_void_p, C.c_float, C.c_float, _f32p]
+        L.emu_wlop_step.argtypes = [C.c_void_p, _f32p, C.c_void_p, _f32p, C.c_float, C.c_float,
+                                    _f32p]
         self.L = L
 
     def index(self, xyz, bbox=None, max_level=0, min_occ=0):
         return EmuIndex(self, xyz, bbox, max_level, min_occ)
+
+    # ---- the host loops of smoothing.cu, restated over the emulated index ------------------
+    def bilateral_filter_points(self, xyz, normals, sigmaf, sigmag, iterations):
+        cur = _f32(xyz).reshape(-1, 3).copy()
+        nrm = _f32(normals).reshape(-1, 3)
+        for _ in range(iterations):
+            ix = self.index(cur)
+            nxt = np.zeros_like(cur)
+            self.L.emu_bilateral_points_step(ix.h, _ptr(nrm, _f32p), sigmaf, sigmag,
+                                             _ptr(nxt, _f32p))
+            cur = nxt
+        return cur
+
+    def bilateral_filter_normals(self, xyz, normals, sigmaf, sigmag, iterations):
+        ix = self.index(_f32(xyz).reshape(-1, 3))
+        cur = _f32(normals).reshape(-1, 3).copy()
+        for _ in range(iterations):
+            nxt = np.zeros_like(cur)
+            self.L.emu_bilateral_normals_step(ix.h, _ptr(cur, _f32p), sigmaf, sigmag,
+                                              _ptr(nxt, _f32p))
+            cur = nxt
+        return cur
+
+    def wlop(self, xyz, initial, mu, h, iterations, uniform=True):
+        xyz = _f32(xyz).reshape(-1, 3)
+        x = xyz[np.asarray(initial, dtype=np.int64)].copy()
+        ixp = self.index(xyz)
+        vj = wi = None
+        if uniform:
+            vj = np.zeros(len(xyz), np.float32)
+            self.L.emu_wlop_density(ixp.h, h, mu, _ptr(vj, _f32p))
+        for _ in range(iterations):
+            ixq = self.index(x)
+            if uniform:
+                wi = np.zeros(len(x), np.float32)
+                self.L.emu_wlop_density(ixq.h, h, mu, _ptr(wi, _f32p))
+            nxt = np.zeros_like(x)
+            self.L.emu_wlop_step(ixp.h, _ptr(vj, _f32p), ixq.h, _ptr(wi, _f32p), h, mu,
+                                 _ptr(nxt, _f32p))
+            x = nxt
+        return x
 
     def smallest_eigenvector(self, cov6):
         c = _f32(cov6)
@@ -94,6 +141,11 @@ class EmuIndex:
         slots = C.c_uint64()
         self.L.emu_index_info(self.h, C.byref(n), C.byref(lcap), C.byref(lfine), C.byref(slots))
         return dict(n_indexed=n.value, lcap=lcap.value, lfine=lfine.value, slots=slots.value)
+
+    def sorted_order(self):
+        out = np.zeros(self.n, np.uint32)
+        self.L.emu_sorted_order(C.c_void_p(self.h), _ptr(out, _u32p))
+        return out
 
     def plan(self, k, margin=1.15):
         lv, rg, occ = C.c_int(), C.c_int(), C.c_double()

@@ -81,3 +81,33 @@ def planted_corner_case(seed, size=None, k=None):
     cloud = np.concatenate([pts, planted], 0)
     box = (np.array([-2, -2, -2], F), np.array([2, 2, 2], F))
     return cloud, np.array([[-1., 1., 1.]], F), k, set(range(size, size + k)), box
+
+
+# test/algorithm/bilateral_filter.cpp:10-70: nine points on a line, two of them displaced, the
+# displaced ones carrying tilted normals; sigmaf = mean distance to the 2 nearest neighbours
+# (:85-101), sigmag = sigmaf / 8, K = 2.  Expected (:121-125): point 2 moves down, point 6 up.
+BILATERAL_LINE_POINTS = np.array(
+    [[-0.1, 0, 0], [-0.075, 0, 0], [-0.05, 0, 0.01], [-0.025, 0, 0], [0, 0, 0], [0.025, 0, 0],
+     [0.05, 0, -0.01], [0.075, 0, 0], [0.1, 0, 0]], F)
+BILATERAL_LINE_NORMALS = np.array(
+    [[0, 0, 1], [0, 0, 1], [-0.19611614, 0, 0.98058068], [0, 0, 1], [0, 0, 1], [0, 0, 1],
+     [0.19611614, 0, 0.98058068], [0, 0, 1], [0, 0, 1]], F)
+BILATERAL_LINE_K = 2
+BILATERAL_LINE_KNN = 2  # neighbours used for sigmaf
+
+
+def wlop_case(seed=1234, n=1000):
+    """test/algorithm/wlop.cpp:8-19,53-65: 1000 uniform points in [-10, 10]^3 (the reference
+    seeds from random_device; a fixed seed stands in), I = n / 2, k = 2 iterations, h = mean
+    distance to the 15 nearest neighbours, uniform = true.  Expected: I finite points.
+
+    scale: with the test's own extent h is about 2.5, and for a radius above 1 the reference's
+    range search drops in-range points (common/intersections.hpp:101 compares a squared distance
+    with the un-squared radius), so its output depends on the shape of its kd-tree.  Value
+    parity is therefore taken on the same cloud scaled into [-1, 1]^3 (h about 0.25); at full
+    scale only the reference test's own expectations are checked."""
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-10, 10, (n, 3)).astype(F)
+
+
+WLOP_PARITY_SCALE = F(0.1)

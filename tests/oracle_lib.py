@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref.so")
+REF_SMOOTHING_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref_smoothing.so")
 
 _f32p = C.POINTER(C.c_float)
 _i64p = C.POINTER(C.c_int64)
@@ -40,6 +41,10 @@ def build_oracle(force=False):
     ref_stale = ref_possible and (
         (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(ref_src)
     )
+    ref2_src = os.path.join(ORACLE_DIR, "ref_bridge_smoothing.cpp")
+    ref_stale = ref_stale or (ref_possible and (
+        (not os.path.exists(REF_SMOOTHING_SO))
+        or os.path.getmtime(REF_SMOOTHING_SO) < os.path.getmtime(ref2_src)))
     if force or stale or ref_stale:
         subprocess.run(["make", "-C", ORACLE_DIR, "all"], check=True, capture_output=True)
 
@@ -83,7 +88,34 @@ class Oracle:
                                             C.c_double, _i64p, _f32p, _u32p]
         L.oracle_radius_count_bruteforce.argtypes = [_f32p, C.c_size_t, _f32p, C.c_size_t,
                                                      _f32p, C.c_float, _u32p]
+        _sz, _dbl = C.c_size_t, C.c_double
+        L.oracle_bilateral_filter_points.argtypes = [_f32p, _f32p, _sz, _dbl, _dbl, _sz, _f32p]
+        L.oracle_bilateral_filter_normals.argtypes = [_f32p, _f32p, _sz, _dbl, _dbl, _sz, _f32p]
+        L.oracle_wlop.argtypes = [_f32p, _sz, _u32p, _sz, _dbl, _dbl, _sz, C.c_int, _f32p]
         self.L = L
+
+    # ---- radius-search callers ---------------------------------------
+    def bilateral_filter_points(self, xyz, normals, sigmaf, sigmag, iterations):
+        xyz, normals = _f32(xyz).reshape(-1, 3), _f32(normals).reshape(-1, 3)
+        out = np.zeros_like(xyz)
+        self.L.oracle_bilateral_filter_points(_ptr(xyz, _f32p), _ptr(normals, _f32p), len(xyz),
+                                              sigmaf, sigmag, iterations, _ptr(out, _f32p))
+        return out
+
+    def bilateral_filter_normals(self, xyz, normals, sigmaf, sigmag, iterations):
+        xyz, normals = _f32(xyz).reshape(-1, 3), _f32(normals).reshape(-1, 3)
+        out = np.zeros_like(xyz)
+        self.L.oracle_bilateral_filter_normals(_ptr(xyz, _f32p), _ptr(normals, _f32p), len(xyz),
+                                               sigmaf, sigmag, iterations, _ptr(out, _f32p))
+        return out
+
+    def wlop(self, xyz, initial, mu, h, iterations, uniform=True):
+        xyz = _f32(xyz).reshape(-1, 3)
+        initial = np.ascontiguousarray(initial, dtype=np.uint32)
+        out = np.zeros((len(initial), 3), np.float32)
+        self.L.oracle_wlop(_ptr(xyz, _f32p), len(xyz), _ptr(initial, _u32p), len(initial), mu, h,
+                           iterations, 1 if uniform else 0, _ptr(out, _f32p))
+        return out
 
     # ---- scalar helpers -----------------------------------------------------------------
     def squared_distance(self, a, b):
@@ -228,6 +260,37 @@ class OracleCloud:
 
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+def have_ref_smoothing():
+    return os.path.exists(REF_SMOOTHING_SO)
+
+
+class RefSmoothing:
+    """The reference's own bilateral_filter_points and WLOP bodies (unmodified headers)."""
+
+    def __init__(self):
+        build_oracle()
+        L = C.CDLL(REF_SMOOTHING_SO)
+        _sz, _dbl = C.c_size_t, C.c_double
+        L.ref_bilateral_filter_points.argtypes = [_f32p, _f32p, _sz, _dbl, _dbl, _sz, _f32p]
+        L.ref_wlop.argtypes = [_f32p, _sz, _u32p, _sz, _dbl, _dbl, _sz, C.c_int, _f32p]
+        self.L = L
+
+    def bilateral_filter_points(self, xyz, normals, sigmaf, sigmag, iterations):
+        xyz, normals = _f32(xyz).reshape(-1, 3), _f32(normals).reshape(-1, 3)
+        out = np.zeros_like(xyz)
+        self.L.ref_bilateral_filter_points(_ptr(xyz, _f32p), _ptr(normals, _f32p), len(xyz),
+                                           sigmaf, sigmag, iterations, _ptr(out, _f32p))
+        return out
+
+    def wlop(self, xyz, initial, mu, h, iterations, uniform=True):
+        xyz = _f32(xyz).reshape(-1, 3)
+        initial = np.ascontiguousarray(initial, dtype=np.uint32)
+        out = np.zeros((len(initial), 3), np.float32)
+        self.L.ref_wlop(_ptr(xyz, _f32p), len(xyz), _ptr(initial, _u32p), len(initial), mu, h,
+                        iterations, 1 if uniform else 0, _ptr(out, _f32p))
+        return out
 
 
 class RefBridge:

@@ -20,7 +20,7 @@ def main():
     lf = float(sys.argv[4]) if len(sys.argv) > 4 else None
     if lf is not None:
         pcpx.set_tuning("success_margin", lf)
-    xyz = pcpx.synth.noisy_plane(n)
+    xyz = getattr(pcpx.synth, os.environ.get('PCPX_CLOUD', 'noisy_plane'))(n)
     d_xyz = torch.from_numpy(xyz).cuda()
     torch.cuda.synchronize()
     ix = pcpx.Index(d_xyz, min_cell_occupancy=int(os.environ.get('PCPX_MIN_OCC', '0')))
