@@ -327,6 +327,56 @@ int pcpx_wlop(
     float* out_xyz,
     float* out_device_ms);
 
+/* ---- normal orientation ---------------------------------------------- */
+
+/*
+ * Orient a normal field consistently.  Replaces pcp::algorithm::propagate_normal_orientations
+ * (algorithm/estimate_normals.hpp:187-302) with a k-nearest-neighbour KnnMap over the indexed
+ * cloud: the directed kNN graph (graph/knn_adjacency_list.hpp:117-156) is searched breadth
+ * first (graph/search.hpp:41-85) from the first point of maximal z, whose normal becomes
+ * (0, 0, 1); every other reached normal is negated iff its inner product with the final normal
+ * of the vertex that reached it is < 0 and not within 1e-5 of 0.  Unreached points keep their
+ * normals.  The result is bit-identical to the reference's sequential search: the queue order
+ * is reproduced exactly (see csrc/orient.cu).
+ *
+ * edge_order: the reference walks the out-edges of a vertex in the order its
+ * std::unordered_multimap yields equal keys (graph/directed_adjacency_list.hpp:79-83,183),
+ * which is the standard library's choice.  PCPX_EDGES_FURTHEST_FIRST is what libstdc++ does
+ * (reverse insertion order; verified against the reference compiled with g++ 13);
+ * PCPX_EDGES_NEAREST_FIRST is insertion order.
+ *
+ * normals: n_input x 3 packed floats in input order, host or device, updated in place.
+ * out_levels / out_reached (may be NULL): BFS depth and number of vertices reached.
+ */
+#define PCPX_EDGES_FURTHEST_FIRST 0
+#define PCPX_EDGES_NEAREST_FIRST 1
+
+int pcpx_orient_normals(
+    const pcpx_index* index,
+    uint32_t k,
+    double eps,
+    int edge_order,
+    float* normals,
+    uint32_t* out_levels,
+    uint64_t* out_reached);
+
+/*
+ * The same search over a caller-supplied directed graph (any KnnMap of the reference's
+ * signature): vertex i has the out-edges neighbours[i*k .. i*k+k) in insertion order,
+ * PCPX_NO_NEIGHBOUR marking unused slots.  xyz (n rows) only selects the root.
+ */
+int pcpx_orient_normals_graph(
+    const float* xyz,
+    size_t n,
+    size_t stride_bytes,
+    const uint32_t* neighbours,
+    uint32_t k,
+    int edge_order,
+    int device,
+    float* normals,
+    uint32_t* out_levels,
+    uint64_t* out_reached);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 
 /* Device time (CUDA events on the launching stream) of the last call of each kind made

@@ -666,6 +666,78 @@ void estimate_normals(ExecutionPolicy&&, ForwardIter1 begin, ForwardIter1 end,
         std::forward<TransformOp>(op));
 }
 
+// algorithm/estimate_normals.hpp:187-302.  Same signature and same result as the reference's
+// sequential breadth-first propagation (built with libstdc++, see pcpx.h: edge_order); the kNN
+// graph is gathered on the host from `knn_map` (one batched device call when it is a
+// gpu_knn_map), the search itself runs on the GPU.  `op(element, normal)` is invoked for the
+// root with (0, 0, 1) and for every element whose normal was negated — the same set of calls
+// the reference makes, in input order instead of search order.  `edge_order` is a pcpx
+// extension (default: what the reference does under libstdc++).
+template <class ForwardIter1, class IndexMap, class KnnMap, class PointViewMap, class NormalMap,
+          class TransformOp>
+void propagate_normal_orientations(ForwardIter1 begin, ForwardIter1 end, IndexMap const& index_map,
+                                   KnnMap&& knn_map, PointViewMap&& point_map,
+                                   NormalMap& normal_map, TransformOp&& op,
+                                   int edge_order = PCPX_EDGES_FURTHEST_FIRST)
+{
+    using knn_type    = std::decay_t<KnnMap>;
+    using normal_type = std::decay_t<decltype(normal_map(*begin))>;
+    using scalar_type = typename normal_type::component_type;
+    std::size_t const n = static_cast<std::size_t>(std::distance(begin, end));
+    if (n == 0)
+        return;
+    std::vector<float> xyz, nrm;
+    xyz.reserve(3 * n), nrm.reserve(3 * n);
+    for (auto it = begin; it != end; ++it)
+    {
+        detail::push_xyz(xyz, point_map(*it));
+        auto const nn = normal_map(*it);
+        nrm.push_back(static_cast<float>(nn.nx()));
+        nrm.push_back(static_cast<float>(nn.ny()));
+        nrm.push_back(static_cast<float>(nn.nz()));
+    }
+    std::vector<std::uint32_t> nbr;
+    std::size_t k = 0;
+    if constexpr (detail::is_gpu_knn_map<knn_type>::value)
+    {
+        knn_result_t const r = knn_map.index->knn_batch(xyz, knn_map.k, knn_map.eps);
+        k                    = r.k;
+        nbr.assign(n * k, PCPX_NO_NEIGHBOUR);
+        auto const& elements = knn_map.index->elements();
+        for (std::size_t i = 0; i < n; ++i)
+            for (std::size_t j = 0; j < r.counts[i]; ++j)
+                nbr[i * k + j] =
+                    static_cast<std::uint32_t>(index_map(elements[r.indices[i * k + j]]));
+    }
+    else
+    {
+        std::vector<std::vector<std::uint32_t>> rows(n);
+        std::size_t i = 0;
+        for (auto it = begin; it != end; ++it, ++i)
+        {
+            auto const neighbours = knn_map(*it);
+            for (auto const& e : neighbours)
+                rows[i].push_back(static_cast<std::uint32_t>(index_map(e)));
+            k = std::max(k, rows[i].size());
+        }
+        nbr.assign(n * k, PCPX_NO_NEIGHBOUR);
+        for (i = 0; i < n; ++i)
+            std::copy(rows[i].begin(), rows[i].end(), nbr.begin() + static_cast<std::ptrdiff_t>(i * k));
+    }
+    std::vector<float> const before = nrm;
+    detail::check(pcpx_orient_normals_graph(xyz.data(), n, 12, nbr.data(),
+                                            static_cast<std::uint32_t>(k), edge_order, -1,
+                                            nrm.data(), nullptr, nullptr),
+                  "pcpx_orient_normals_graph");
+    std::size_t i = 0;
+    for (auto it = begin; it != end; ++it, ++i)
+        if (nrm[3 * i] != before[3 * i] || nrm[3 * i + 1] != before[3 * i + 1] ||
+            nrm[3 * i + 2] != before[3 * i + 2])
+            op(*it, normal_type{static_cast<scalar_type>(nrm[3 * i]),
+                                static_cast<scalar_type>(nrm[3 * i + 1]),
+                                static_cast<scalar_type>(nrm[3 * i + 2])});
+}
+
 // algorithm/average_distance_to_neighbors.hpp:39-73 for the index's own elements, in their
 // original order (bit-exact fp32 per point), and :95-113 for their mean.
 template <class Index, class ScalarType = float>
@@ -716,6 +788,117 @@ std::vector<typename Index::element_type> filter_by_density(Index const& index, 
         *mask = std::move(keep);
     return out;
 }
+
+// ---- radius-search callers ---------------------------------------------
+namespace bilateral {
+// algorithm/bilateral_filter.hpp:28-33
+struct params_t
+{
+    double sigmaf = 1.;  ///< standard deviation of the spatial weight f (support = 2 sigmaf)
+    double sigmag = 0.1; ///< standard deviation of the influence weight g
+    std::size_t K = 1u;  ///< iterations
+};
+namespace detail {
+template <class Iter, class PointMap, class NormalMap>
+void flatten(Iter begin, Iter end, PointMap const& point_map, NormalMap const& normal_map,
+             std::vector<float>& xyz, std::vector<float>& nrm)
+{
+    for (auto it = begin; it != end; ++it)
+    {
+        pcp::detail::push_xyz(xyz, point_map(*it));
+        auto const n = normal_map(*it);
+        nrm.push_back(static_cast<float>(n.nx()));
+        nrm.push_back(static_cast<float>(n.ny()));
+        nrm.push_back(static_cast<float>(n.nz()));
+    }
+}
+} // namespace detail
+} // namespace bilateral
+
+// Drop-in for algorithm/bilateral_filter.hpp:301-421: same signature, the K iterations
+// (index rebuild + one kernel each) run on the GPU; *out_begin++ receives points constructible
+// from (x, y, z).
+template <class RandomAccessIter, class OutputIter, class PointMap, class NormalMap>
+OutputIter bilateral_filter_points(RandomAccessIter begin, RandomAccessIter end,
+                                   OutputIter out_begin, PointMap const& point_map,
+                                   NormalMap const& normal_map, bilateral::params_t const& params)
+{
+    using point_type  = std::decay_t<decltype(point_map(*begin))>;
+    using scalar_type = typename point_type::coordinate_type;
+    std::vector<float> xyz, nrm;
+    bilateral::detail::flatten(begin, end, point_map, normal_map, xyz, nrm);
+    std::size_t const n = xyz.size() / 3;
+    std::vector<float> out(xyz.size());
+    detail::check(pcpx_bilateral_filter_points(xyz.data(), n, 12, nrm.data(), 12, params.sigmaf,
+                                               params.sigmag,
+                                               static_cast<std::uint32_t>(params.K), -1,
+                                               out.data(), nullptr),
+                  "pcpx_bilateral_filter_points");
+    for (std::size_t i = 0; i < n; ++i)
+        *out_begin++ = point_type{static_cast<scalar_type>(out[3 * i]),
+                                  static_cast<scalar_type>(out[3 * i + 1]),
+                                  static_cast<scalar_type>(out[3 * i + 2])};
+    return out_begin;
+}
+
+// Drop-in for algorithm/bilateral_filter.hpp:452-575.
+template <class RandomAccessIter, class OutputIter, class PointMap, class NormalMap>
+OutputIter bilateral_filter_normals(RandomAccessIter begin, RandomAccessIter end,
+                                    OutputIter out_begin, PointMap const& point_map,
+                                    NormalMap const& normal_map, bilateral::params_t const& params)
+{
+    using normal_type = std::decay_t<decltype(normal_map(*begin))>;
+    using scalar_type = typename normal_type::component_type;
+    std::vector<float> xyz, nrm;
+    bilateral::detail::flatten(begin, end, point_map, normal_map, xyz, nrm);
+    std::size_t const n = xyz.size() / 3;
+    std::vector<float> out(xyz.size());
+    detail::check(pcpx_bilateral_filter_normals(xyz.data(), n, 12, nrm.data(), 12, params.sigmaf,
+                                                params.sigmag,
+                                                static_cast<std::uint32_t>(params.K), -1,
+                                                out.data(), nullptr),
+                  "pcpx_bilateral_filter_normals");
+    for (std::size_t i = 0; i < n; ++i)
+        *out_begin++ = normal_type{static_cast<scalar_type>(out[3 * i]),
+                                   static_cast<scalar_type>(out[3 * i + 1]),
+                                   static_cast<scalar_type>(out[3 * i + 2])};
+    return out_begin;
+}
+
+namespace wlop {
+// algorithm/wlop.hpp:233-241, plus the seed of the start set (the reference draws it from
+// std::random_device, :346-358, which no caller can reproduce)
+struct params_t
+{
+    std::size_t I = 0u;   ///< size of the resampled cloud
+    double mu     = 0.45; ///< repulsion coefficient, in [0, 0.5]
+    double h      = 0.;   ///< support radius
+    std::size_t k = 10u;  ///< solver iterations
+    bool uniform  = true; ///< WLOP density weights; false = plain LOP
+    std::uint32_t seed = 5489u; ///< std::mt19937 seed of the start set (pcpx extension)
+};
+
+// Drop-in for algorithm/wlop.hpp:278-438.  `Point` = the type written to out_begin.
+template <class Point = pcp::point_t, class RandomAccessIter, class OutputIter, class PointMap>
+OutputIter wlop(RandomAccessIter begin, RandomAccessIter end, OutputIter out_begin,
+                PointMap point_map, params_t const& params)
+{
+    using scalar_type = typename Point::coordinate_type;
+    std::vector<float> xyz;
+    for (auto it = begin; it != end; ++it)
+        pcp::detail::push_xyz(xyz, point_map(*it));
+    std::vector<float> out(3 * params.I);
+    detail::check(pcpx_wlop(xyz.data(), xyz.size() / 3, 12, nullptr, params.I, params.mu, params.h,
+                            static_cast<std::uint32_t>(params.k), params.uniform ? 1 : 0,
+                            params.seed, -1, out.data(), nullptr),
+                  "pcpx_wlop");
+    for (std::size_t i = 0; i < params.I; ++i)
+        *out_begin++ = Point{static_cast<scalar_type>(out[3 * i]),
+                             static_cast<scalar_type>(out[3 * i + 1]),
+                             static_cast<scalar_type>(out[3 * i + 2])};
+    return out_begin;
+}
+} // namespace wlop
 
 } // namespace algorithm
 } // namespace pcp

@@ -1144,3 +1144,61 @@ void oracle_wlop(const float* xyz, size_t n, const uint32_t* initial, size_t I, 
     oracle_cloud_destroy(cp);
     free(x), free(xp), free(vj), free(wi);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * propagate_normal_orientations: algorithm/estimate_normals.hpp:187-302
+ *
+ * knn: n rows of k neighbour indices (nearest first, -1 = none) — the directed kNN graph of
+ * graph/knn_adjacency_list.hpp:117-156.  Root = the FIRST point of maximal z
+ * (std::max_element, :223-230); its normal is replaced by (0, 0, 1) (:233-237).  Breadth-first
+ * search as graph/search.hpp:41-85 (FIFO queue; a vertex is marked when first reached and the
+ * edge that reaches it is the only one whose op runs): the reached normal is negated iff
+ * inner_product(n_parent, n_child) < 0 and |inner_product| >= 1e-5 (:289-300,
+ * common/norm.hpp:34-45, common/vector3d_queries.hpp:31-35), the parent's normal being its
+ * final one.  Vertices the search never reaches keep their normals.
+ *
+ * Edge order: the reference keeps edges in a std::unordered_multimap keyed by the source vertex
+ * (graph/directed_adjacency_list.hpp:79-83) and walks equal_range(source) (:183); the order of
+ * equal keys is the standard library's.  libstdc++ (this image, and the only build of the
+ * reference that can be run here) yields them in REVERSE insertion order, i.e. furthest
+ * neighbour first: reverse_edges = 1.  reverse_edges = 0 is insertion order (nearest first).
+ *
+ * Parity status: PINNED against the unmodified reference compiled here
+ * (oracle/ref_bridge_orient.cpp) with reverse_edges = 1.
+ * ---------------------------------------------------------------------------------------- */
+void oracle_propagate_normal_orientations(const float* xyz, size_t n, const int64_t* knn, size_t k,
+                                          int reverse_edges, float* normals)
+{
+    if (n == 0)
+        return;
+    size_t root = 0;
+    for (size_t i = 1; i < n; ++i)
+        if (xyz[3 * root + 2] < xyz[3 * i + 2])
+            root = i;
+    normals[3 * root] = 0.f, normals[3 * root + 1] = 0.f, normals[3 * root + 2] = 1.f;
+    uint8_t* visited = (uint8_t*)calloc(n, 1);
+    uint32_t* queue  = (uint32_t*)malloc(n * sizeof(uint32_t) + 4);
+    size_t head = 0, tail = 0;
+    queue[tail++] = (uint32_t)root;
+    while (head < tail)
+    {
+        size_t const u = queue[head++];
+        for (size_t e = 0; e < k; ++e)
+        {
+            int64_t const v = knn[u * k + (reverse_edges ? k - 1 - e : e)];
+            if (v < 0 || visited[v])
+                continue;
+            const float* n1 = normals + 3 * u;
+            float* n2       = normals + 3 * (size_t)v;
+            volatile float xx = n2[0] * n1[0], yy = n2[1] * n1[1], zz = n2[2] * n1[2];
+            volatile float s  = xx + yy;
+            float const prod  = s + zz;
+            if (prod < 0.f && !fp_equals(prod, 0.f, (float)1e-5))
+                n2[0] = -n2[0], n2[1] = -n2[1], n2[2] = -n2[2];
+            visited[v] = 1;
+            queue[tail++] = (uint32_t)v;
+        }
+        visited[u] = 1; /* search.hpp:81-82; only matters for the root, which has no self edge */
+    }
+    free(visited), free(queue);
+}

@@ -21,6 +21,7 @@ from .capi import (  # noqa: F401
     exported_symbols,
     lib,
     normals_from_neighbourhoods,
+    orient_normals_graph,
     set_tuning,
     wlop,
 )

@@ -89,6 +89,11 @@ _SIGNATURES = {
     "pcpx_wlop": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
                             C.c_double, C.c_double, C.c_uint32, C.c_int, C.c_uint32, C.c_int,
                             C.c_void_p, C.POINTER(C.c_float)]),
+    "pcpx_orient_normals": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_void_p,
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "pcpx_orient_normals_graph": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                            C.c_uint32, C.c_int, C.c_int, C.c_void_p,
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "pcpx_last_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "pcpx_set_tuning": (C.c_int, [C.c_char_p, C.c_double]),
     "pcpx_debug_knn_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]),
@@ -182,6 +187,23 @@ def bilateral_filter_normals(xyz, normals, sigmaf, sigmag, iterations=1, device=
     res, ms = _bilateral(lib().pcpx_bilateral_filter_normals, xyz, normals, sigmaf, sigmag,
                          iterations, device, out)
     return (res, ms) if want_ms else res
+
+
+def orient_normals_graph(xyz, neighbours, normals, nearest_first=False, device=-1):
+    """propagate_normal_orientations over an explicit directed graph: `neighbours` is n x k
+    uint32 (NO_NEIGHBOUR = unused slot); `normals` is updated in place and returned."""
+    n = _count(xyz)
+    bx = _Buf(xyz, np.float32)
+    if not _is_torch(neighbours):
+        neighbours = np.ascontiguousarray(neighbours, np.uint32)
+    k = neighbours.shape[1]
+    bn = _Buf(neighbours)
+    if not _is_torch(normals):
+        assert normals.dtype == np.float32 and normals.flags["C_CONTIGUOUS"]
+    bo = _Buf(normals, np.float32, True)
+    _check(lib().pcpx_orient_normals_graph(bx.ptr, n, 12, bn.ptr, k, 1 if nearest_first else 0,
+                                           device, bo.ptr, None, None))
+    return normals
 
 
 def wlop(xyz, n_out, h, mu=0.45, iterations=10, uniform=True, initial=None, seed=0, device=-1,
@@ -374,3 +396,14 @@ class Index:
         if out_xyz is not None and not _is_torch(out_xyz):
             out_xyz = out_xyz[: kept.value]
         return out_mask, out_xyz, kept.value
+
+    def orient_normals(self, normals, k, eps=1e-5, nearest_first=False, want_stats=False):
+        """propagate_normal_orientations over the kNN graph; `normals` (numpy array or CUDA
+        tensor, n x 3 float32) is updated IN PLACE and returned."""
+        if not _is_torch(normals):
+            assert normals.dtype == np.float32 and normals.flags["C_CONTIGUOUS"]
+        b = _Buf(normals, np.float32, True)
+        levels, reached = C.c_uint32(), C.c_uint64()
+        _check(lib().pcpx_orient_normals(self._h, int(k), float(eps), 1 if nearest_first else 0,
+                                         b.ptr, C.byref(levels), C.byref(reached)))
+        return (normals, levels.value, reached.value) if want_stats else normals

@@ -1,0 +1,451 @@
+// Normal orientation by breadth-first propagation over the directed kNN graph (SURVEY.md §8f
+// rank 4; reference: algorithm/estimate_normals.hpp:187-302, graph/knn_adjacency_list.hpp:117-156,
+// graph/search.hpp:41-85).
+//
+// The reference's search is a sequential FIFO walk, and which edge first reaches a vertex decides
+// the vertex's sign, so the result is defined by the queue order.  That order is reproduced
+// exactly, level by level, without a queue:
+//   * the queue content of one BFS level is an array `frontier` in queue order;
+//   * edge e of frontier entry i has the code i * k + e; a vertex not reached in earlier levels
+//     is reached by the edge of MINIMAL code pointing at it (atomicMin on a 64-bit key);
+//   * the next level's queue order is the order of the winning codes, i.e. an ordered compaction
+//     (per-entry count -> exclusive scan -> emit), not a sort.
+// All sizes stay on the device; the host queues levels in batches and only reads back the
+// frontier size once per batch to see whether the search has ended.  No CPU path.
+#include "api_util.hpp"
+
+using namespace pcpx;
+
+namespace {
+
+constexpr int kB         = 256;
+constexpr int kGrid      = 148 * 4;
+constexpr int kChunk     = 8; // edges whose loads are in flight together
+constexpr uint32_t kPad  = 0xFFFFFFFFu;
+
+struct BfsState
+{
+    uint32_t size[2];    // frontier sizes, ping-pong by level parity
+    uint32_t levels;     // levels that reached at least one new vertex
+    uint32_t pad;
+    unsigned long long reached; // vertices reached, root included
+    unsigned long long root_key;
+};
+
+__device__ __forceinline__ uint32_t orderable(float z)
+{
+    uint32_t const b = __float_as_uint(z + 0.f); // -0 -> +0
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// root = FIRST point of maximal z in input order (std::max_element, estimate_normals.hpp:223-230)
+__global__ void __launch_bounds__(kB) root_kernel(const float4* __restrict__ pts, uint32_t n,
+                                                  BfsState* st)
+{
+    unsigned long long best = 0;
+    for (uint32_t t = blockIdx.x * kB + threadIdx.x; t < n; t += gridDim.x * kB)
+    {
+        float4 const p = pts[t];
+        unsigned long long const key =
+            ((unsigned long long)orderable(p.z) << 32) | (0xFFFFFFFFu - __float_as_uint(p.w));
+        best = key > best ? key : best;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        unsigned long long const other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best)
+        atomicMax(&st->root_key, best);
+}
+
+__global__ void start_kernel(BfsState* st, uint32_t* frontier, uint8_t* visited, float* normals)
+{
+    uint32_t const root = 0xFFFFFFFFu - (uint32_t)(st->root_key & 0xFFFFFFFFu);
+    frontier[0]         = root;
+    visited[root]       = 1;
+    normals[3 * (size_t)root] = 0.f, normals[3 * (size_t)root + 1] = 0.f,
+                    normals[3 * (size_t)root + 2] = 1.f; // :233-237
+    st->size[0] = 1, st->size[1] = 0;
+    st->levels = 0, st->reached = 1;
+}
+
+__device__ __forceinline__ uint32_t edge_target(const uint32_t* __restrict__ nbr, uint32_t u,
+                                                uint32_t k, uint32_t e, int reverse)
+{
+    return nbr[(size_t)u * k + (reverse ? k - 1 - e : e)];
+}
+
+__global__ void __launch_bounds__(kB) propose_kernel(const BfsState* st, int parity,
+                                                     const uint32_t* __restrict__ frontier,
+                                                     const uint32_t* __restrict__ nbr, uint32_t k,
+                                                     int reverse,
+                                                     const uint8_t* __restrict__ visited,
+                                                     unsigned long long* __restrict__ key)
+{
+    unsigned long long const total = (unsigned long long)st->size[parity] * k;
+    for (unsigned long long c = blockIdx.x * (unsigned long long)kB + threadIdx.x; c < total;
+         c += (unsigned long long)gridDim.x * kB)
+    {
+        uint32_t const i = (uint32_t)(c / k), e = (uint32_t)(c % k);
+        uint32_t const v = edge_target(nbr, frontier[i], k, e, reverse);
+        if (v != kPad && !visited[v])
+            atomicMin(&key[v], c);
+    }
+}
+
+// per frontier entry: flip the children it wins (search.hpp:72-78 + estimate_normals.hpp:289-300)
+// and count them
+__global__ void __launch_bounds__(kB) accept_kernel(const BfsState* st, int parity,
+                                                    const uint32_t* __restrict__ frontier,
+                                                    const uint32_t* __restrict__ nbr, uint32_t k,
+                                                    int reverse,
+                                                    const uint8_t* __restrict__ visited,
+                                                    const unsigned long long* __restrict__ key,
+                                                    float* __restrict__ normals,
+                                                    uint32_t* __restrict__ won)
+{
+    uint32_t const m = st->size[parity];
+    for (uint32_t i = blockIdx.x * kB + threadIdx.x; i < m; i += gridDim.x * kB)
+    {
+        uint32_t const u = frontier[i];
+        float const ax = normals[3 * (size_t)u], ay = normals[3 * (size_t)u + 1],
+                    az = normals[3 * (size_t)u + 2];
+        uint32_t cnt = 0;
+        for (uint32_t e0 = 0; e0 < k; e0 += kChunk)
+        {
+            // the chunk's loads are issued together (three dependent rounds per chunk instead of
+            // three per edge); the flips below still happen in edge order
+            uint32_t v[kChunk];
+            bool mine[kChunk];
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c)
+                v[c] = e0 + c < k ? edge_target(nbr, u, k, e0 + c, reverse) : kPad;
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c)
+                mine[c] = v[c] != kPad && !visited[v[c]] &&
+                          key[v[c]] == (unsigned long long)i * k + e0 + c;
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c)
+            {
+                if (!mine[c])
+                    continue;
+                float* nv      = normals + 3 * (size_t)v[c];
+                float const bx = nv[0], by = nv[1], bz = nv[2];
+                // common::inner_product (common/norm.hpp:34-45): v2 * v1 per axis, left to right
+                float const prod =
+                    __fadd_rn(__fadd_rn(__fmul_rn(bx, ax), __fmul_rn(by, ay)), __fmul_rn(bz, az));
+                if (prod < 0.f && !(fabsf(prod - 0.f) < 1e-5f))
+                    nv[0] = -bx, nv[1] = -by, nv[2] = -bz;
+                ++cnt;
+            }
+        }
+        won[i] = cnt;
+    }
+}
+
+// exclusive scan of won[0 .. m) in place by ONE block (the sum of all frontier sizes over a whole
+// search is n, so this never does more than n / 1024 rounds in total); publishes the next size
+__global__ void __launch_bounds__(1024) scan_kernel(BfsState* st, int parity, uint32_t* won)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    uint32_t const m = st->size[parity];
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < m; base += 1024)
+    {
+        uint32_t const i = base + threadIdx.x;
+        uint32_t const x = i < m ? won[i] : 0u;
+        uint32_t incl    = x;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t const y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((threadIdx.x & 31) >= o)
+                incl += y;
+        }
+        if ((threadIdx.x & 31) == 31)
+            warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            uint32_t w = warp_sums[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                uint32_t const y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (threadIdx.x >= o)
+                    w += y;
+            }
+            warp_sums[threadIdx.x] = w; // inclusive over warps
+        }
+        __syncthreads();
+        uint32_t const before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0u);
+        if (i < m)
+            won[i] = before + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            carry += warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        st->size[parity ^ 1] = carry;
+        st->reached += carry;
+        st->levels += carry ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kB) emit_kernel(const BfsState* st, int parity,
+                                                  const uint32_t* __restrict__ frontier,
+                                                  const uint32_t* __restrict__ nbr, uint32_t k,
+                                                  int reverse, uint8_t* __restrict__ visited,
+                                                  const unsigned long long* __restrict__ key,
+                                                  const uint32_t* __restrict__ offset,
+                                                  uint32_t* __restrict__ next)
+{
+    uint32_t const m = st->size[parity];
+    for (uint32_t i = blockIdx.x * kB + threadIdx.x; i < m; i += gridDim.x * kB)
+    {
+        uint32_t const u = frontier[i];
+        uint32_t w       = offset[i];
+        for (uint32_t e0 = 0; e0 < k; e0 += kChunk)
+        {
+            uint32_t v[kChunk];
+            bool mine[kChunk];
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c)
+                v[c] = e0 + c < k ? edge_target(nbr, u, k, e0 + c, reverse) : kPad;
+            // the owner of v is unique, so nobody else tests visited[v] with a matching key
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c)
+                mine[c] = v[c] != kPad && key[v[c]] == (unsigned long long)i * k + e0 + c &&
+                          !visited[v[c]];
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c)
+                if (mine[c])
+                {
+                    next[w++]     = v[c];
+                    visited[v[c]] = 1;
+                }
+        }
+    }
+}
+
+// same for a caller-supplied graph: points in input order, packed or strided
+__global__ void __launch_bounds__(kB) root_from_rows_kernel(const float* __restrict__ xyz,
+                                                            uint32_t stride_f, uint32_t n,
+                                                            BfsState* st)
+{
+    unsigned long long best = 0;
+    for (uint32_t t = blockIdx.x * kB + threadIdx.x; t < n; t += gridDim.x * kB)
+    {
+        unsigned long long const key =
+            ((unsigned long long)orderable(xyz[(size_t)t * stride_f + 2]) << 32) |
+            (0xFFFFFFFFu - t);
+        best = key > best ? key : best;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        unsigned long long const other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best)
+        atomicMax(&st->root_key, best);
+}
+
+uint32_t grid_of(size_t n) { return (uint32_t)std::min<size_t>(std::max<size_t>((n + kB - 1) / kB, 1), kGrid); }
+
+// The search proper.  `st` holds the root key; nbr = n rows of k targets (kPad = no edge).
+BfsState run_search(cudaStream_t s, size_t n, uint32_t k, const uint32_t* nbr, int reverse,
+                    float* d_nrm, BfsState* st, uint32_t& launches)
+{
+    DevBuf<uint32_t> fa(n), fb(n), won(n);
+    DevBuf<uint8_t> visited(n);
+    DevBuf<unsigned long long> key(n);
+    PCPX_CUDA(cudaMemsetAsync(visited.get(), 0, n, s));
+    PCPX_CUDA(cudaMemsetAsync(key.get(), 0xFF, n * 8, s));
+    start_kernel<<<1, 1, 0, s>>>(st, fa.get(), visited.get(), d_nrm);
+    PCPX_CHECK_LAUNCH();
+    ++launches;
+    uint32_t const gn = grid_of(n);
+    uint32_t *cur = fa.get(), *nxt = fb.get();
+    int parity = 0;
+    BfsState h{};
+    for (uint64_t level = 0; level < n && k > 0;)
+    {
+        // a batch of levels, then one look at the frontier size; levels queued past the end of
+        // the search see an empty frontier and do nothing
+        for (int b = 0; b < 32; ++b, ++level)
+        {
+            propose_kernel<<<gn, kB, 0, s>>>(st, parity, cur, nbr, k, reverse, visited.get(),
+                                             key.get());
+            accept_kernel<<<gn, kB, 0, s>>>(st, parity, cur, nbr, k, reverse, visited.get(),
+                                            key.get(), d_nrm, won.get());
+            scan_kernel<<<1, 1024, 0, s>>>(st, parity, won.get());
+            emit_kernel<<<gn, kB, 0, s>>>(st, parity, cur, nbr, k, reverse, visited.get(),
+                                          key.get(), won.get(), nxt);
+            launches += 4;
+            std::swap(cur, nxt);
+            parity ^= 1;
+        }
+        PCPX_CHECK_LAUNCH();
+        PCPX_CUDA(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
+        PCPX_CUDA(cudaStreamSynchronize(s));
+        if (h.size[parity] == 0)
+            return h;
+    }
+    PCPX_CUDA(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
+    PCPX_CUDA(cudaStreamSynchronize(s)); // also keeps the buffers above alive until done
+    return h;
+}
+
+void check_edge_order(int edge_order)
+{
+    if (edge_order != PCPX_EDGES_FURTHEST_FIRST && edge_order != PCPX_EDGES_NEAREST_FIRST)
+        fail(PCPX_ERR_INVALID_ARG,
+             "edge_order must be PCPX_EDGES_FURTHEST_FIRST or PCPX_EDGES_NEAREST_FIRST");
+}
+
+} // namespace
+
+extern "C" {
+
+int pcpx_orient_normals(const pcpx_index* index, uint32_t k, double eps, int edge_order,
+                        float* normals, uint32_t* out_levels, uint64_t* out_reached)
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        size_t const n = ix.n_input;
+        if (out_levels)
+            *out_levels = 0;
+        if (out_reached)
+            *out_reached = 0;
+        if (n == 0)
+            return;
+        if (!normals)
+            fail(PCPX_ERR_INVALID_ARG, "normals is NULL");
+        check_edge_order(edge_order);
+        std::lock_guard<std::mutex> lock(ix.mtx);
+        ScopedDevice guard(ix.device);
+        CallTimer timer(ix);
+        cudaStream_t const s = ix.stream;
+
+        // normals in place on the device
+        bool const direct = is_device_pointer(normals);
+        DevBuf<float> staged;
+        float* d_nrm = normals;
+        if (!direct)
+        {
+            staged.alloc(3 * n);
+            PCPX_CUDA(cudaMemcpyAsync(staged.get(), normals, 12 * n, cudaMemcpyHostToDevice, s));
+            d_nrm = staged.get();
+        }
+
+        // the directed kNN graph (graph/knn_adjacency_list.hpp:139-152), rows in input order
+        uint32_t const kk = std::max(k, 1u);
+        DevBuf<uint32_t> nbr(n * (size_t)kk);
+        timer.kernel_begin();
+        if (k > 0)
+        {
+            DevBuf<uint32_t> retries(1);
+            PCPX_CUDA(cudaMemsetAsync(retries.get(), 0, 4, s));
+            QueryBatch const qb{nullptr, 3u, nullptr, (uint32_t)n};
+            launch_knn(ix, qb, k, (float)eps, nbr.get(), nullptr, nullptr, retries.get());
+            PCPX_CUDA(cudaStreamSynchronize(s)); // `retries` is released here
+        }
+        DevBuf<BfsState> st(1);
+        PCPX_CUDA(cudaMemsetAsync(st.get(), 0, sizeof(BfsState), s));
+        root_kernel<<<grid_of(n), kB, 0, s>>>(ix.grid.pts, (uint32_t)n, st.get());
+        uint32_t launches = 3;
+        BfsState const h  = run_search(s, n, k, nbr.get(), edge_order == PCPX_EDGES_FURTHEST_FIRST,
+                                       d_nrm, st.get(), launches);
+        timer.kernel_end();
+        if (!direct)
+            PCPX_CUDA(cudaMemcpyAsync(normals, d_nrm, 12 * n, cudaMemcpyDeviceToHost, s));
+        timer.done();
+        ix.timings.kernel_launches = launches;
+        if (out_levels)
+            *out_levels = h.levels;
+        if (out_reached)
+            *out_reached = h.reached;
+    });
+}
+
+int pcpx_orient_normals_graph(const float* xyz, size_t n, size_t stride_bytes,
+                              const uint32_t* neighbours, uint32_t k, int edge_order, int device,
+                              float* normals, uint32_t* out_levels, uint64_t* out_reached)
+{
+    return guarded([&] {
+        if (out_levels)
+            *out_levels = 0;
+        if (out_reached)
+            *out_reached = 0;
+        if (n == 0)
+            return;
+        if (n >= 0xFFFFFFFFull)
+            fail(PCPX_ERR_UNSUPPORTED, "graphs of 2^32 - 1 vertices or more need 64-bit indices");
+        if (!xyz || !normals || (k && !neighbours))
+            fail(PCPX_ERR_INVALID_ARG, "xyz / neighbours / normals is NULL");
+        check_edge_order(edge_order);
+        if (stride_bytes == 0)
+            stride_bytes = 12;
+        if (stride_bytes < 12 || stride_bytes % 4)
+            fail(PCPX_ERR_INVALID_ARG, "stride_bytes must be a multiple of 4 and >= 12");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            fail(PCPX_ERR_NO_DEVICE, "no CUDA device: libpcpx has no CPU path");
+        if (device < 0)
+            PCPX_CUDA(cudaGetDevice(&device));
+        if (device >= ndev)
+            fail(PCPX_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
+        ScopedDevice guard(device);
+        cudaStream_t s = nullptr;
+        PCPX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        struct StreamGuard
+        {
+            cudaStream_t s;
+            ~StreamGuard() { cudaStreamDestroy(s); }
+        } sg{s};
+
+        InBuf pts;
+        pts.stage(xyz, n, stride_bytes, 3, s);
+        DevBuf<uint32_t> nbr_staged;
+        const uint32_t* d_nbr = neighbours;
+        if (k && !is_device_pointer(neighbours))
+        {
+            for (size_t i = 0; i < n * (size_t)k; ++i)
+                if (neighbours[i] != kPad && neighbours[i] >= n)
+                    fail(PCPX_ERR_INVALID_ARG, "neighbours[%llu] = %u is not a vertex",
+                         (unsigned long long)i, neighbours[i]);
+            nbr_staged.alloc(n * (size_t)k);
+            PCPX_CUDA(cudaMemcpyAsync(nbr_staged.get(), neighbours, n * (size_t)k * 4,
+                                      cudaMemcpyHostToDevice, s));
+            d_nbr = nbr_staged.get();
+        }
+        bool const direct = is_device_pointer(normals);
+        DevBuf<float> staged;
+        float* d_nrm = normals;
+        if (!direct)
+        {
+            staged.alloc(3 * n);
+            PCPX_CUDA(cudaMemcpyAsync(staged.get(), normals, 12 * n, cudaMemcpyHostToDevice, s));
+            d_nrm = staged.get();
+        }
+        DevBuf<BfsState> st(1);
+        PCPX_CUDA(cudaMemsetAsync(st.get(), 0, sizeof(BfsState), s));
+        root_from_rows_kernel<<<grid_of(n), kB, 0, s>>>(pts.d, pts.stride_f, (uint32_t)n, st.get());
+        uint32_t launches = 1;
+        BfsState const h  = run_search(s, n, k, d_nbr, edge_order == PCPX_EDGES_FURTHEST_FIRST,
+                                       d_nrm, st.get(), launches);
+        if (!direct)
+            PCPX_CUDA(cudaMemcpyAsync(normals, d_nrm, 12 * n, cudaMemcpyDeviceToHost, s));
+        PCPX_CUDA(cudaStreamSynchronize(s));
+        if (out_levels)
+            *out_levels = h.levels;
+        if (out_reached)
+            *out_reached = h.reached;
+    });
+}
+
+} // extern "C"

@@ -2,10 +2,13 @@
 // include/pcpx/pcp.hpp with the reference's call signatures (test/octree/octree_knn.cpp,
 // test/octree/octree_range_search.cpp, test/kdtree/knn.cpp, test/common/normal_estimation.cpp,
 // test/algorithm/estimate_normals.cpp, test/algorithm/average_distance_to_neighbors.cpp,
-// examples/simple_example.cpp, examples/filter_point_cloud_noise_by_density.cpp).
+// examples/simple_example.cpp, examples/filter_point_cloud_noise_by_density.cpp,
+// test/algorithm/bilateral_filter.cpp, test/algorithm/wlop.cpp).
 // Exit code 0 = every scenario holds.  Needs a GPU (libpcpx has no CPU path).
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
+#include <numeric>
 #include <random>
 
 #include <pcpx/pcp.hpp>
@@ -252,6 +255,142 @@ static void normals_scenarios()
         REQUIRE(kept[i - 1].point() < kept[i].point());
 }
 
+// test/algorithm/bilateral_filter.cpp and test/algorithm/wlop.cpp, same calls
+static void smoothing_scenarios()
+{
+    std::vector<pcp::point_t> points{{-0.1f, 0.f, 0.f},   {-0.075f, 0.f, 0.f}, {-0.05f, 0.f, 0.01f},
+                                     {-0.025f, 0.f, 0.f}, {0.0f, 0.f, 0.f},    {0.025f, 0.f, 0.f},
+                                     {0.05f, 0.f, -0.01f}, {0.075f, 0.f, 0.f}, {0.1f, 0.f, 0.f}};
+    std::vector<pcp::normal_t> normals(9, pcp::normal_t{0.f, 0.f, 1.f});
+    normals[2] = pcp::normal_t{-0.19611614f, 0.f, 0.98058068f};
+    normals[6] = pcp::normal_t{0.19611614f, 0.f, 0.98058068f};
+    std::vector<std::size_t> indices(points.size());
+    std::iota(indices.begin(), indices.end(), std::size_t{0});
+    auto const pmap = [&](std::size_t const i) { return points[i]; };
+    auto const nmap = [&](std::size_t const i) { return normals[i]; };
+    auto const cmap = [&](std::size_t const i) {
+        return std::array<float, 3u>{points[i].x(), points[i].y(), points[i].z()};
+    };
+    pcp::kdtree::construction_params_t kp;
+    kp.compute_max_depth = true;
+    pcp::basic_linked_kdtree_t<std::size_t, 3u, decltype(cmap)> kdtree{indices.begin(),
+                                                                       indices.end(), cmap, kp};
+    pcp::algorithm::bilateral::params_t params;
+    params.K      = 2u;
+    params.sigmaf = static_cast<double>(pcp::algorithm::average_distance_to_neighbors(kdtree, 2u));
+    params.sigmag = params.sigmaf / 8.;
+    std::vector<pcp::point_t> filtered_points;
+    pcp::algorithm::bilateral_filter_points(indices.begin(), indices.end(),
+                                            std::back_inserter(filtered_points), pmap, nmap, params);
+    REQUIRE(filtered_points.size() == points.size());
+    REQUIRE(points[2].z() > filtered_points[2].z());
+    REQUIRE(points[6].z() < filtered_points[6].z());
+    std::vector<pcp::normal_t> filtered_normals;
+    pcp::algorithm::bilateral_filter_normals(indices.begin(), indices.end(),
+                                             std::back_inserter(filtered_normals), pmap, nmap,
+                                             params);
+    REQUIRE(filtered_normals.size() == indices.size());
+
+    // WLOP: 1000 uniform points in [-10, 10]^3, I = n / 2, k = 2, h = mean 15-NN distance
+    std::mt19937 gen(2024);
+    std::uniform_real_distribution<float> dis(-10.f, 10.f);
+    std::vector<pcp::point_t> cloud(1000);
+    for (auto& p : cloud)
+        p = pcp::point_t{dis(gen), dis(gen), dis(gen)};
+    std::vector<std::size_t> ids(cloud.size());
+    std::iota(ids.begin(), ids.end(), std::size_t{0});
+    auto const cloud_map = [&](std::size_t const i) { return cloud[i]; };
+    auto const cloud_cmap = [&](std::size_t const i) {
+        return std::array<float, 3u>{cloud[i].x(), cloud[i].y(), cloud[i].z()};
+    };
+    pcp::basic_linked_kdtree_t<std::size_t, 3u, decltype(cloud_cmap)> cloud_tree{
+        ids.begin(), ids.end(), cloud_cmap, kp};
+    pcp::algorithm::wlop::params_t wp;
+    wp.k       = 2u;
+    wp.I       = cloud.size() / 2;
+    wp.h       = static_cast<double>(pcp::algorithm::average_distance_to_neighbors(cloud_tree, 15u));
+    wp.uniform = true;
+    std::vector<pcp::point_t> down;
+    pcp::algorithm::wlop::wlop(ids.begin(), ids.end(), std::back_inserter(down), cloud_map, wp);
+    REQUIRE(down.size() == wp.I);
+    for (auto const& p : down)
+        REQUIRE(std::isfinite(p.x()) && std::isfinite(p.y()) && std::isfinite(p.z()));
+}
+
+// examples/normals_estimation.cpp:69-117: kd-tree -> estimate_normals -> propagate orientations
+static void orientation_scenario()
+{
+    std::mt19937 gen(77);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::size_t const n = 20000;
+    std::vector<pcp::point_t> points(n);
+    for (auto& p : points)
+    {
+        float x = nd(gen), y = nd(gen), z = nd(gen);
+        float const r = std::sqrt(x * x + y * y + z * z);
+        p = pcp::point_t{x / r, y / r, z / r};
+    }
+    std::vector<pcp::normal_t> normals(n);
+    std::vector<std::size_t> indices(n);
+    std::iota(indices.begin(), indices.end(), std::size_t{0});
+    auto const pmap = [&](std::size_t const i) { return points[i]; };
+    auto const cmap = [&](std::size_t const i) {
+        return std::array<float, 3u>{points[i].x(), points[i].y(), points[i].z()};
+    };
+    auto const imap = [](std::size_t const i) { return i; };
+    auto nmap       = [&](std::size_t const i) { return normals[i]; };
+    pcp::kdtree::construction_params_t kp;
+    kp.compute_max_depth = true;
+    pcp::basic_linked_kdtree_t<std::size_t, 3u, decltype(cmap)> kdtree{indices.begin(),
+                                                                       indices.end(), cmap, kp};
+    auto const knn = pcp::make_gpu_knn_map(kdtree, 12u, pmap);
+    pcp::algorithm::estimate_normals(
+        std::execution::par, indices.begin(), indices.end(), normals.begin(), pmap, knn,
+        pcp::algorithm::default_normal_transform<std::size_t, pcp::normal_t>);
+    std::size_t calls = 0;
+    auto const set_normal = [&](std::size_t const i, pcp::normal_t const& v) {
+        normals[i] = v;
+        ++calls;
+    };
+    pcp::algorithm::propagate_normal_orientations(indices.begin(), indices.end(), imap, knn, pmap,
+                                                  nmap, set_normal);
+    REQUIRE(calls >= 1u);
+    std::size_t outward = 0;
+    for (std::size_t i = 0; i < n; ++i)
+        outward += (normals[i].nx() * points[i].x() + normals[i].ny() * points[i].y() +
+                    normals[i].nz() * points[i].z()) > 0.f;
+    REQUIRE(outward > n - n / 100);
+
+    // an arbitrary KnnMap lambda (per-element calls) gives the same orientation (2 000 points)
+    std::size_t const m = 2000;
+    std::vector<pcp::point_t> small(points.begin(), points.begin() + m);
+    std::vector<std::size_t> ids(m);
+    std::iota(ids.begin(), ids.end(), std::size_t{0});
+    auto const spmap = [&](std::size_t const i) { return small[i]; };
+    auto const scmap = [&](std::size_t const i) {
+        return std::array<float, 3u>{small[i].x(), small[i].y(), small[i].z()};
+    };
+    pcp::basic_linked_kdtree_t<std::size_t, 3u, decltype(scmap)> stree{ids.begin(), ids.end(),
+                                                                       scmap, kp};
+    std::vector<pcp::normal_t> a(m), b;
+    auto const sknn = pcp::make_gpu_knn_map(stree, 8u, spmap);
+    pcp::algorithm::estimate_normals(
+        ids.begin(), ids.end(), a.begin(), spmap, sknn,
+        pcp::algorithm::default_normal_transform<std::size_t, pcp::normal_t>);
+    b           = a;
+    auto amap   = [&](std::size_t const i) { return a[i]; };
+    auto bmap   = [&](std::size_t const i) { return b[i]; };
+    auto const set_a = [&](std::size_t const i, pcp::normal_t const& v) { a[i] = v; };
+    auto const set_b = [&](std::size_t const i, pcp::normal_t const& v) { b[i] = v; };
+    auto const per_element = [&](std::size_t const i) { return stree.nearest_neighbours(i, 8u); };
+    pcp::algorithm::propagate_normal_orientations(ids.begin(), ids.end(), imap, sknn, spmap, amap,
+                                                  set_a);
+    pcp::algorithm::propagate_normal_orientations(ids.begin(), ids.end(), imap, per_element, spmap,
+                                                  bmap, set_b);
+    for (std::size_t i = 0; i < m; ++i)
+        REQUIRE(a[i].nx() == b[i].nx() && a[i].ny() == b[i].ny() && a[i].nz() == b[i].nz());
+}
+
 int main()
 {
     if (pcpx_device_count() < 1)
@@ -263,6 +402,8 @@ int main()
     octree_range_scenarios();
     kdtree_scenarios();
     normals_scenarios();
+    smoothing_scenarios();
+    orientation_scenario();
     std::printf("dropin_test: all scenarios hold\n");
     return 0;
 }

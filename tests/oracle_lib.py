@@ -16,6 +16,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref.so")
 REF_SMOOTHING_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref_smoothing.so")
+REF_ORIENT_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref_orient.so")
 
 _f32p = C.POINTER(C.c_float)
 _i64p = C.POINTER(C.c_int64)
@@ -41,10 +42,11 @@ def build_oracle(force=False):
     ref_stale = ref_possible and (
         (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(ref_src)
     )
-    ref2_src = os.path.join(ORACLE_DIR, "ref_bridge_smoothing.cpp")
-    ref_stale = ref_stale or (ref_possible and (
-        (not os.path.exists(REF_SMOOTHING_SO))
-        or os.path.getmtime(REF_SMOOTHING_SO) < os.path.getmtime(ref2_src)))
+    for so, name in ((REF_SMOOTHING_SO, "ref_bridge_smoothing.cpp"),
+                     (REF_ORIENT_SO, "ref_bridge_orient.cpp")):
+        bridge_src = os.path.join(ORACLE_DIR, name)
+        ref_stale = ref_stale or (ref_possible and (
+            (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(bridge_src)))
     if force or stale or ref_stale:
         subprocess.run(["make", "-C", ORACLE_DIR, "all"], check=True, capture_output=True)
 
@@ -92,7 +94,18 @@ class Oracle:
         L.oracle_bilateral_filter_points.argtypes = [_f32p, _f32p, _sz, _dbl, _dbl, _sz, _f32p]
         L.oracle_bilateral_filter_normals.argtypes = [_f32p, _f32p, _sz, _dbl, _dbl, _sz, _f32p]
         L.oracle_wlop.argtypes = [_f32p, _sz, _u32p, _sz, _dbl, _dbl, _sz, C.c_int, _f32p]
+        L.oracle_propagate_normal_orientations.argtypes = [_f32p, _sz, _i64p, _sz, C.c_int, _f32p]
         self.L = L
+
+    def propagate_normal_orientations(self, xyz, knn, normals, reverse_edges=True):
+        """knn: n x k int64 neighbour indices, nearest first, -1 = none.  Returns a copy."""
+        xyz = _f32(xyz).reshape(-1, 3)
+        knn = np.ascontiguousarray(knn, dtype=np.int64)
+        out = _f32(normals).reshape(-1, 3).copy()
+        self.L.oracle_propagate_normal_orientations(_ptr(xyz, _f32p), len(xyz), _ptr(knn, _i64p),
+                                                    knn.shape[1], 1 if reverse_edges else 0,
+                                                    _ptr(out, _f32p))
+        return out
 
     # ---- radius-search callers (SURVEY.md 8f rank 3) ---------------------------------------
     def bilateral_filter_points(self, xyz, normals, sigmaf, sigmag, iterations):
@@ -290,6 +303,32 @@ class RefSmoothing:
         out = np.zeros((len(initial), 3), np.float32)
         self.L.ref_wlop(_ptr(xyz, _f32p), len(xyz), _ptr(initial, _u32p), len(initial), mu, h,
                         iterations, 1 if uniform else 0, _ptr(out, _f32p))
+        return out
+
+
+def have_ref_orient():
+    return os.path.exists(REF_ORIENT_SO)
+
+
+class RefOrient:
+    """The reference's own propagate_normal_orientations (unmodified headers)."""
+
+    def __init__(self):
+        build_oracle()
+        L = C.CDLL(REF_ORIENT_SO)
+        L.ref_propagate_normal_orientations.argtypes = [_f32p, C.c_size_t, _i64p, C.c_size_t,
+                                                        _f32p]
+        self.L = L
+
+    def propagate_normal_orientations(self, xyz, k, normals, knn=None):
+        """knn = None: the reference's own kd-tree neighbours; else n x k int64 (-1 = none)."""
+        xyz = _f32(xyz).reshape(-1, 3)
+        if knn is not None:
+            knn = np.ascontiguousarray(knn, dtype=np.int64)
+            k = knn.shape[1]
+        out = _f32(normals).reshape(-1, 3).copy()
+        self.L.ref_propagate_normal_orientations(_ptr(xyz, _f32p), len(xyz), _ptr(knn, _i64p), k,
+                                                 _ptr(out, _f32p))
         return out
 
 
