@@ -17,6 +17,7 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref.so")
 REF_SMOOTHING_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref_smoothing.so")
 REF_ORIENT_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref_orient.so")
+REF_PLY_SO = os.path.join(ORACLE_DIR, "_ref", "libpcp_ref_ply.so")
 
 _f32p = C.POINTER(C.c_float)
 _i64p = C.POINTER(C.c_int64)
@@ -43,7 +44,8 @@ def build_oracle(force=False):
         (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(ref_src)
     )
     for so, name in ((REF_SMOOTHING_SO, "ref_bridge_smoothing.cpp"),
-                     (REF_ORIENT_SO, "ref_bridge_orient.cpp")):
+                     (REF_ORIENT_SO, "ref_bridge_orient.cpp"),
+                     (REF_PLY_SO, "ref_bridge_ply.cpp")):
         bridge_src = os.path.join(ORACLE_DIR, name)
         ref_stale = ref_stale or (ref_possible and (
             (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(bridge_src)))
@@ -330,6 +332,44 @@ class RefOrient:
         self.L.ref_propagate_normal_orientations(_ptr(xyz, _f32p), len(xyz), _ptr(knn, _i64p), k,
                                                  _ptr(out, _f32p))
         return out
+
+
+def have_ref_ply():
+    return os.path.exists(REF_PLY_SO)
+
+
+class RefPly:
+    """The reference's own PLY writer / reader (unmodified pcp/io/ply.hpp) on byte strings."""
+
+    FORMATS = {"ascii": 0, "binary_little_endian": 1, "binary_big_endian": 2}
+
+    def __init__(self):
+        build_oracle()
+        L = C.CDLL(REF_PLY_SO)
+        L.ref_write_ply.restype = C.c_size_t
+        L.ref_write_ply.argtypes = [_f32p, C.c_size_t, _f32p, C.c_size_t, C.c_int, _u8p,
+                                    C.c_size_t]
+        L.ref_read_ply.argtypes = [_u8p, C.c_size_t, _f32p, C.c_size_t, _f32p, C.c_size_t,
+                                   C.POINTER(C.c_size_t)]
+        self.L = L
+
+    def write(self, xyz, normals, fmt):
+        xyz, normals = _f32(xyz).reshape(-1, 3), _f32(normals).reshape(-1, 3)
+        cap = 4096 + 64 * (len(xyz) + len(normals))
+        buf = np.zeros(cap, np.uint8)
+        size = self.L.ref_write_ply(_ptr(xyz, _f32p), len(xyz), _ptr(normals, _f32p),
+                                    len(normals), self.FORMATS[fmt], _ptr(buf, _u8p), cap)
+        assert size <= cap
+        return buf[:size].tobytes()
+
+    def read(self, data, max_rows=1 << 22):
+        b = np.frombuffer(data, np.uint8)
+        xyz = np.zeros((max_rows, 3), np.float32)
+        nrm = np.zeros((max_rows, 3), np.float32)
+        counts = (C.c_size_t * 2)()
+        self.L.ref_read_ply(_ptr(b, _u8p), len(b), _ptr(xyz, _f32p), max_rows, _ptr(nrm, _f32p),
+                            max_rows, counts)
+        return xyz[: counts[0]].copy(), nrm[: counts[1]].copy()
 
 
 class RefBridge:
