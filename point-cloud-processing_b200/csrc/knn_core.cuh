@@ -409,8 +409,9 @@ PCPX_HD float candidate_d2(const float4& c, float qx, float qy, float qz, float 
 {
     float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
     float d2       = sqdist_x(dx, dy, dz);
-    // exclusion box, common/vector3d_queries.hpp:31-35,59-63 (strict <, all axes)
-    if (fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps)
+    // exclusion box, common/vector3d_queries.hpp:31-35,59-63 (strict <, all axes): all three
+    // below eps <=> the largest is
+    if (fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz)) < eps)
         d2 = INFINITY;
     return d2;
 }
@@ -418,12 +419,17 @@ PCPX_HD float candidate_d2(const float4& c, float qx, float qy, float qz, float 
 // Pass 1 over one chunk of spans: distances of every candidate go through the sorted list, two
 // at a time, with the next pair already in flight; candidates at or below the running worst
 // distance are remembered for pass 2.  Spans whose bound exceeds the running worst are skipped.
+//
+// The short list's fill count lives in a register for the whole walk (as a struct member it is
+// reloaded from local memory after every store into pos[]), and the two pushes of a step are
+// predicated stores behind ONE capacity test instead of two branches each.
 template <int K, class SL>
 PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, float qy, float qz,
                            float eps, TopD<K>& top, SL& sl, SearchStats* st)
 {
     int e = 0;                // next span to enter
     uint32_t p = 0, pend = 0; // position inside the current span
+    uint32_t sn = sl.n;
     float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
     // the next span's record is fetched from local memory one span ahead, so that entering it
     // does not wait on the load
@@ -469,15 +475,32 @@ PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, floa
         float const d0 = candidate_d2(a0, qx, qy, qz, eps);
         float const d1 = has1 ? candidate_d2(a1, qx, qy, qz, eps) : INFINITY;
         float const w = fminf(top.worst(), 3.402823466e+38f); // finite: +inf (excluded) never passes
-        if (d0 <= w)
-            sl.push(p);
-        if (d1 <= w)
-            sl.push(p + 1);
+        bool const k0 = d0 <= w, k1 = d1 <= w;
+        if (sn + 2u <= (uint32_t)SL::capacity)
+        {
+            if (k0)
+                sl.pos[sn] = p;
+            sn += k0;
+            if (k1)
+                sl.pos[sn] = p + 1;
+            sn += k1;
+        }
+        else // the list is (nearly) full: pass 2 will walk the region again
+        {
+            if (k0 && sn < (uint32_t)SL::capacity)
+                sl.pos[sn] = p;
+            sn += k0;
+            if (k1 && sn < (uint32_t)SL::capacity)
+                sl.pos[sn] = p + 1;
+            sn += k1;
+        }
         top.insert2(d0, d1);
         if (st)
             st->candidates += has1 ? 2 : 1;
         p += 2;
     }
+    sl.n        = sn;
+    sl.overflow = sl.overflow || sn > (uint32_t)SL::capacity;
 }
 
 // What a kNN-shaped call tries first: a (2 * rings + 1)^3 block at `level`.
