@@ -264,13 +264,17 @@ def run_ours(args):
     d_own, d_stage = d_buf[:n_owned], d_stage_buf[:n_owned]
     d_own.copy_(h_xyz)
     slab_lo, slab_hi = float(rank * L), float((rank + 1) * L)
+    # strips hold about n * HALO / L points; twice that is the exchange capacity
+    scratch = None
+    if world > 1:
+        scratch = pcpx.sharding.HaloScratch(int(2 * n_owned * HALO / L) + 4096, "cuda")
 
     def local_cloud(d_points, d_buffer):
         """N > 1: the exchange step — boundary strips go to the neighbouring ranks over NCCL"""
         if world == 1:
             return d_points
         return pcpx.sharding.exchange_halo(d_points, 0, slab_lo, slab_hi, HALO, rank, world,
-                                           dist, buffer=d_buffer)[0]
+                                           dist, buffer=d_buffer, scratch=scratch)[0]
 
     n_local = int(local_cloud(d_own, d_buf).shape[0])
     d_nrm = torch.empty((n_local, 3), dtype=torch.float32, device="cuda")

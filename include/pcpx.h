@@ -377,6 +377,32 @@ int pcpx_orient_normals_graph(
     uint32_t* out_levels,
     uint64_t* out_reached);
 
+/* ---- multi-GPU plumbing ---------------------------------------------------- */
+
+/*
+ * Cut the two boundary strips of a slab out of a device-resident cloud: rows whose coordinate
+ * `axis` is < below go to out_below, rows with coordinate > above to out_above, both in input
+ * order (an ordered compaction, so the assembled local cloud is reproducible).  These are the
+ * strips a rank sends to its neighbours across the two inner faces of its slab
+ * (point-cloud-processing_b200/sharding.py: exchange_halo).  xyz / out_*: DEVICE memory; out_*
+ * hold `capacity` packed rows each, rows beyond the capacity are counted but not written.
+ * counts[0..1] (host or device memory) receive the two strip sizes.  cuda_stream: the
+ * cudaStream_t to run on (NULL = the legacy default stream); the call returns after the stream
+ * has finished the work.
+ */
+int pcpx_extract_bands(
+    const float* xyz,
+    size_t n,
+    size_t stride_bytes,
+    int axis,
+    float below,
+    float above,
+    float* out_below,
+    float* out_above,
+    size_t capacity,
+    uint64_t* counts,
+    void* cuda_stream);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 
 /* Device time (CUDA events on the launching stream) of the last call of each kind made

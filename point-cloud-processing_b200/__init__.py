@@ -19,6 +19,7 @@ from .capi import (  # noqa: F401
     bilateral_filter_points,
     device_count,
     exported_symbols,
+    extract_bands,
     lib,
     normals_from_neighbourhoods,
     orient_normals_graph,

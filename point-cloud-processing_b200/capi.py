@@ -94,6 +94,9 @@ _SIGNATURES = {
     "pcpx_orient_normals_graph": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                             C.c_uint32, C.c_int, C.c_int, C.c_void_p,
                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "pcpx_extract_bands": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_float,
+                                     C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                     C.c_void_p]),
     "pcpx_last_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "pcpx_set_tuning": (C.c_int, [C.c_char_p, C.c_double]),
     "pcpx_debug_knn_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]),
@@ -204,6 +207,17 @@ def orient_normals_graph(xyz, neighbours, normals, nearest_first=False, device=-
     _check(lib().pcpx_orient_normals_graph(bx.ptr, n, 12, bn.ptr, k, 1 if nearest_first else 0,
                                            device, bo.ptr, None, None))
     return normals
+
+
+def extract_bands(xyz, axis, below, above, out_below, out_above, counts, stream=None):
+    """Boundary strips of a device-resident slab (CUDA tensors throughout; see pcpx.h).
+    `counts`: a 2-element int64 CUDA tensor or numpy uint64 array."""
+    n = _count(xyz)
+    cap = min(out_below.shape[0], out_above.shape[0])
+    cptr = counts.data_ptr() if _is_torch(counts) else counts.ctypes.data
+    _check(lib().pcpx_extract_bands(xyz.data_ptr(), n, 12, int(axis), float(below), float(above),
+                                    out_below.data_ptr(), out_above.data_ptr(), cap, cptr,
+                                    stream))
 
 
 def wlop(xyz, n_out, h, mu=0.45, iterations=10, uniform=True, initial=None, seed=0, device=-1,

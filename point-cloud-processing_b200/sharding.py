@@ -48,15 +48,86 @@ def query_slice(n, rank, world):
     return b, e
 
 
-def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None, buffer=None):
+class HaloScratch:
+    """Device buffers of the fast exchange path, allocated once per rank: fixed-capacity strip
+    buffers (so that the strip sizes travel in the same message round as the strips) and the
+    two size counters."""
+
+    def __init__(self, capacity, device):
+        import torch
+
+        self.capacity = int(capacity)
+        f = dict(dtype=torch.float32, device=device)
+        self.send = {-1: torch.empty((self.capacity, 3), **f), +1: torch.empty((self.capacity, 3), **f)}
+        self.recv = {-1: torch.empty((self.capacity, 3), **f), +1: torch.empty((self.capacity, 3), **f)}
+        self.counts_out = torch.zeros(2, dtype=torch.int64, device=device)
+        self.counts_in = torch.zeros(2, dtype=torch.int64, device=device)
+
+
+def _exchange_halo_device(own_xyz, axis, lo, hi, halo, rank, world, dist, group, buffer, scratch):
+    """CUDA path: strips cut by one ordered compaction kernel of the library
+    (pcpx_extract_bands), sizes and strips exchanged in ONE round of point-to-point messages,
+    strips copied behind the owned rows of `buffer`."""
+    import torch
+
+    from . import capi
+
+    inf = float("inf")
+    below = lo + halo if rank > 0 else -inf
+    above = hi - halo if rank < world - 1 else inf
+    stream = torch.cuda.current_stream().cuda_stream
+    capi.extract_bands(own_xyz, axis, below, above, scratch.send[-1], scratch.send[+1],
+                       scratch.counts_out, stream=stream)
+    ops = []
+    for side, peer in ((-1, rank - 1), (+1, rank + 1)):
+        if peer < 0 or peer >= world:
+            continue
+        k = 0 if side < 0 else 1
+        ops.append(dist.P2POp(dist.isend, scratch.counts_out[k:k + 1], peer, group))
+        ops.append(dist.P2POp(dist.irecv, scratch.counts_in[k:k + 1], peer, group))
+        ops.append(dist.P2POp(dist.isend, scratch.send[side], peer, group))
+        ops.append(dist.P2POp(dist.irecv, scratch.recv[side], peer, group))
+    if rank == 0:
+        scratch.counts_in[0] = 0
+    if rank == world - 1:
+        scratch.counts_in[1] = 0
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    sent = scratch.counts_out.tolist()
+    got = scratch.counts_in.tolist()  # one device -> host read for both neighbours
+    if max(sent + got) > scratch.capacity:
+        raise RuntimeError("halo strip of %d points exceeds the exchange capacity %d"
+                           % (max(sent + got), scratch.capacity))
+    n_own = own_xyz.shape[0]
+    at = n_own
+    if buffer.shape[0] < n_own + got[0] + got[1]:
+        raise RuntimeError("local-cloud buffer too small for the received strips")
+    for k, side in ((0, -1), (1, +1)):
+        if got[k]:
+            buffer[at:at + got[k]].copy_(scratch.recv[side][:got[k]])
+            at += got[k]
+    return buffer[:at], n_own
+
+
+def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None, buffer=None,
+                  scratch=None):
     """The one exchange step of the sharded path: every rank sends the points of its slab that
     lie within `halo` of an inner face to the neighbour across that face and receives the
     neighbour's strip (torch tensors on any device; NCCL moves device tensors over NVLink, gloo
     CPU tensors in the tests).  Returns the local cloud [own ; from the left ; from the right]
-    and the number of owned points.  Strip sizes are exchanged first (two 8-byte messages).
-    When `own_xyz` is the leading rows of a larger `buffer`, the strips are received straight
-    into the rows behind it and the local cloud is a view of `buffer` (no concatenation copy)."""
+    and the number of owned points.
+
+    With CUDA tensors, `own_xyz` the leading rows of `buffer` and a `HaloScratch`, the device
+    path above runs.  Otherwise (CPU tensors, the gloo tests): strips by boolean masking, strip
+    sizes exchanged first (two 8-byte messages), then the strips; when `own_xyz` is the leading
+    rows of a larger `buffer` the strips are received straight into the rows behind it."""
     import torch
+
+    if (scratch is not None and own_xyz.is_cuda and buffer is not None
+            and buffer.data_ptr() == own_xyz.data_ptr()):
+        return _exchange_halo_device(own_xyz, axis, lo, hi, halo, rank, world, dist, group,
+                                     buffer, scratch)
 
     c = own_xyz[:, axis]
     send = {}
