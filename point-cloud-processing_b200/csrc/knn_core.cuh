@@ -325,13 +325,21 @@ struct CellList
     int n;
 };
 
+#ifndef PCPX_COLLECT_UNROLL
+#define PCPX_COLLECT_UNROLL 27
+#endif
+constexpr int kCollectUnroll = PCPX_COLLECT_UNROLL;
+
 // Rings 0-1 (the 3^3 block): every in-grid cell is looked up, in visiting order.
 PCPX_HD void collect_block27(const GridView& g, const BlockGeom& b, int level, CellList& cl,
                              SearchStats* st)
 {
     uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
     int n               = 0;
-#pragma unroll 1
+    // Fully unrolled (kCollectUnroll): offsets, key deltas and the grid-edge tests become
+    // immediates, which halves the instructions of a lookup.  The candidate walk is NOT inside
+    // this loop, so the unrolled code is 27 short lookups, not 27 copies of the hot loop.
+#pragma unroll kCollectUnroll
     for (int i = 0; i < 27; ++i)
     {
         Offset3 const o = block27_offset(i);
