@@ -318,11 +318,22 @@ PCPX_HD Offset3 ring_offset(int i)
 // at the same time); the candidate loops then run FLAT per lane over these spans, so a warp's
 // cost is max over lanes of (total candidates) rather than the sum over cells of max over lanes
 // of (cell size).  Lives in local memory (dynamically indexed), which L1 caches.
+// Entry n is a sentinel (start = end = kSpanEnd, bound -1: never pruned) that ends the walk, so
+// the walk tests no counter; entry n + 1 exists only so that the walk's one-ahead prefetch of
+// the record after the sentinel stays inside the arrays.
+constexpr uint32_t kSpanEnd = 0xFFFFFFFFu;
 struct CellList
 {
-    uint32_t start[27], end[27];
-    float lb2[27];
+    uint32_t start[29], end[29];
+    float lb2[29];
     int n;
+
+    PCPX_HD void close(int count)
+    {
+        n            = count;
+        start[count] = kSpanEnd, end[count] = kSpanEnd;
+        lb2[count]   = -1.f;
+    }
 };
 
 #ifndef PCPX_COLLECT_UNROLL
@@ -355,7 +366,7 @@ PCPX_HD void collect_block27(const GridView& g, const BlockGeom& b, int level, C
         cl.lb2[n]   = cell_lb2_near(b, o.dx, o.dy, o.dz);
         ++n;
     }
-    cl.n = n;
+    cl.close(n);
 }
 
 // Ring 2, in chunks of up to 27 spans starting at ring offset `i` (advanced): cells outside the
@@ -385,7 +396,7 @@ PCPX_HD void collect_ring2(const GridView& g, const BlockGeom& b, int level, int
         cl.lb2[n]   = lb;
         ++n;
     }
-    cl.n = n;
+    cl.close(n);
 }
 
 // Candidates that were at or below the list's worst distance when pass 1 met them — a superset
@@ -440,39 +451,29 @@ PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, floa
     uint32_t sn = sl.n;
     float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
     // the next span's record is fetched from local memory one span ahead, so that entering it
-    // does not wait on the load
-    float nlb    = 0.f;
-    uint32_t ns = 0, nen = 0;
-    if (cl.n > 0)
-        nlb = cl.lb2[0], ns = cl.start[0], nen = cl.end[0];
+    // does not wait on the load; the sentinel record makes every load unconditional
+    float nlb   = cl.lb2[0];
+    uint32_t ns = cl.start[0], nen = cl.end[0];
     for (;;)
     {
-        bool done = false;
         if (p >= pend)
         {
+            uint32_t s, en;
             for (;;)
             {
-                if (e >= cl.n)
-                {
-                    done = true;
-                    break;
-                }
-                float const lb    = nlb;
-                uint32_t const s  = ns;
-                uint32_t const en = nen;
+                float const lb = nlb;
+                s = ns, en = nen;
                 ++e;
-                if (e < cl.n)
-                    nlb = cl.lb2[e], ns = cl.start[e], nen = cl.end[e];
-                if (lb > top.worst()) // equal: a tie may hide there
-                    continue;
-                p = s, pend = en;
-                c0 = load_pt(g.pts + p);
-                c1 = load_pt(g.pts + (p + 1 < pend ? p + 1 : p));
-                break;
+                nlb = cl.lb2[e], ns = cl.start[e], nen = cl.end[e];
+                if (!(lb > top.worst())) // equal: a tie may hide there
+                    break;
             }
+            if (s == kSpanEnd)
+                break;
+            p = s, pend = en;
+            c0 = load_pt(g.pts + p);
+            c1 = load_pt(g.pts + (p + 1 < pend ? p + 1 : p));
         }
-        if (done)
-            break;
         bool const has1 = p + 1 < pend;
         float4 const a0 = c0, a1 = c1;
         if (p + 2 < pend) // prefetch the next pair
