@@ -55,8 +55,17 @@ def build(force=False, verbose=False, defines=(), out=None):
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
 
+    headers = [os.path.join(ROOT, "include", "pcpx.h")] + [
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
     def compile_one(unit):
         obj = os.path.join(OBJDIR, unit.replace(".cu", ".o"))
+        src = os.path.join(CSRC, unit)
+        # an object newer than its source and every header is kept (query.cu takes minutes)
+        if (not defines and not verbose and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(newest_header, os.path.getmtime(src))):
+            return obj
         cmd = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, unit), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -80,6 +80,8 @@ struct __align__(16) HashSlot
     uint32_t start, count;   // the cell's span in the sorted point array
 };
 
+constexpr uint32_t kPtsPad = 4; // readable (zero) entries behind the sorted point array
+
 struct GridView
 {
     float ox, oy, oz; // root cube origin

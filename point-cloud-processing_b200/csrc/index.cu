@@ -447,7 +447,10 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
     ix.code_bits = 3u * (uint32_t)g.lcap;
 
     // 4. codes -> sort -> SoA
-    ix.pts.alloc(std::max<size_t>(n, 1));
+    // kPtsPad readable entries behind the last point: the kNN walk loads up to three entries
+    // past the end of a span without a bounds test (knn_core.cuh: knn_scan_dist)
+    ix.pts.alloc(n + kPtsPad);
+    PCPX_CUDA(cudaMemsetAsync(ix.pts.get() + n, 0, kPtsPad * sizeof(float4), ix.stream));
     g.pts = ix.pts.get();
     SortScratch sc;
     Event ev_sort0, ev_sort1;

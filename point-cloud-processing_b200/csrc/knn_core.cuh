@@ -472,17 +472,19 @@ PCPX_HD void knn_scan_dist(const GridView& g, const CellList& cl, float qx, floa
                 break;
             p = s, pend = en;
             c0 = load_pt(g.pts + p);
-            c1 = load_pt(g.pts + (p + 1 < pend ? p + 1 : p));
+            c1 = load_pt(g.pts + p + 1);
         }
+        // The loads run up to three entries past the span (and, at the very end, past the last
+        // point: the array is padded by kPtsPad) rather than test for its end; what they fetch
+        // there is never used — the second candidate is masked by has1 and the prefetched pair is
+        // overwritten when the next span is entered.
         bool const has1 = p + 1 < pend;
         float4 const a0 = c0, a1 = c1;
-        if (p + 2 < pend) // prefetch the next pair
-        {
-            c0 = load_pt(g.pts + p + 2);
-            c1 = load_pt(g.pts + (p + 3 < pend ? p + 3 : p + 2));
-        }
+        c0 = load_pt(g.pts + p + 2); // prefetch the next pair
+        c1 = load_pt(g.pts + p + 3);
         float const d0 = candidate_d2(a0, qx, qy, qz, eps);
-        float const d1 = has1 ? candidate_d2(a1, qx, qy, qz, eps) : INFINITY;
+        float const d1x = candidate_d2(a1, qx, qy, qz, eps);
+        float const d1  = has1 ? d1x : INFINITY;
         float const w = fminf(top.worst(), 3.402823466e+38f); // finite: +inf (excluded) never passes
         bool const k0 = d0 <= w, k1 = d1 <= w;
         if (sn + 2u <= (uint32_t)SL::capacity)

@@ -12,9 +12,12 @@
 //     (per-entry count -> exclusive scan -> emit), not a sort.
 // All sizes stay on the device; the host queues levels in batches and only reads back the
 // frontier size once per batch to see whether the search has ended.  No CPU path.
+#include <cooperative_groups.h>
+
 #include "api_util.hpp"
 
 using namespace pcpx;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -76,41 +79,45 @@ __device__ __forceinline__ uint32_t edge_target(const uint32_t* __restrict__ nbr
     return nbr[(size_t)u * k + (reverse ? k - 1 - e : e)];
 }
 
-__global__ void __launch_bounds__(kB) propose_kernel(const BfsState* st, int parity,
-                                                     const uint32_t* __restrict__ frontier,
-                                                     const uint32_t* __restrict__ nbr, uint32_t k,
-                                                     int reverse,
-                                                     const uint8_t* __restrict__ visited,
-                                                     unsigned long long* __restrict__ key)
+// ---- the four phases of one BFS level ---------------------------------------------------------
+// Written as device functions over (tid, nthreads) so that the same code runs as four small
+// kernels or inside the persistent cooperative kernel below.  Arrays other phases write
+// (frontier, visited, key, won, normals, the state) are deliberately NOT const __restrict__: in
+// the persistent kernel they change between phases and must not go through the read-only path;
+// they are read with ld.global.cg (L2), never from a possibly stale L1 line.
+
+__device__ __forceinline__ void propose_phase(const BfsState* st, int parity,
+                                              const uint32_t* frontier,
+                                              const uint32_t* __restrict__ nbr, uint32_t k,
+                                              int reverse, const uint8_t* visited,
+                                              unsigned long long* key, uint32_t tid,
+                                              uint32_t nthreads)
 {
-    unsigned long long const total = (unsigned long long)st->size[parity] * k;
-    for (unsigned long long c = blockIdx.x * (unsigned long long)kB + threadIdx.x; c < total;
-         c += (unsigned long long)gridDim.x * kB)
+    unsigned long long const total = (unsigned long long)__ldcg(&st->size[parity]) * k;
+    for (unsigned long long c = tid; c < total; c += nthreads)
     {
         uint32_t const i = (uint32_t)(c / k), e = (uint32_t)(c % k);
-        uint32_t const v = edge_target(nbr, frontier[i], k, e, reverse);
-        if (v != kPad && !visited[v])
+        uint32_t const v = edge_target(nbr, __ldcg(frontier + i), k, e, reverse);
+        if (v != kPad && !__ldcg(visited + v))
             atomicMin(&key[v], c);
     }
 }
 
 // per frontier entry: flip the children it wins (search.hpp:72-78 + estimate_normals.hpp:289-300)
 // and count them
-__global__ void __launch_bounds__(kB) accept_kernel(const BfsState* st, int parity,
-                                                    const uint32_t* __restrict__ frontier,
-                                                    const uint32_t* __restrict__ nbr, uint32_t k,
-                                                    int reverse,
-                                                    const uint8_t* __restrict__ visited,
-                                                    const unsigned long long* __restrict__ key,
-                                                    float* __restrict__ normals,
-                                                    uint32_t* __restrict__ won)
+__device__ __forceinline__ void accept_phase(const BfsState* st, int parity,
+                                             const uint32_t* frontier,
+                                             const uint32_t* __restrict__ nbr, uint32_t k,
+                                             int reverse, const uint8_t* visited,
+                                             const unsigned long long* key, float* normals,
+                                             uint32_t* won, uint32_t tid, uint32_t nthreads)
 {
-    uint32_t const m = st->size[parity];
-    for (uint32_t i = blockIdx.x * kB + threadIdx.x; i < m; i += gridDim.x * kB)
+    uint32_t const m = __ldcg(&st->size[parity]);
+    for (uint32_t i = tid; i < m; i += nthreads)
     {
-        uint32_t const u = frontier[i];
-        float const ax = normals[3 * (size_t)u], ay = normals[3 * (size_t)u + 1],
-                    az = normals[3 * (size_t)u + 2];
+        uint32_t const u = __ldcg(frontier + i);
+        float const ax = __ldcg(normals + 3 * (size_t)u), ay = __ldcg(normals + 3 * (size_t)u + 1),
+                    az = __ldcg(normals + 3 * (size_t)u + 2);
         uint32_t cnt = 0;
         for (uint32_t e0 = 0; e0 < k; e0 += kChunk)
         {
@@ -123,15 +130,15 @@ __global__ void __launch_bounds__(kB) accept_kernel(const BfsState* st, int pari
                 v[c] = e0 + c < k ? edge_target(nbr, u, k, e0 + c, reverse) : kPad;
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
-                mine[c] = v[c] != kPad && !visited[v[c]] &&
-                          key[v[c]] == (unsigned long long)i * k + e0 + c;
+                mine[c] = v[c] != kPad && !__ldcg(visited + v[c]) &&
+                          __ldcg(key + v[c]) == (unsigned long long)i * k + e0 + c;
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
             {
                 if (!mine[c])
                     continue;
                 float* nv      = normals + 3 * (size_t)v[c];
-                float const bx = nv[0], by = nv[1], bz = nv[2];
+                float const bx = __ldcg(nv), by = __ldcg(nv + 1), bz = __ldcg(nv + 2);
                 // common::inner_product (common/norm.hpp:34-45): v2 * v1 per axis, left to right
                 float const prod =
                     __fadd_rn(__fadd_rn(__fmul_rn(bx, ax), __fmul_rn(by, ay)), __fmul_rn(bz, az));
@@ -144,20 +151,22 @@ __global__ void __launch_bounds__(kB) accept_kernel(const BfsState* st, int pari
     }
 }
 
-// exclusive scan of won[0 .. m) in place by ONE block (the sum of all frontier sizes over a whole
-// search is n, so this never does more than n / 1024 rounds in total); publishes the next size
-__global__ void __launch_bounds__(1024) scan_kernel(BfsState* st, int parity, uint32_t* won)
+// exclusive scan of won[0 .. m) in place by ONE block of up to 1024 threads (the sum of all
+// frontier sizes over a whole search is n, so this never does more than n / blockDim rounds in
+// total); publishes the next frontier size
+__device__ __forceinline__ void scan_phase(BfsState* st, int parity, uint32_t* won)
 {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
-    uint32_t const m = st->size[parity];
+    uint32_t const m      = __ldcg(&st->size[parity]);
+    uint32_t const nwarps = blockDim.x >> 5;
     if (threadIdx.x == 0)
         carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < m; base += 1024)
+    for (uint32_t base = 0; base < m; base += blockDim.x)
     {
         uint32_t const i = base + threadIdx.x;
-        uint32_t const x = i < m ? won[i] : 0u;
+        uint32_t const x = i < m ? __ldcg(won + i) : 0u;
         uint32_t incl    = x;
         for (int o = 1; o < 32; o <<= 1)
         {
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(BfsState* st, int parity, ui
         __syncthreads();
         if (threadIdx.x < 32)
         {
-            uint32_t w = warp_sums[threadIdx.x];
+            uint32_t w = threadIdx.x < nwarps ? warp_sums[threadIdx.x] : 0u;
             for (int o = 1; o < 32; o <<= 1)
             {
                 uint32_t const y = __shfl_up_sync(0xFFFFFFFFu, w, o);
@@ -196,19 +205,17 @@ __global__ void __launch_bounds__(1024) scan_kernel(BfsState* st, int parity, ui
     }
 }
 
-__global__ void __launch_bounds__(kB) emit_kernel(const BfsState* st, int parity,
-                                                  const uint32_t* __restrict__ frontier,
-                                                  const uint32_t* __restrict__ nbr, uint32_t k,
-                                                  int reverse, uint8_t* __restrict__ visited,
-                                                  const unsigned long long* __restrict__ key,
-                                                  const uint32_t* __restrict__ offset,
-                                                  uint32_t* __restrict__ next)
+__device__ __forceinline__ void emit_phase(const BfsState* st, int parity, const uint32_t* frontier,
+                                           const uint32_t* __restrict__ nbr, uint32_t k,
+                                           int reverse, uint8_t* visited,
+                                           const unsigned long long* key, const uint32_t* offset,
+                                           uint32_t* next, uint32_t tid, uint32_t nthreads)
 {
-    uint32_t const m = st->size[parity];
-    for (uint32_t i = blockIdx.x * kB + threadIdx.x; i < m; i += gridDim.x * kB)
+    uint32_t const m = __ldcg(&st->size[parity]);
+    for (uint32_t i = tid; i < m; i += nthreads)
     {
-        uint32_t const u = frontier[i];
-        uint32_t w       = offset[i];
+        uint32_t const u = __ldcg(frontier + i);
+        uint32_t w       = __ldcg(offset + i);
         for (uint32_t e0 = 0; e0 < k; e0 += kChunk)
         {
             uint32_t v[kChunk];
@@ -219,8 +226,9 @@ __global__ void __launch_bounds__(kB) emit_kernel(const BfsState* st, int parity
             // the owner of v is unique, so nobody else tests visited[v] with a matching key
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
-                mine[c] = v[c] != kPad && key[v[c]] == (unsigned long long)i * k + e0 + c &&
-                          !visited[v[c]];
+                mine[c] = v[c] != kPad &&
+                          __ldcg(key + v[c]) == (unsigned long long)i * k + e0 + c &&
+                          !__ldcg(visited + v[c]);
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
                 if (mine[c])
@@ -229,6 +237,74 @@ __global__ void __launch_bounds__(kB) emit_kernel(const BfsState* st, int parity
                     visited[v[c]] = 1;
                 }
         }
+    }
+}
+
+__global__ void __launch_bounds__(kB) propose_kernel(const BfsState* st, int parity,
+                                                     const uint32_t* frontier, const uint32_t* nbr,
+                                                     uint32_t k, int reverse,
+                                                     const uint8_t* visited,
+                                                     unsigned long long* key)
+{
+    propose_phase(st, parity, frontier, nbr, k, reverse, visited, key,
+                  blockIdx.x * kB + threadIdx.x, gridDim.x * kB);
+}
+__global__ void __launch_bounds__(kB) accept_kernel(const BfsState* st, int parity,
+                                                    const uint32_t* frontier, const uint32_t* nbr,
+                                                    uint32_t k, int reverse, const uint8_t* visited,
+                                                    const unsigned long long* key, float* normals,
+                                                    uint32_t* won)
+{
+    accept_phase(st, parity, frontier, nbr, k, reverse, visited, key, normals, won,
+                 blockIdx.x * kB + threadIdx.x, gridDim.x * kB);
+}
+__global__ void __launch_bounds__(1024) scan_kernel(BfsState* st, int parity, uint32_t* won)
+{
+    scan_phase(st, parity, won);
+}
+__global__ void __launch_bounds__(kB) emit_kernel(const BfsState* st, int parity,
+                                                  const uint32_t* frontier, const uint32_t* nbr,
+                                                  uint32_t k, int reverse, uint8_t* visited,
+                                                  const unsigned long long* key,
+                                                  const uint32_t* offset, uint32_t* next)
+{
+    emit_phase(st, parity, frontier, nbr, k, reverse, visited, key, offset, next,
+               blockIdx.x * kB + threadIdx.x, gridDim.x * kB);
+}
+
+// The whole search in ONE cooperative launch: the four phases of every level separated by grid
+// barriers (about 2 us each on 148 resident blocks) instead of kernel boundaries.  Every block
+// executes every barrier: nothing returns early, the loop ends for all blocks on the same
+// (uniformly read) empty frontier.
+__global__ void __launch_bounds__(kB) bfs_persistent_kernel(BfsState* st, uint32_t* fa,
+                                                            uint32_t* fb, const uint32_t* nbr,
+                                                            uint32_t k, int reverse,
+                                                            uint8_t* visited,
+                                                            unsigned long long* key,
+                                                            float* normals, uint32_t* won,
+                                                            uint32_t max_levels)
+{
+    cg::grid_group grid  = cg::this_grid();
+    uint32_t const tid   = blockIdx.x * kB + threadIdx.x;
+    uint32_t const nthr  = gridDim.x * kB;
+    uint32_t *cur = fa, *nxt = fb;
+    int parity = 0;
+    for (uint32_t level = 0; level < max_levels; ++level)
+    {
+        if (__ldcg(&st->size[parity]) == 0u)
+            break;
+        propose_phase(st, parity, cur, nbr, k, reverse, visited, key, tid, nthr);
+        grid.sync();
+        accept_phase(st, parity, cur, nbr, k, reverse, visited, key, normals, won, tid, nthr);
+        grid.sync();
+        if (blockIdx.x == 0)
+            scan_phase(st, parity, won);
+        grid.sync();
+        emit_phase(st, parity, cur, nbr, k, reverse, visited, key, won, nxt, tid, nthr);
+        grid.sync();
+        uint32_t* t = cur;
+        cur = nxt, nxt = t;
+        parity ^= 1;
     }
 }
 
@@ -268,10 +344,34 @@ BfsState run_search(cudaStream_t s, size_t n, uint32_t k, const uint32_t* nbr, i
     start_kernel<<<1, 1, 0, s>>>(st, fa.get(), visited.get(), d_nrm);
     PCPX_CHECK_LAUNCH();
     ++launches;
+    BfsState h{};
+    if (k > 0 && tuning().orient_persistent)
+    {
+        // one block per SM keeps the grid barrier cheap; the launch fails (and we fall through to
+        // the per-level kernels) where cooperative launches are unsupported
+        int dev = 0, sms = 0, coop = 0, per_sm = 0;
+        PCPX_CUDA(cudaGetDevice(&dev));
+        PCPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PCPX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        PCPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_persistent_kernel, kB, 0));
+        if (coop && per_sm >= 1)
+        {
+            uint32_t *a = fa.get(), *b = fb.get(), *w = won.get();
+            uint8_t* vis = visited.get();
+            unsigned long long* ky = key.get();
+            uint32_t max_levels = (uint32_t)std::min<size_t>(n, 0xFFFFFFFFu);
+            void* args[] = {&st, &a, &b, &nbr, &k, &reverse, &vis, &ky, &d_nrm, &w, &max_levels};
+            PCPX_CUDA(cudaLaunchCooperativeKernel((void*)bfs_persistent_kernel, dim3((unsigned)sms),
+                                                  dim3(kB), args, 0, s));
+            ++launches;
+            PCPX_CUDA(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
+            PCPX_CUDA(cudaStreamSynchronize(s));
+            return h;
+        }
+    }
     uint32_t const gn = grid_of(n);
     uint32_t *cur = fa.get(), *nxt = fb.get();
     int parity = 0;
-    BfsState h{};
     for (uint64_t level = 0; level < n && k > 0;)
     {
         // a batch of levels, then one look at the frontier size; levels queued past the end of

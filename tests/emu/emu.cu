@@ -115,7 +115,7 @@ void* emu_index_create(const float* xyz, size_t n, int use_box, const float* box
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(),
                      [&](uint32_t a, uint32_t b) { return code[a] < code[b]; });
-    ix->pts.resize(std::max<size_t>(n, 1));
+    ix->pts.assign(n + kPtsPad, make_float4(0.f, 0.f, 0.f, 0.f)); // padded like the device array
     for (size_t i = 0; i < n; ++i)
     {
         uint32_t o = order[i];
