@@ -422,10 +422,7 @@ int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
 
 /* Process-wide tunables (performance only, never results).  Known names:
  *   "success_margin"  a kNN-shaped call first tries the cheapest (level, rings) block whose ball
- *                     is expected to hold success_margin * (k + 1) points (default 1.15).
- *   "orient_persistent" 1 (default): pcpx_orient_normals runs its search as one cooperative
- *                     kernel with grid barriers between the phases of a level; 0: four small
- *                     kernels per level. */
+ *                     is expected to hold success_margin * (k + 1) points (default 1.15). */
 int pcpx_set_tuning(const char* name, double value);
 
 /* Search work of a self-kNN over the whole cloud, summed over queries:

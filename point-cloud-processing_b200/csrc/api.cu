@@ -392,8 +392,6 @@ int pcpx_set_tuning(const char* name, double value)
             fail(PCPX_ERR_INVALID_ARG, "name is NULL");
         if (!std::strcmp(name, "success_margin"))
             tuning().success_margin = (float)value;
-        else if (!std::strcmp(name, "orient_persistent"))
-            tuning().orient_persistent = value != 0.0;
         else
             fail(PCPX_ERR_INVALID_ARG, "unknown tuning parameter '%s'", name);
     });

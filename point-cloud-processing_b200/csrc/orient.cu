@@ -12,18 +12,15 @@
 //     (per-entry count -> exclusive scan -> emit), not a sort.
 // All sizes stay on the device; the host queues levels in batches and only reads back the
 // frontier size once per batch to see whether the search has ended.  No CPU path.
-#include <cooperative_groups.h>
-
 #include "api_util.hpp"
 
 using namespace pcpx;
-namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int kB         = 256;
 constexpr int kGrid      = 148 * 4;
-constexpr int kChunk     = 8; // edges whose loads are in flight together
+constexpr int kChunk     = 8;  // edges whose loads are in flight together
 constexpr uint32_t kPad  = 0xFFFFFFFFu;
 
 struct BfsState
@@ -80,11 +77,11 @@ __device__ __forceinline__ uint32_t edge_target(const uint32_t* __restrict__ nbr
 }
 
 // ---- the four phases of one BFS level ---------------------------------------------------------
-// Written as device functions over (tid, nthreads) so that the same code runs as four small
-// kernels or inside the persistent cooperative kernel below.  Arrays other phases write
-// (frontier, visited, key, won, normals, the state) are deliberately NOT const __restrict__: in
-// the persistent kernel they change between phases and must not go through the read-only path;
-// they are read with ld.global.cg (L2), never from a possibly stale L1 line.
+// Four small kernels per level.  (A single cooperative kernel with grid barriers between the
+// phases was measured and is not faster: 49 - 62 ms against 48 - 55 ms for 996 levels over 5 M
+// points; the level time is the chain of dependent random loads, not the kernel boundaries.)
+// Arrays other phases write (frontier, visited, key, won, normals, the state) are read with
+// ld.global.cg and are deliberately not const __restrict__.
 
 __device__ __forceinline__ void propose_phase(const BfsState* st, int parity,
                                               const uint32_t* frontier,
@@ -94,6 +91,17 @@ __device__ __forceinline__ void propose_phase(const BfsState* st, int parity,
                                               uint32_t nthreads)
 {
     unsigned long long const total = (unsigned long long)__ldcg(&st->size[parity]) * k;
+    if (total <= 0xFFFFFFFFull) // the usual case: 32-bit index arithmetic (k is not a power of 2)
+    {
+        for (uint32_t c = tid; c < (uint32_t)total; c += nthreads)
+        {
+            uint32_t const i = c / k, e = c - i * k;
+            uint32_t const v = edge_target(nbr, __ldcg(frontier + i), k, e, reverse);
+            if (v != kPad && !__ldcg(visited + v))
+                atomicMin(&key[v], (unsigned long long)c);
+        }
+        return;
+    }
     for (unsigned long long c = tid; c < total; c += nthreads)
     {
         uint32_t const i = (uint32_t)(c / k), e = (uint32_t)(c % k);
@@ -127,11 +135,25 @@ __device__ __forceinline__ void accept_phase(const BfsState* st, int parity,
             bool mine[kChunk];
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
-                v[c] = e0 + c < k ? edge_target(nbr, u, k, e0 + c, reverse) : kPad;
+            {
+                uint32_t const t = edge_target(nbr, u, k, e0 + c < k ? e0 + c : 0u, reverse);
+                v[c]             = e0 + c < k ? t : kPad;
+            }
+            // every load of the chunk is issued before any is used: no short-circuit, absent
+            // edges read entry 0 and are masked afterwards
+            uint8_t seen[kChunk];
+            unsigned long long owner[kChunk];
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
-                mine[c] = v[c] != kPad && !__ldcg(visited + v[c]) &&
-                          __ldcg(key + v[c]) == (unsigned long long)i * k + e0 + c;
+            {
+                uint32_t const vv = v[c] != kPad ? v[c] : 0u;
+                seen[c]  = __ldcg(visited + vv);
+                owner[c] = __ldcg(key + vv);
+            }
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c)
+                mine[c] = (v[c] != kPad) & (seen[c] == 0) &
+                          (owner[c] == (unsigned long long)i * k + e0 + c);
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
             {
@@ -156,18 +178,27 @@ __device__ __forceinline__ void accept_phase(const BfsState* st, int parity,
 // total); publishes the next frontier size
 __device__ __forceinline__ void scan_phase(BfsState* st, int parity, uint32_t* won)
 {
+    constexpr int kScanItems = 8; // consecutive entries per thread and round
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     uint32_t const m      = __ldcg(&st->size[parity]);
     uint32_t const nwarps = blockDim.x >> 5;
+    uint32_t const span   = blockDim.x * kScanItems;
     if (threadIdx.x == 0)
         carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < m; base += blockDim.x)
+    for (uint32_t base = 0; base < m; base += span)
     {
-        uint32_t const i = base + threadIdx.x;
-        uint32_t const x = i < m ? __ldcg(won + i) : 0u;
-        uint32_t incl    = x;
+        uint32_t const i0 = base + threadIdx.x * kScanItems;
+        uint32_t x[kScanItems];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int r = 0; r < kScanItems; ++r)
+        {
+            x[r] = i0 + r < m ? __ldcg(won + i0 + r) : 0u;
+            mine += x[r];
+        }
+        uint32_t incl = mine;
         for (int o = 1; o < 32; o <<= 1)
         {
             uint32_t const y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -189,9 +220,15 @@ __device__ __forceinline__ void scan_phase(BfsState* st, int parity, uint32_t* w
             warp_sums[threadIdx.x] = w; // inclusive over warps
         }
         __syncthreads();
-        uint32_t const before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0u);
-        if (i < m)
-            won[i] = before + incl - x;
+        uint32_t run = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0u) +
+                       incl - mine;
+#pragma unroll
+        for (int r = 0; r < kScanItems; ++r)
+        {
+            if (i0 + r < m)
+                won[i0 + r] = run;
+            run += x[r];
+        }
         __syncthreads();
         if (threadIdx.x == 0)
             carry += warp_sums[31];
@@ -222,13 +259,24 @@ __device__ __forceinline__ void emit_phase(const BfsState* st, int parity, const
             bool mine[kChunk];
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
-                v[c] = e0 + c < k ? edge_target(nbr, u, k, e0 + c, reverse) : kPad;
+            {
+                uint32_t const t = edge_target(nbr, u, k, e0 + c < k ? e0 + c : 0u, reverse);
+                v[c]             = e0 + c < k ? t : kPad;
+            }
             // the owner of v is unique, so nobody else tests visited[v] with a matching key
+            uint8_t seen[kChunk];
+            unsigned long long owner[kChunk];
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
-                mine[c] = v[c] != kPad &&
-                          __ldcg(key + v[c]) == (unsigned long long)i * k + e0 + c &&
-                          !__ldcg(visited + v[c]);
+            {
+                uint32_t const vv = v[c] != kPad ? v[c] : 0u;
+                seen[c]  = __ldcg(visited + vv);
+                owner[c] = __ldcg(key + vv);
+            }
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c)
+                mine[c] = (v[c] != kPad) & (seen[c] == 0) &
+                          (owner[c] == (unsigned long long)i * k + e0 + c);
 #pragma unroll
             for (int c = 0; c < kChunk; ++c)
                 if (mine[c])
@@ -272,42 +320,6 @@ __global__ void __launch_bounds__(kB) emit_kernel(const BfsState* st, int parity
                blockIdx.x * kB + threadIdx.x, gridDim.x * kB);
 }
 
-// The whole search in ONE cooperative launch: the four phases of every level separated by grid
-// barriers (about 2 us each on 148 resident blocks) instead of kernel boundaries.  Every block
-// executes every barrier: nothing returns early, the loop ends for all blocks on the same
-// (uniformly read) empty frontier.
-__global__ void __launch_bounds__(kB) bfs_persistent_kernel(BfsState* st, uint32_t* fa,
-                                                            uint32_t* fb, const uint32_t* nbr,
-                                                            uint32_t k, int reverse,
-                                                            uint8_t* visited,
-                                                            unsigned long long* key,
-                                                            float* normals, uint32_t* won,
-                                                            uint32_t max_levels)
-{
-    cg::grid_group grid  = cg::this_grid();
-    uint32_t const tid   = blockIdx.x * kB + threadIdx.x;
-    uint32_t const nthr  = gridDim.x * kB;
-    uint32_t *cur = fa, *nxt = fb;
-    int parity = 0;
-    for (uint32_t level = 0; level < max_levels; ++level)
-    {
-        if (__ldcg(&st->size[parity]) == 0u)
-            break;
-        propose_phase(st, parity, cur, nbr, k, reverse, visited, key, tid, nthr);
-        grid.sync();
-        accept_phase(st, parity, cur, nbr, k, reverse, visited, key, normals, won, tid, nthr);
-        grid.sync();
-        if (blockIdx.x == 0)
-            scan_phase(st, parity, won);
-        grid.sync();
-        emit_phase(st, parity, cur, nbr, k, reverse, visited, key, won, nxt, tid, nthr);
-        grid.sync();
-        uint32_t* t = cur;
-        cur = nxt, nxt = t;
-        parity ^= 1;
-    }
-}
-
 // same for a caller-supplied graph: points in input order, packed or strided
 __global__ void __launch_bounds__(kB) root_from_rows_kernel(const float* __restrict__ xyz,
                                                             uint32_t stride_f, uint32_t n,
@@ -345,30 +357,6 @@ BfsState run_search(cudaStream_t s, size_t n, uint32_t k, const uint32_t* nbr, i
     PCPX_CHECK_LAUNCH();
     ++launches;
     BfsState h{};
-    if (k > 0 && tuning().orient_persistent)
-    {
-        // one block per SM keeps the grid barrier cheap; the launch fails (and we fall through to
-        // the per-level kernels) where cooperative launches are unsupported
-        int dev = 0, sms = 0, coop = 0, per_sm = 0;
-        PCPX_CUDA(cudaGetDevice(&dev));
-        PCPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        PCPX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        PCPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_persistent_kernel, kB, 0));
-        if (coop && per_sm >= 1)
-        {
-            uint32_t *a = fa.get(), *b = fb.get(), *w = won.get();
-            uint8_t* vis = visited.get();
-            unsigned long long* ky = key.get();
-            uint32_t max_levels = (uint32_t)std::min<size_t>(n, 0xFFFFFFFFu);
-            void* args[] = {&st, &a, &b, &nbr, &k, &reverse, &vis, &ky, &d_nrm, &w, &max_levels};
-            PCPX_CUDA(cudaLaunchCooperativeKernel((void*)bfs_persistent_kernel, dim3((unsigned)sms),
-                                                  dim3(kB), args, 0, s));
-            ++launches;
-            PCPX_CUDA(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
-            PCPX_CUDA(cudaStreamSynchronize(s));
-            return h;
-        }
-    }
     uint32_t const gn = grid_of(n);
     uint32_t *cur = fa.get(), *nxt = fb.get();
     int parity = 0;

@@ -19,7 +19,6 @@ struct Tuning
 {
     float success_margin = 1.15f; // a block is tried when its ball should hold margin * (k + 1) points
     int block_threads  = 128;
-    int orient_persistent = 1; // orientation search as one cooperative kernel (0: four kernels per level)
 };
 Tuning& tuning();
 

@@ -94,18 +94,3 @@ def test_explicit_graph_entry_point(pcpx, oracle, fix):
         bad[3, 2] = len(xyz)
         pcpx.orient_normals_graph(xyz, bad, nrm.copy())
 
-
-def test_persistent_and_per_level_kernels_agree(pcpx, fix):
-    # the search runs as one cooperative kernel by default; the four-kernels-per-level form is
-    # the same phases behind kernel boundaries
-    xyz, nrm, k = fix["random_xyz"], fix["random_normals"], int(fix["random_k"])
-    ix = pcpx.Index(xyz)
-    try:
-        pcpx.set_tuning("orient_persistent", 0)
-        a = ix.orient_normals(nrm.copy(), k)
-        pcpx.set_tuning("orient_persistent", 1)
-        b = ix.orient_normals(nrm.copy(), k)
-    finally:
-        pcpx.set_tuning("orient_persistent", 1)
-        ix.close()
-    assert np.array_equal(a, fix["random_oriented"]) and np.array_equal(b, fix["random_oriented"])
