@@ -12,6 +12,8 @@
 #include <random>
 
 #include <pcpx/pcp.hpp>
+#include <pcpx/ply.hpp>
+#include <sstream>
 
 #define REQUIRE(cond)                                                                          \
     do                                                                                         \
@@ -391,6 +393,27 @@ static void orientation_scenario()
         REQUIRE(a[i].nx() == b[i].nx() && a[i].ny() == b[i].ny() && a[i].nz() == b[i].nz());
 }
 
+// examples/normals_estimation.cpp:60-66,132-140: the cloud comes from and goes back to a PLY file
+static void ply_round_trip()
+{
+    std::vector<pcp::point_t> points{{0.f, 0.25f, -1.5f}, {1.f, 2.f, 3.f}, {-4.f, 5.5f, 6.f}};
+    std::vector<pcp::normal_t> normals{{0.f, 0.f, 1.f}, {0.f, 1.f, 0.f}, {1.f, 0.f, 0.f}};
+    for (auto format : {pcp::io::ply_format_t::ascii, pcp::io::ply_format_t::binary_little_endian,
+                        pcp::io::ply_format_t::binary_big_endian})
+    {
+        std::stringstream ss(std::ios::in | std::ios::out | std::ios::binary);
+        pcp::io::write_ply<pcp::point_t, pcp::normal_t>(ss, points, normals, format);
+        auto [p, n] = pcp::io::read_ply<pcp::point_t, pcp::normal_t>(ss);
+        REQUIRE(p.size() == points.size() && n.size() == normals.size());
+        for (std::size_t i = 0; i < p.size(); ++i)
+        {
+            REQUIRE(pcp::common::are_vectors_equal(p[i], points[i]));
+            REQUIRE(n[i].nx() == normals[i].nx() && n[i].ny() == normals[i].ny() &&
+                    n[i].nz() == normals[i].nz());
+        }
+    }
+}
+
 int main()
 {
     if (pcpx_device_count() < 1)
@@ -404,6 +427,7 @@ int main()
     normals_scenarios();
     smoothing_scenarios();
     orientation_scenario();
+    ply_round_trip();
     std::printf("dropin_test: all scenarios hold\n");
     return 0;
 }

@@ -346,3 +346,28 @@ def test_10m_density_filter(pcpx, oracle):
         # idempotence-like: filtering the kept set with threshold 1 keeps everything
         with pcpx.Index(pts) as ix2:
             assert ix2.density_filter(radius, 1)[2] == kept
+
+
+def test_short_code_build_and_its_fallback(pcpx, oracle):
+    """Clouds of up to 2^24 points are first indexed with 10 levels (32-bit sort keys); when the
+    cell counts say an 11th level would still hold >= 4 points per cell the build repeats with
+    the full code length.  Either way the answers are the oracle's."""
+    rng = np.random.default_rng(41)
+    n = 300_000
+    plain = pcpx.synth.noisy_sphere(n, seed=4)
+    # a dense clump plus one far point: at level 10 the clump still sits in a handful of cells
+    clump = (rng.uniform(0, 0.002, (n, 3))).astype(np.float32)
+    clump[0] = (1.0, 1.0, 1.0)
+    line = np.zeros((n, 3), np.float32)
+    line[:, 0] = rng.uniform(0, 1, n).astype(np.float32)
+    line[:, 1:] = (1e-6 * rng.standard_normal((n, 2))).astype(np.float32)
+    for name, xyz, want_bits in (("plain", plain, 30), ("clump", clump, 33), ("line", line, 33)):
+        ix = pcpx.Index(xyz)
+        info = ix.info()
+        assert info["code_bits"] == want_bits, (name, info["code_bits"])
+        idx, d2, cnt = ix.knn(None, 8)
+        oi, od2, oc = oracle.cloud(xyz).knn(None, 8)
+        assert np.array_equal(cnt, oc), name
+        assert np.array_equal(idx.astype(np.int64), oi), name
+        assert np.array_equal(d2, od2), name
+        ix.close()

@@ -23,7 +23,13 @@ def main():
     xyz = getattr(pcpx.synth, os.environ.get('PCPX_CLOUD', 'noisy_plane'))(n)
     d_xyz = torch.from_numpy(xyz).cuda()
     torch.cuda.synchronize()
-    ix = pcpx.Index(d_xyz, min_cell_occupancy=int(os.environ.get('PCPX_MIN_OCC', '0')))
+    ix = pcpx.Index(d_xyz, min_cell_occupancy=int(os.environ.get('PCPX_MIN_OCC', '0')),
+                    max_level=int(os.environ.get('PCPX_MAX_LEVEL', '0')))
+    for _ in range(3):
+        ix.close()
+        ix = pcpx.Index(d_xyz, min_cell_occupancy=int(os.environ.get('PCPX_MIN_OCC', '0')),
+                        max_level=int(os.environ.get('PCPX_MAX_LEVEL', '0')))
+    print('build ms', ix.info()['build_ms'], 'code bits', ix.info()['code_bits'])
     print('finest level', ix.info()['finest_level'], 'cells', ix.info()['n_cells'])
     d_nrm = torch.empty((n, 3), dtype=torch.float32, device="cuda")
     d_idx = torch.empty((n, k), dtype=torch.int32, device="cuda")
