@@ -16,7 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libpcpx.so")
-UNITS = ["index.cu", "query.cu", "api.cu", "smoothing.cu", "orient.cu", "shard.cu"]
+UNITS = ["index.cu", "query.cu", "query_normals.cu", "query_mean.cu", "api.cu", "smoothing.cu",
+         "orient.cu", "shard.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

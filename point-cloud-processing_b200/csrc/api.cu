@@ -1,5 +1,5 @@
 // The C ABI of libpcpx.so (include/pcpx.h): argument checking, host <-> device staging,
-// timing.  All compute is in index.cu / query.cu; there is no CPU path.
+// timing.  All compute is in index.cu / query_body.inc; there is no CPU path.
 #include <cmath>
 #include <cstring>
 #include <memory>

@@ -1,6 +1,6 @@
 // Per-query exact kNN over the multi-level grid: register-resident sorted top-K list and the
 // 3x3x3 block walk with conservative float pruning.  __host__ __device__ so tests/emu can run
-// it on the CPU; the product only reaches it through the __global__ kernels in query.cu.
+// it on the CPU; the product only reaches it through the __global__ kernels in query_body.inc.
 //
 // Result contract (what the reference's octree/kd-tree return, made deterministic):
 //   the k eligible points with the smallest (fp32 squared distance, tie-break id), ascending;

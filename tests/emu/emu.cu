@@ -30,7 +30,7 @@ struct EmuIndex
     uint64_t cells_per_level[kMaxLevel + 2] = {};
 };
 
-// mirrors plan_for() in query.cu
+// mirrors plan_for() in query_body.inc
 static SearchPlan plan_for(const EmuIndex* ix, uint32_t k, double margin)
 {
     PlanChoice const c = choose_plan(ix->g.n, ix->cells_per_level, ix->g.lfine, k, margin);
@@ -229,7 +229,7 @@ static int list_size_for(uint32_t k)
 }
 constexpr int exact_k(int K) { return (K + 3) / 4 * 4; }
 
-// mirrors knn_kernel / knn_exact_row in query.cu; mode 0 = two-pass with fallback (the
+// mirrors knn_main_kernel / knn_retry_kernel in query_body.inc; mode 0 = two-pass with fallback (the
 // product path), 1 = force the exact 64-bit search for every query
 template <int K>
 static void knn_impl(EmuIndex* ix, const float* q, size_t nq, uint32_t k, float eps,
