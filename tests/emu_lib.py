@@ -30,7 +30,7 @@ def _f32(a):
 
 def build_emu(force=False):
     srcs = [os.path.join(EMU_DIR, "emu.cu")] + [
-        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp"))
     ]
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < newest:
