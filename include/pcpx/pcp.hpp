@@ -196,7 +196,107 @@ struct axis_aligned_bounding_box_t
                p.y() <= max.y() && p.z() <= max.z();
     }
     Point center() const { return (min + max) / 2.f; }
+    // common/axis_aligned_bounding_box.hpp:119-129
+    template <class P>
+    Point nearest_point_from(P const& p) const
+    {
+        return Point{std::clamp(p.x(), min.x(), max.x()), std::clamp(p.y(), min.y(), max.y()),
+                     std::clamp(p.z(), min.z(), max.z())};
+    }
 };
+
+// common/axis_aligned_bounding_box.hpp:12-77: the kd-tree's box over std::array coordinates
+template <class CoordinateType, std::size_t K>
+struct kd_axis_aligned_bounding_box_t
+{
+    using scalar_type = CoordinateType;
+    using point_type  = std::array<CoordinateType, K>;
+    point_type min{}, max{};
+    bool contains(point_type const& p) const
+    {
+        for (std::size_t i = 0; i < K; ++i)
+            if (!(p[i] >= min[i] && p[i] <= max[i]))
+                return false;
+        return true;
+    }
+    point_type center() const
+    {
+        point_type c{};
+        for (std::size_t i = 0; i < K; ++i)
+            c[i] = (min[i] + max[i]) / CoordinateType(2);
+        return c;
+    }
+    point_type nearest_point_from(point_type const& p) const
+    {
+        point_type q = p;
+        for (std::size_t i = 0; i < K; ++i)
+            q[i] = std::clamp(q[i], min[i], max[i]);
+        return q;
+    }
+};
+
+// common/axis_aligned_bounding_box.hpp:214-251 (point views) and :164-201 (coordinate maps).
+// Per-axis minima / maxima are exact in any order, so these host loops, the reference's
+// accumulate / par for_each and the device bbox_kernel all agree bit for bit.
+template <class ForwardIter, class Point, class AABB = axis_aligned_bounding_box_t<Point>>
+inline AABB bounding_box(ForwardIter begin, ForwardIter end)
+{
+    using T = typename Point::coordinate_type;
+    T lo[3] = {std::numeric_limits<T>::max(), std::numeric_limits<T>::max(),
+               std::numeric_limits<T>::max()};
+    T hi[3] = {std::numeric_limits<T>::lowest(), std::numeric_limits<T>::lowest(),
+               std::numeric_limits<T>::lowest()};
+    for (auto it = begin; it != end; ++it)
+    {
+        T const c[3] = {static_cast<T>(it->x()), static_cast<T>(it->y()), static_cast<T>(it->z())};
+        for (int a = 0; a < 3; ++a)
+            lo[a] = c[a] < lo[a] ? c[a] : lo[a], hi[a] = c[a] > hi[a] ? c[a] : hi[a];
+    }
+    AABB box;
+    box.min = Point{lo[0], lo[1], lo[2]};
+    box.max = Point{hi[0], hi[1], hi[2]};
+    return box;
+}
+template <class CoordinateType, std::size_t K, class CoordinateMap, class ForwardIter>
+inline kd_axis_aligned_bounding_box_t<CoordinateType, K>
+kd_bounding_box(ForwardIter begin, ForwardIter end, CoordinateMap const& coordinate_map)
+{
+    kd_axis_aligned_bounding_box_t<CoordinateType, K> box;
+    for (std::size_t i = 0; i < K; ++i)
+        box.min[i] = std::numeric_limits<CoordinateType>::max(),
+        box.max[i] = std::numeric_limits<CoordinateType>::lowest();
+    for (auto it = begin; it != end; ++it)
+    {
+        auto const p = coordinate_map(*it);
+        for (std::size_t i = 0; i < K; ++i)
+            box.min[i] = p[i] < box.min[i] ? p[i] : box.min[i],
+            box.max[i] = p[i] > box.max[i] ? p[i] : box.max[i];
+    }
+    return box;
+}
+
+// common/intersections.hpp:87-130.  The reference compares the SQUARED box distance with the
+// un-squared radius (:101, :129) — the slip behind its missed points for radii above 1; these
+// use radius * radius, the predicate the range searches of this library are built on.
+template <class Point>
+inline bool intersects(axis_aligned_bounding_box_t<Point> const& b, sphere_t<Point> const& s)
+{
+    Point const c = s.center();
+    if (b.contains(c))
+        return true;
+    return common::squared_distance(b.nearest_point_from(c), c) <= s.radius * s.radius;
+}
+template <class CoordinateType>
+inline bool intersects(kd_axis_aligned_bounding_box_t<CoordinateType, 3> const& b,
+                       sphere_a<CoordinateType> const& s)
+{
+    auto const c = s.center();
+    if (b.contains(c))
+        return true;
+    auto const q = b.nearest_point_from(c);
+    CoordinateType const dx = q[0] - c[0], dy = q[1] - c[1], dz = q[2] - c[2];
+    return dx * dx + dy * dy + dz * dz <= s.radius * s.radius;
+}
 
 // ---- index parameters (octree/linked_octree_node.hpp:31-40, kdtree/linked_kdtree.hpp:26-33):
 // accepted for source compatibility; tree shape does not change exact results, only the voxel
@@ -529,6 +629,27 @@ class basic_linked_kdtree_t : public device_spatial_index<Element>
                                static_cast<float>(c[2])});
         }
         return this->knn_batch(q, k, static_cast<double>(eps));
+    }
+    // ... and for the kd box range: circumscribed sphere on the GPU, exact box predicate after
+    std::vector<element_type>
+    range_search(kd_axis_aligned_bounding_box_t<coordinate_type, 3> const& range) const
+    {
+        float h[3], c[3];
+        for (int a = 0; a < 3; ++a)
+        {
+            h[a] = 0.5f * static_cast<float>(range.max[a] - range.min[a]);
+            c[a] = static_cast<float>(range.min[a]) + h[a];
+        }
+        std::vector<float> cc{c[0], c[1], c[2]};
+        std::vector<float> r{std::sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]) * 1.0001f + 1e-30f};
+        std::vector<std::uint64_t> off;
+        std::vector<std::uint32_t> idx;
+        this->radius_batch(cc, r, off, idx);
+        std::vector<element_type> out;
+        for (auto i : idx)
+            if (range.contains(coordinate_map_(this->elements_[i])))
+                out.push_back(this->elements_[i]);
+        return out;
     }
     // kdtree/linked_kdtree.hpp:270-277 for sphere_a
     std::vector<element_type> range_search(sphere_a<coordinate_type> const& range) const

@@ -414,6 +414,44 @@ static void ply_round_trip()
     }
 }
 
+// common/axis_aligned_bounding_box.hpp, common/intersections.hpp and the kd-tree box range
+// (test/kdtree/kdtree_range_search.cpp:84-117)
+static void geometry_helpers()
+{
+    std::vector<pcp::point_t> pts{{-1.f, 2.f, 0.5f}, {3.f, -4.f, 0.25f}, {0.f, 0.f, -7.f}};
+    auto const box = pcp::bounding_box<std::vector<pcp::point_t>::const_iterator, pcp::point_t>(
+        pts.cbegin(), pts.cend());
+    REQUIRE(box.min.x() == -1.f && box.min.y() == -4.f && box.min.z() == -7.f);
+    REQUIRE(box.max.x() == 3.f && box.max.y() == 2.f && box.max.z() == 0.5f);
+    REQUIRE(box.contains(pcp::point_t{0.f, 0.f, 0.f}) && !box.contains(pcp::point_t{4.f, 0.f, 0.f}));
+    auto const np = box.nearest_point_from(pcp::point_t{10.f, 0.f, -9.f});
+    REQUIRE(np.x() == 3.f && np.y() == 0.f && np.z() == -7.f);
+    pcp::sphere_t<pcp::point_t> s;
+    s.position = pcp::point_t{5.f, 0.f, 0.f};
+    s.radius   = 1.5f;
+    REQUIRE(!pcp::intersects(box, s)); // 2 away from the box
+    s.radius = 2.f;
+    REQUIRE(pcp::intersects(box, s));
+
+    std::vector<std::size_t> ids{0u, 1u, 2u};
+    auto const cmap = [&](std::size_t const i) {
+        return std::array<float, 3u>{pts[i].x(), pts[i].y(), pts[i].z()};
+    };
+    auto const kbox = pcp::kd_bounding_box<float, 3u>(ids.begin(), ids.end(), cmap);
+    REQUIRE(kbox.min[0] == -1.f && kbox.max[1] == 2.f && kbox.min[2] == -7.f);
+    pcp::basic_linked_kdtree_t<std::size_t, 3u, decltype(cmap)> kdtree{ids.begin(), ids.end(), cmap};
+    pcp::kd_axis_aligned_bounding_box_t<float, 3u> q;
+    q.min = {-2.f, -5.f, 0.f};
+    q.max = {4.f, 3.f, 1.f};
+    auto in_box = kdtree.range_search(q);
+    std::sort(in_box.begin(), in_box.end());
+    REQUIRE(in_box.size() == 2u && in_box[0] == 0u && in_box[1] == 1u);
+    pcp::sphere_a<float> sa;
+    sa.position = {0.f, 0.f, -7.f};
+    sa.radius   = 0.5f;
+    REQUIRE(pcp::intersects(kbox, sa));
+}
+
 int main()
 {
     if (pcpx_device_count() < 1)
@@ -428,6 +466,7 @@ int main()
     smoothing_scenarios();
     orientation_scenario();
     ply_round_trip();
+    geometry_helpers();
     std::printf("dropin_test: all scenarios hold\n");
     return 0;
 }
