@@ -371,3 +371,55 @@ def test_short_code_build_and_its_fallback(pcpx, oracle):
         assert np.array_equal(idx.astype(np.int64), oi), name
         assert np.array_equal(d2, od2), name
         ix.close()
+
+
+def test_100m_scan_properties_and_brute_force_sample(pcpx):
+    """configs[3] / configs[4] size: 100 M-point synthetic scan on one GPU.  No oracle tree at
+    this size; instead the size-independent properties of the answer and an exact brute-force
+    check (numpy, fp32, the reference's operation order) of sixteen queries against all
+    100 M points.  Results stay on the device; only samples come back."""
+    import torch
+
+    n, k = 100_000_000, 8
+    xyz = pcpx.synth.scan(n)
+    d_xyz = torch.from_numpy(xyz).cuda()
+    with pcpx.Index(d_xyz) as ix:
+        info = ix.info()
+        assert info["n_indexed"] == n and info["code_bits"] > 32  # the full-length code path
+        d_idx = torch.empty((n, k), dtype=torch.int32, device="cuda")
+        d_d2 = torch.empty((n, k), dtype=torch.float32, device="cuda")
+        d_cnt = torch.empty((n,), dtype=torch.int32, device="cuda")
+        ix.knn(None, k, out_idx=d_idx, out_d2=d_d2, out_count=d_cnt)
+        assert bool((d_cnt == k).all())
+        assert bool((d_d2[:, 1:] >= d_d2[:, :-1]).all())  # nearest -> furthest
+        rows = torch.arange(n, device="cuda", dtype=torch.int32)[:, None]
+        assert bool((d_idx != rows).all())  # self excluded
+        del rows
+        # equal distances are ordered by original index
+        tie = d_d2[:, 1:] == d_d2[:, :-1]
+        assert bool((d_idx[:, 1:][tie] > d_idx[:, :-1][tie]).all())
+        del tie
+        # distances are the reference's squared_distance of the returned indices (1 M sample)
+        rng = np.random.default_rng(5)
+        sample = np.sort(rng.choice(n, 1_000_000, replace=False))
+        s_idx = d_idx[torch.from_numpy(sample).cuda()].cpu().numpy().astype(np.int64)
+        s_d2 = d_d2[torch.from_numpy(sample).cuda()].cpu().numpy()
+        assert np.array_equal(host_d2(xyz, s_idx, sample), s_d2)
+        # exact brute force for 16 queries over all 100 M points
+        for q in rng.choice(n, 16, replace=False):
+            d = xyz - xyz[q]
+            dd = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+            excluded = (np.abs(d[:, 0]) < np.float32(1e-5)) & (np.abs(d[:, 1]) < np.float32(1e-5)) \
+                & (np.abs(d[:, 2]) < np.float32(1e-5))
+            dd[excluded] = np.inf
+            cand = np.argpartition(dd, k + 8)[: k + 8]
+            order = cand[np.lexsort((cand, dd[cand]))][:k]
+            assert np.array_equal(d_idx[int(q)].cpu().numpy().astype(np.int64), order), int(q)
+            assert np.array_equal(d_d2[int(q)].cpu().numpy(), dd[order])
+        del d_idx, d_d2, d_cnt
+        # normals k = 30 (configs[3]): unit length, finite, mostly vertical on the height field
+        d_nrm = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+        ix.estimate_normals(None, 30, out=d_nrm)
+        norms = torch.linalg.vector_norm(d_nrm, dim=1)
+        assert bool(torch.isfinite(d_nrm).all()) and float((norms - 1).abs().max()) < 1e-5
+        assert float(d_nrm[:, 2].abs().median()) > 0.9
