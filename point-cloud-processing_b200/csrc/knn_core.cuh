@@ -342,8 +342,10 @@ struct CellList
 constexpr int kCollectUnroll = PCPX_COLLECT_UNROLL;
 
 // Rings 0-1 (the 3^3 block): every in-grid cell is looked up, in visiting order.
+// `bound`: cells whose lower bound exceeds it are dropped before they cost a lookup (the radius
+// search knows r * r up front; the kNN search passes nothing and prunes while it walks).
 PCPX_HD void collect_block27(const GridView& g, const BlockGeom& b, int level, CellList& cl,
-                             SearchStats* st)
+                             SearchStats* st, float bound = INFINITY)
 {
     uint64_t const key0 = cell_key(level, b.cx, b.cy, b.cz);
     int n               = 0;
@@ -356,6 +358,9 @@ PCPX_HD void collect_block27(const GridView& g, const BlockGeom& b, int level, C
         Offset3 const o = block27_offset(i);
         if (outside_block_near(b, o.dx, o.dy, o.dz))
             continue;
+        float const lb = cell_lb2_near(b, o.dx, o.dy, o.dz);
+        if (lb > bound)
+            continue;
         uint32_t start, count;
         if (st)
             st->lookups++;
@@ -363,7 +368,7 @@ PCPX_HD void collect_block27(const GridView& g, const BlockGeom& b, int level, C
             continue;
         cl.start[n] = start;
         cl.end[n]   = start + count;
-        cl.lb2[n]   = cell_lb2_near(b, o.dx, o.dy, o.dz);
+        cl.lb2[n]   = lb;
         ++n;
     }
     cl.close(n);

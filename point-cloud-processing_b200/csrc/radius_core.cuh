@@ -31,39 +31,42 @@ PCPX_HD int radius_level(const GridView& g, const QueryCell& qc, float qx, float
 }
 
 // Calls f(point, sorted position) for every indexed point inside the ball; f returns true to
-// stop early.  Cells whose conservative lower bound exceeds r*r are skipped.
+// stop early.  The cells of the block whose conservative lower bound exceeds r * r are dropped
+// before they are looked up (the unrolled lookups of knn_core.cuh: collect_block27); the
+// remaining spans are walked FLAT — one loop over all candidates of the lane, the next point
+// already in flight — so a warp pays max over lanes of the candidate total, not the sum over
+// cells of the max over lanes of the cell size.  Visiting order: cells in block order (own,
+// faces, edges, corners), points of a cell in sorted order.
 template <class F>
 PCPX_HD void radius_visit(const GridView& g, float qx, float qy, float qz, float r, F&& f)
 {
     float const rr     = fmul_x(r, r);
     QueryCell const qc = query_cell(g, qx, qy, qz);
     BlockGeom b;
-    int const l         = radius_level(g, qc, qx, qy, qz, r, rr, b);
-    uint64_t const key0 = cell_key(l, b.cx, b.cy, b.cz);
-#pragma unroll 1
-    for (int i = 0; i < 27; ++i)
+    int const l = radius_level(g, qc, qx, qy, qz, r, rr, b);
+    CellList cl;
+    collect_block27(g, b, l, cl, nullptr, rr);
+    int e = 0;
+    uint32_t p = 0, pend = 0;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (;;)
     {
-        Offset3 const o = block27_offset(i);
-        int const dx = o.dx, dy = o.dy, dz = o.dz;
-        if ((dx < 0 && b.cx == 0u) || (dx > 0 && b.cx == b.last) || (dy < 0 && b.cy == 0u) ||
-            (dy > 0 && b.cy == b.last) || (dz < 0 && b.cz == 0u) || (dz > 0 && b.cz == b.last))
-            continue;
-        float const sx = dx < 0 ? b.sm[0] : (dx > 0 ? b.sp[0] : 0.f);
-        float const sy = dy < 0 ? b.sm[1] : (dy > 0 ? b.sp[1] : 0.f);
-        float const sz = dz < 0 ? b.sm[2] : (dz > 0 ? b.sp[2] : 0.f);
-        if (fadd_x(fadd_x(sx, sy), sz) > rr)
-            continue;
-        uint32_t start, count;
-        if (!find_cell(g, key0 + key_delta(dx, dy, dz), start, count))
-            continue;
-        for (uint32_t p = start; p < start + count; ++p)
+        if (p >= pend)
         {
-            float4 const c = load_pt(g.pts + p);
-            float const d2 = sqdist_x(fsub_x(c.x, qx), fsub_x(c.y, qy), fsub_x(c.z, qz));
-            if (d2 <= rr)
-                if (f(c, p))
-                    return;
+            uint32_t const s = cl.start[e], en = cl.end[e];
+            ++e;
+            if (s == kSpanEnd) // the sentinel record: every span has been walked
+                return;
+            p = s, pend = en;
+            c = load_pt(g.pts + p);
         }
+        float4 const a = c;
+        c = load_pt(g.pts + p + 1); // unconditional: the array is padded (kPtsPad)
+        float const d2 = sqdist_x(fsub_x(a.x, qx), fsub_x(a.y, qy), fsub_x(a.z, qz));
+        if (d2 <= rr)
+            if (f(a, p))
+                return;
+        ++p;
     }
 }
 
