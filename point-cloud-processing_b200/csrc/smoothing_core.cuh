@@ -159,7 +159,7 @@ PCPX_HD bool wlop_same_point(float ax, float ay, float az, float bx, float by, f
 PCPX_HD float wlop_density(const GridView& g, const WlopParams& w, float x, float y, float z)
 {
     float v = 1.f;
-    radius_visit(g, x, y, z, w.h, [&](float4 const& p, uint32_t) {
+    radius_visit_lazy(g, x, y, z, w.h, [&](float4 const& p, uint32_t) {
         if (!wlop_same_point(x, y, z, p.x, p.y, p.z))
             v += wlop_theta(w, sqdist_x(fsub_x(p.x, x), fsub_x(p.y, y), fsub_x(p.z, z)));
         return false;
@@ -177,7 +177,7 @@ PCPX_HD void wlop_step(const GridView& gp, const float* vj_sorted, const GridVie
 {
     float const eps = 1e-9f;
     float sum = 0.f, mx = 0.f, my = 0.f, mz = 0.f;
-    radius_visit(gp, qx, qy, qz, w.h, [&](float4 const& p, uint32_t pos) {
+    radius_visit_lazy(gp, qx, qy, qz, w.h, [&](float4 const& p, uint32_t pos) {
         if (wlop_same_point(qx, qy, qz, p.x, p.y, p.z))
             return false;
         float const r2 = sqdist_x(fsub_x(p.x, qx), fsub_x(p.y, qy), fsub_x(p.z, qz));
@@ -195,7 +195,7 @@ PCPX_HD void wlop_step(const GridView& gp, const float* vj_sorted, const GridVie
         mx /= sum, my /= sum, mz /= sum;
 
     float rsum = 0.f, rx = 0.f, ry = 0.f, rz = 0.f;
-    radius_visit(gq, qx, qy, qz, w.h, [&](float4 const& p, uint32_t pos) {
+    radius_visit_lazy(gq, qx, qy, qz, w.h, [&](float4 const& p, uint32_t pos) {
         if (wlop_same_point(p.x, p.y, p.z, qx, qy, qz))
             return false;
         float const dx = qx - p.x, dy = qy - p.y, dz = qz - p.z; // d = qip - qi

@@ -453,8 +453,8 @@ int emu_density_keep(void* h, float r, uint32_t threshold, uint8_t* keep)
         float4 q = ix->pts[i];
         uint32_t c = 0;
         if (threshold)
-            radius_visit(ix->g, q.x, q.y, q.z, r,
-                         [&](float4 const&, uint32_t) { return ++c >= threshold; });
+            radius_visit_lazy(ix->g, q.x, q.y, q.z, r,
+                              [&](float4 const&, uint32_t) { return ++c >= threshold; });
         keep[f2u(q.w)] = c >= threshold;
     }
     return 0;
