@@ -19,7 +19,7 @@ using namespace pcpx;
 namespace {
 
 constexpr int kB         = 256;
-constexpr int kGrid      = 148 * 4;
+constexpr int kGrid      = 148;
 constexpr int kChunk     = 8;  // edges whose loads are in flight together
 constexpr uint32_t kPad  = 0xFFFFFFFFu;
 
@@ -27,7 +27,7 @@ struct BfsState
 {
     uint32_t size[2];    // frontier sizes, ping-pong by level parity
     uint32_t levels;     // levels that reached at least one new vertex
-    uint32_t pad;
+    uint32_t done;       // blocks of the current accept kernel that have finished
     unsigned long long reached; // vertices reached, root included
     unsigned long long root_key;
 };
@@ -59,15 +59,19 @@ __global__ void __launch_bounds__(kB) root_kernel(const float4* __restrict__ pts
         atomicMax(&st->root_key, best);
 }
 
-__global__ void start_kernel(BfsState* st, uint32_t* frontier, uint8_t* visited, float* normals)
+// relabel: original index -> vertex id of the search (nullptr: the ids are the original indices)
+__global__ void start_kernel(BfsState* st, uint32_t* frontier, uint8_t* visited, float* normals,
+                             const uint32_t* relabel)
 {
-    uint32_t const root = 0xFFFFFFFFu - (uint32_t)(st->root_key & 0xFFFFFFFFu);
+    uint32_t root = 0xFFFFFFFFu - (uint32_t)(st->root_key & 0xFFFFFFFFu);
+    if (relabel)
+        root = relabel[root];
     frontier[0]         = root;
     visited[root]       = 1;
     normals[3 * (size_t)root] = 0.f, normals[3 * (size_t)root + 1] = 0.f,
                     normals[3 * (size_t)root + 2] = 1.f; // :233-237
     st->size[0] = 1, st->size[1] = 0;
-    st->levels = 0, st->reached = 1;
+    st->levels = 0, st->reached = 1, st->done = 0;
 }
 
 __device__ __forceinline__ uint32_t edge_target(const uint32_t* __restrict__ nbr, uint32_t u,
@@ -77,7 +81,7 @@ __device__ __forceinline__ uint32_t edge_target(const uint32_t* __restrict__ nbr
 }
 
 // ---- the four phases of one BFS level ---------------------------------------------------------
-// Four small kernels per level.  (A single cooperative kernel with grid barriers between the
+// Three small kernels per level.  (A single cooperative kernel with grid barriers between the
 // phases was measured and is not faster: 49 - 62 ms against 48 - 55 ms for 996 levels over 5 M
 // points; the level time is the chain of dependent random loads, not the kernel boundaries.)
 // Arrays other phases write (frontier, visited, key, won, normals, the state) are read with
@@ -297,18 +301,31 @@ __global__ void __launch_bounds__(kB) propose_kernel(const BfsState* st, int par
     propose_phase(st, parity, frontier, nbr, k, reverse, visited, key,
                   blockIdx.x * kB + threadIdx.x, gridDim.x * kB);
 }
-__global__ void __launch_bounds__(kB) accept_kernel(const BfsState* st, int parity,
-                                                    const uint32_t* frontier, const uint32_t* nbr,
-                                                    uint32_t k, int reverse, const uint8_t* visited,
-                                                    const unsigned long long* key, float* normals,
-                                                    uint32_t* won)
+// accept + scan in one launch: the block that finishes last (a ticket counter, no waiting) scans
+// the counts of the whole frontier.  One launch less per level is worth more than the three
+// warps-worth of scan parallelism it gives up: a level is bound by the ~9 us each dependent
+// launch costs, not by the work.
+__global__ void __launch_bounds__(kB) accept_scan_kernel(BfsState* st, int parity,
+                                                         const uint32_t* frontier,
+                                                         const uint32_t* nbr, uint32_t k,
+                                                         int reverse, const uint8_t* visited,
+                                                         const unsigned long long* key,
+                                                         float* normals, uint32_t* won)
 {
     accept_phase(st, parity, frontier, nbr, k, reverse, visited, key, normals, won,
                  blockIdx.x * kB + threadIdx.x, gridDim.x * kB);
-}
-__global__ void __launch_bounds__(1024) scan_kernel(BfsState* st, int parity, uint32_t* won)
-{
+    __shared__ bool is_last;
+    __threadfence(); // this block's counts are visible before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0)
+        is_last = atomicAdd(&st->done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!is_last)
+        return;
+    __threadfence();
     scan_phase(st, parity, won);
+    if (threadIdx.x == 0)
+        st->done = 0;
 }
 __global__ void __launch_bounds__(kB) emit_kernel(const BfsState* st, int parity,
                                                   const uint32_t* frontier, const uint32_t* nbr,
@@ -318,6 +335,48 @@ __global__ void __launch_bounds__(kB) emit_kernel(const BfsState* st, int parity
 {
     emit_phase(st, parity, frontier, nbr, k, reverse, visited, key, offset, next,
                blockIdx.x * kB + threadIdx.x, gridDim.x * kB);
+}
+
+// ---- the search in the index's own order -----------------------------------------------------
+// The queue order of the search depends on the graph and the edge order only, not on how the
+// vertices are numbered.  With the original indices as ids every access of a level — neighbour
+// row, visited flag, key, normal — lands on a random page; numbered by SORTED position the
+// neighbours of a vertex are a few thousand ids away at most, and a level stays inside a few
+// pages (TLB) and L2 lines.
+__global__ void __launch_bounds__(kB) inverse_kernel(const float4* __restrict__ pts, uint32_t n,
+                                                     uint32_t* __restrict__ inv)
+{
+    uint32_t const t = blockIdx.x * kB + threadIdx.x;
+    if (t < n)
+        inv[__float_as_uint(pts[t].w)] = t;
+}
+
+__global__ void __launch_bounds__(kB) relabel_graph_kernel(const float4* __restrict__ pts,
+                                                           uint32_t n, uint32_t k,
+                                                           const uint32_t* __restrict__ nbr,
+                                                           const uint32_t* __restrict__ inv,
+                                                           uint32_t* __restrict__ nbr_sorted)
+{
+    unsigned long long const c = blockIdx.x * (unsigned long long)kB + threadIdx.x;
+    if (c >= (unsigned long long)n * k)
+        return;
+    uint32_t const pos = (uint32_t)(c / k), j = (uint32_t)(c % k);
+    uint32_t const v   = nbr[(size_t)__float_as_uint(pts[pos].w) * k + j];
+    nbr_sorted[c]      = v == kPad ? kPad : inv[v];
+}
+
+// forward: rows in input order -> rows in sorted order; !forward: back
+__global__ void __launch_bounds__(kB) permute_rows_kernel(const float4* __restrict__ pts,
+                                                          uint32_t n, const float* __restrict__ in,
+                                                          float* __restrict__ out, int forward)
+{
+    uint32_t const t = blockIdx.x * kB + threadIdx.x;
+    if (t >= n)
+        return;
+    size_t const o   = __float_as_uint(pts[t].w);
+    const float* src = in + 3 * (forward ? o : (size_t)t);
+    float* dst       = out + 3 * (forward ? (size_t)t : o);
+    dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
 }
 
 // same for a caller-supplied graph: points in input order, packed or strided
@@ -346,41 +405,72 @@ uint32_t grid_of(size_t n) { return (uint32_t)std::min<size_t>(std::max<size_t>(
 
 // The search proper.  `st` holds the root key; nbr = n rows of k targets (kPad = no edge).
 BfsState run_search(cudaStream_t s, size_t n, uint32_t k, const uint32_t* nbr, int reverse,
-                    float* d_nrm, BfsState* st, uint32_t& launches)
+                    float* d_nrm, BfsState* st, uint32_t& launches,
+                    const uint32_t* relabel = nullptr)
 {
     DevBuf<uint32_t> fa(n), fb(n), won(n);
     DevBuf<uint8_t> visited(n);
     DevBuf<unsigned long long> key(n);
     PCPX_CUDA(cudaMemsetAsync(visited.get(), 0, n, s));
     PCPX_CUDA(cudaMemsetAsync(key.get(), 0xFF, n * 8, s));
-    start_kernel<<<1, 1, 0, s>>>(st, fa.get(), visited.get(), d_nrm);
+    start_kernel<<<1, 1, 0, s>>>(st, fa.get(), visited.get(), d_nrm, relabel);
     PCPX_CHECK_LAUNCH();
     ++launches;
     BfsState h{};
     uint32_t const gn = grid_of(n);
-    uint32_t *cur = fa.get(), *nxt = fb.get();
-    int parity = 0;
-    for (uint64_t level = 0; level < n && k > 0;)
+    if (k == 0)
     {
-        // a batch of levels, then one look at the frontier size; levels queued past the end of
-        // the search see an empty frontier and do nothing
-        for (int b = 0; b < 32; ++b, ++level)
+        PCPX_CUDA(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
+        PCPX_CUDA(cudaStreamSynchronize(s));
+        return h;
+    }
+    // kLevelsPerBatch levels (3 kernels each) are captured ONCE into a CUDA graph and the graph is
+    // launched per batch: the search is otherwise bound by the host's launch rate (4 100 launches
+    // for 996 levels took as long as the kernels).  The batch is an even number of levels, so the
+    // two frontier buffers and the parity are back where they started and the graph can be
+    // replayed as is.  Levels past the end of the search see an empty frontier and do nothing;
+    // the host looks at the frontier size once per batch.
+    constexpr int kLevelsPerBatch = 32;
+    struct GraphGuard
+    {
+        cudaGraph_t graph   = nullptr;
+        cudaGraphExec_t exe = nullptr;
+        ~GraphGuard()
+        {
+            if (exe)
+                cudaGraphExecDestroy(exe);
+            if (graph)
+                cudaGraphDestroy(graph);
+        }
+    } gg;
+    PCPX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    {
+        uint32_t *cur = fa.get(), *nxt = fb.get();
+        int parity = 0;
+        for (int b = 0; b < kLevelsPerBatch; ++b)
         {
             propose_kernel<<<gn, kB, 0, s>>>(st, parity, cur, nbr, k, reverse, visited.get(),
                                              key.get());
-            accept_kernel<<<gn, kB, 0, s>>>(st, parity, cur, nbr, k, reverse, visited.get(),
-                                            key.get(), d_nrm, won.get());
-            scan_kernel<<<1, 1024, 0, s>>>(st, parity, won.get());
+            accept_scan_kernel<<<gn, kB, 0, s>>>(st, parity, cur, nbr, k, reverse, visited.get(),
+                                                 key.get(), d_nrm, won.get());
             emit_kernel<<<gn, kB, 0, s>>>(st, parity, cur, nbr, k, reverse, visited.get(),
                                           key.get(), won.get(), nxt);
-            launches += 4;
             std::swap(cur, nxt);
             parity ^= 1;
         }
-        PCPX_CHECK_LAUNCH();
+    }
+    cudaError_t const cap = cudaStreamEndCapture(s, &gg.graph);
+    if (cap != cudaSuccess)
+        fail(PCPX_ERR_CUDA, "stream capture of the orientation search failed: %s",
+             cudaGetErrorString(cap));
+    PCPX_CUDA(cudaGraphInstantiate(&gg.exe, gg.graph, 0));
+    for (uint64_t level = 0; level < n; level += kLevelsPerBatch)
+    {
+        PCPX_CUDA(cudaGraphLaunch(gg.exe, s));
+        launches += 3 * kLevelsPerBatch;
         PCPX_CUDA(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
         PCPX_CUDA(cudaStreamSynchronize(s));
-        if (h.size[parity] == 0)
+        if (h.size[0] == 0) // an even number of levels per batch: the live frontier is parity 0
             return h;
     }
     PCPX_CUDA(cudaMemcpyAsync(&h, st, sizeof h, cudaMemcpyDeviceToHost, s));
@@ -442,12 +532,27 @@ int pcpx_orient_normals(const pcpx_index* index, uint32_t k, double eps, int edg
             launch_knn(ix, qb, k, (float)eps, nbr.get(), nullptr, nullptr, retries.get());
             PCPX_CUDA(cudaStreamSynchronize(s)); // `retries` is released here
         }
+        // renumber the graph and the normals by sorted position (see inverse_kernel)
+        uint32_t const n32 = (uint32_t)n;
+        uint32_t const nb  = (uint32_t)((n + kB - 1) / kB);
+        DevBuf<uint32_t> inv(n), nbr_sorted(n * (size_t)kk);
+        DevBuf<float> nrm_sorted(3 * n);
+        inverse_kernel<<<nb, kB, 0, s>>>(ix.grid.pts, n32, inv.get());
+        if (k > 0)
+            relabel_graph_kernel<<<(uint32_t)((n * (size_t)k + kB - 1) / kB), kB, 0, s>>>(
+                ix.grid.pts, n32, k, nbr.get(), inv.get(), nbr_sorted.get());
+        permute_rows_kernel<<<nb, kB, 0, s>>>(ix.grid.pts, n32, d_nrm, nrm_sorted.get(), 1);
+        PCPX_CHECK_LAUNCH();
         DevBuf<BfsState> st(1);
         PCPX_CUDA(cudaMemsetAsync(st.get(), 0, sizeof(BfsState), s));
-        root_kernel<<<grid_of(n), kB, 0, s>>>(ix.grid.pts, (uint32_t)n, st.get());
-        uint32_t launches = 3;
-        BfsState const h  = run_search(s, n, k, nbr.get(), edge_order == PCPX_EDGES_FURTHEST_FIRST,
-                                       d_nrm, st.get(), launches);
+        root_kernel<<<grid_of(n), kB, 0, s>>>(ix.grid.pts, n32, st.get());
+        uint32_t launches = 6;
+        BfsState const h =
+            run_search(s, n, k, nbr_sorted.get(), edge_order == PCPX_EDGES_FURTHEST_FIRST,
+                       nrm_sorted.get(), st.get(), launches, inv.get());
+        permute_rows_kernel<<<nb, kB, 0, s>>>(ix.grid.pts, n32, nrm_sorted.get(), d_nrm, 0);
+        PCPX_CHECK_LAUNCH();
+        ++launches;
         timer.kernel_end();
         if (!direct)
             PCPX_CUDA(cudaMemcpyAsync(normals, d_nrm, 12 * n, cudaMemcpyDeviceToHost, s));
