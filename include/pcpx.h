@@ -422,7 +422,12 @@ int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
 
 /* Process-wide tunables (performance only, never results).  Known names:
  *   "success_margin"  a kNN-shaped call first tries the cheapest (level, rings) block whose ball
- *                     is expected to hold success_margin * (k + 1) points (default 1.15). */
+ *                     is expected to hold success_margin * (k + 1) points (default 1.15).
+ *   "tile"            1 (default): calls whose queries are the indexed points themselves take the
+ *                     tile-cooperative kernel (shared-memory staged candidates); 0: never.
+ *   "tile_sub"        sub-bins per cell of the tile kernel's local grid, 1 or 2 (default 2).
+ *   "tile_cap"        largest scan radius of the tile kernel in cell sides (default 1).
+ *   "tile_margin"     like success_margin, for the tile kernel's level (default 1.15). */
 int pcpx_set_tuning(const char* name, double value);
 
 /* Search work of a self-kNN over the whole cloud, summed over queries:

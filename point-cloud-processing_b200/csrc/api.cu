@@ -399,6 +399,14 @@ int pcpx_set_tuning(const char* name, double value)
             fail(PCPX_ERR_INVALID_ARG, "name is NULL");
         if (!std::strcmp(name, "success_margin"))
             tuning().success_margin = (float)value;
+        else if (!std::strcmp(name, "tile"))
+            tuning().tile = (int)value;
+        else if (!std::strcmp(name, "tile_sub"))
+            tuning().tile_sub = (int)value;
+        else if (!std::strcmp(name, "tile_cap"))
+            tuning().tile_cap = (float)value;
+        else if (!std::strcmp(name, "tile_margin"))
+            tuning().tile_margin = (float)value;
         else
             fail(PCPX_ERR_INVALID_ARG, "unknown tuning parameter '%s'", name);
     });

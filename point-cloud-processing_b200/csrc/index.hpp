@@ -20,6 +20,11 @@ struct pcpx_index
     pcpx::DevBuf<pcpx::HashSlot> table; // all levels
     pcpx_timings timings{-1.f, -1.f, -1.f, -1.f, -1.f, 0u, 0u};
     std::mutex mtx; // one call at a time per index (calls serialise on `stream`)
+    // tile list of one level (query.cu: ensure_tile_list), built on first use and kept:
+    // tile_starts[i] = first sorted position of tile i, tile_starts[n_tiles] = n_indexed
+    mutable pcpx::DevBuf<uint32_t> tile_starts, tile_count, tile_scratch;
+    mutable int tile_level         = -1;
+    mutable uint32_t tile_capacity = 0;
 
     ~pcpx_index()
     {

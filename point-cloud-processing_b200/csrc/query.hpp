@@ -19,6 +19,11 @@ struct Tuning
 {
     float success_margin = 1.15f; // a block is tried when its ball should hold margin * (k + 1) points
     int block_threads  = 128;
+    // the tile path (tile_core.cuh) for calls whose queries are the indexed points
+    int tile           = 1;    // 0: never
+    int tile_sub       = 2;    // sub-bins per main-level cell along the two in-plane axes (1 or 2)
+    float tile_cap     = 1.0f; // largest scan radius in units of the main-level cell
+    float tile_margin  = 1.15f; // main level: finest whose ball of one cell side holds margin * (k + 1) points
 };
 Tuning& tuning();
 
@@ -44,6 +49,8 @@ void launch_mean_reduce(const pcpx_index& ix, const float* v, uint32_t n, double
                         uint32_t* out_valid);
 void launch_normals_from_neighbourhoods(cudaStream_t stream, const float* nbr_xyz,
                                         const uint64_t* offsets, uint32_t n, float* normals);
+// builds (once per level) the tile list the tile path iterates over; returns its capacity
+uint32_t ensure_tile_list(const pcpx_index& ix, int tile_level);
 void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long long* stats4);
 
 } // namespace pcpx

@@ -1,0 +1,558 @@
+// Tile-cooperative exact kNN: the fast path of every kNN-shaped call whose queries are the
+// indexed points themselves (estimate_normals, mean neighbour distance, kNN graphs).
+//
+// Every query of one finest cell sees the same 3x3x3 block, so the per-thread search of
+// knn_core.cuh re-derives 27 table lookups and a span list per THREAD that are identical for all
+// queries of the cell.  Here a CTA owns a *tile* — one cell two levels above the call's main
+// level, i.e. 4x4x4 main-level cells, a contiguous run of the sorted point array — and does the
+// structure work ONCE per tile:
+//
+//   1. 64 table lookups (the 4x4x4 cells one level above the main level that cover the tile plus
+//      one main-level cell of halo on every side) give the spans of every point a tile query can
+//      need;
+//   2. those points are copied into shared memory RE-BINNED into a dense local grid: S x S
+//      sub-bins per main-level cell along two axes (a, b), whole cells along the third (c = the
+//      axis along which the tile's neighbourhood is thinnest), rows along a contiguous — so the
+//      candidates of a query are a handful of contiguous shared-memory ranges, found by two
+//      loads from a 864-entry start table instead of hash probes;
+//   3. one thread per query scans, row by row, only the bins its current search ball touches
+//      (a disc, not a box; the ball shrinks as soon as the list is full), with broadcast /
+//      near-broadcast shared-memory loads, no local memory and no per-thread lists.
+//
+// The top-k list is KL (>= k + 1) 32-bit keys in registers: (bits(d2) & ~mask) | staged position.
+// d2 >= 0, so unsigned order of the bits is the fp32 order; the low `mask` bits are replaced by
+// the position of the candidate in shared memory, which makes ONE pass enough (no second pass to
+// recover identities) at the price of comparing distances truncated to (23 - bits(mask)) mantissa
+// bits.  That is still exact:
+//   * truncation is monotone, so every member of the k smallest KEYS has d2 <= every non-member
+//     — unless the k-th and (k+1)-th keys agree in all kept bits; that case is detected and the
+//     query goes to the retry queue (the exact per-thread search of knn_core.cuh);
+//   * the order among members is re-established from the exact distances (and original indices)
+//     of the k winners when a call needs it (kNN rows, mean distance).
+// A query is final when the k-th key's upper bound lies inside the ball that was scanned and that
+// ball lies inside the staged region; everything else (sparse neighbourhoods, outliers, tiles
+// whose region does not fit) is appended to the same retry queue.
+//
+// __host__ __device__ throughout (see grid_core.cuh): tests/emu runs the same phases on the CPU.
+#pragma once
+#include "normals_core.cuh"
+
+namespace pcpx {
+
+constexpr int kTileShift      = 2;                   // tile = cell at (main level - 2)
+constexpr int kTileCells      = 1 << kTileShift;     // main-level cells per tile and axis
+constexpr int kRegionCells    = kTileCells + 2;      // + one cell of halo on every side
+constexpr int kTileSpans      = 64;                  // 4^3 cells at (main level - 1) cover the region
+constexpr int kTileScanLanes  = 32;                  // threads that scan the bin counts
+constexpr uint32_t kKeyEmpty  = 0xFFFFFFFFu;
+constexpr uint32_t kTilePad   = 2;                   // readable entries behind the staged points
+
+template <int S>
+struct TileDims
+{
+    static constexpr int na = kRegionCells * S, nb = kRegionCells * S, nc = kRegionCells;
+    static constexpr int bins = na * nb * nc;
+};
+
+// per call, computed on the host (make_tile_params)
+struct TileParams
+{
+    int level;           // main level L
+    int rows_b, rows_c;  // rows on either side of the query's own row that a scan can touch
+    uint32_t max_points; // capacity of the staged region
+    uint32_t key_mask;   // low key bits that carry the staged position
+    float h;             // cell side at L
+    float bins_per_len;  // S * 2^L / extent
+    float len_per_bin;   // h / S
+    float cells_per_len; // 2^L / extent
+    float delta_bins;    // g.delta in (a, b) bin units: slack of every float-evaluated bin bound
+    float delta_cells;   // g.delta in cell units
+    float scan_cap;      // largest scan radius, in units of h
+};
+
+template <int S>
+inline TileParams make_tile_params(const GridView& g, int level, uint32_t max_points,
+                                   float scan_cap)
+{
+    TileParams tp;
+    tp.level         = level;
+    tp.max_points    = max_points;
+    uint32_t bits    = 1;
+    while ((1u << bits) < max_points + kTilePad)
+        ++bits;
+    tp.key_mask      = (1u << bits) - 1u;
+    tp.h             = ldexpf(g.extent, -level);
+    tp.cells_per_len = ldexpf(1.f, level) / g.extent;
+    tp.bins_per_len  = tp.cells_per_len * (float)S;
+    tp.len_per_bin   = tp.h / (float)S;
+    tp.delta_bins    = g.delta * tp.bins_per_len * 1.5f + 1e-6f;
+    tp.delta_cells   = g.delta * tp.cells_per_len * 1.5f + 1e-6f;
+    tp.scan_cap      = scan_cap;
+    tp.rows_b        = (int)ceilf(scan_cap * (float)S);
+    tp.rows_c        = (int)ceilf(scan_cap);
+    return tp;
+}
+
+// per tile, written by one thread (tile_plan)
+struct TileGeom
+{
+    int32_t r0[3];      // region origin in main-level cells along a, b, c (may be -1)
+    int32_t ax[3];      // world axis (0 = x, 1 = y, 2 = z) of a, b, c
+    uint32_t n_spans;   // non-empty spans among the 64
+    uint32_t raw_total; // points in those spans (a superset of the region)
+    uint32_t n_points;  // points of the region (staged)
+    int32_t fallback;   // the region does not fit: every query of the tile goes to the retry queue
+};
+
+// pointers into the CTA's shared memory (or the emulator's arrays)
+struct TileSmem
+{
+    float4* P;            // max_points + kTilePad, bin order
+    uint32_t* F;          // bins + 1: start of every bin (F[bins] = n_points)
+    uint32_t* span_start; // kTileSpans
+    uint32_t* span_off;   // kTileSpans + 1 (prefix over the compacted spans)
+    uint32_t* partial;    // kTileScanLanes
+    TileGeom* geom;
+};
+
+PCPX_HD float axis_of(float x, float y, float z, int ax) { return ax == 0 ? x : (ax == 1 ? y : z); }
+PCPX_HD int32_t axis_of_i(int32_t x, int32_t y, int32_t z, int ax)
+{
+    return ax == 0 ? x : (ax == 1 ? y : z);
+}
+
+// Fine coordinate with S steps per finest cell.  (x - o) * (scale * 2) == 2 * ((x - o) * scale)
+// exactly, so quantise_sub<2>(x) >> 1 == quantise(x): a point's sub-bin always lies inside the cell
+// the index assigned it to.
+template <int S>
+PCPX_HD uint32_t quantise_sub(float x, float o, float scale, int lcap)
+{
+    float t = (x - o) * (scale * (float)S);
+    t       = t > 0.f ? t : 0.f;
+    float m = (float)(((1u << lcap) * (uint32_t)S) - 1u);
+    t       = t < m ? t : m;
+    return (uint32_t)t;
+}
+
+PCPX_HD uint32_t tile_atomic_inc(uint32_t* p)
+{
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, 1u);
+#else
+    return (*p)++;
+#endif
+}
+
+// bin of a point in the tile's local grid, -1 when its cell lies outside the region
+template <int S>
+PCPX_HD int tile_bin(const GridView& g, const TileParams& tp, const TileGeom& tg, const float4& p)
+{
+    using D      = TileDims<S>;
+    int const sh = g.lcap - tp.level;
+    int const a = tg.ax[0], b = tg.ax[1], c = tg.ax[2];
+    uint32_t const ua =
+        quantise_sub<S>(axis_of(p.x, p.y, p.z, a), axis_of(g.ox, g.oy, g.oz, a), g.scale, g.lcap);
+    uint32_t const ub =
+        quantise_sub<S>(axis_of(p.x, p.y, p.z, b), axis_of(g.ox, g.oy, g.oz, b), g.scale, g.lcap);
+    uint32_t const uc =
+        quantise(axis_of(p.x, p.y, p.z, c), axis_of(g.ox, g.oy, g.oz, c), g.scale, g.lcap);
+    int const ia = (int)(ua >> sh) - tg.r0[0] * S;
+    int const ib = (int)(ub >> sh) - tg.r0[1] * S;
+    int const ic = (int)(uc >> sh) - tg.r0[2];
+    if ((unsigned)ia >= (unsigned)D::na || (unsigned)ib >= (unsigned)D::nb ||
+        (unsigned)ic >= (unsigned)D::nc)
+        return -1;
+    return (ic * D::nb + ib) * D::na + ia;
+}
+
+// ---- staging phases (a barrier between consecutive phases) -----------------------------------
+
+// phase 0: clear the bin table; the first 64 threads look up the covering cells
+template <int S>
+PCPX_HD void tile_phase_lookup(const GridView& g, const TileParams& tp, const TileSmem& sm,
+                               uint32_t tile_first, int tid, int nthreads)
+{
+    for (int i = tid; i <= TileDims<S>::bins; i += nthreads)
+        sm.F[i] = 0u;
+    if (tid < kTileSpans)
+    {
+        float4 const f     = load_pt(g.pts + tile_first);
+        QueryCell const qc = query_cell(g, f.x, f.y, f.z);
+        int const l1       = tp.level - 1; // level of the covering cells
+        int const sh       = g.lcap - (tp.level - kTileShift);
+        // covering cell = 2 * tile - 1 + (0..3) per axis
+        int const cx = 2 * (int)(qc.ux >> sh) - 1 + (tid & 3);
+        int const cy = 2 * (int)(qc.uy >> sh) - 1 + ((tid >> 2) & 3);
+        int const cz = 2 * (int)(qc.uz >> sh) - 1 + (tid >> 4);
+        int const last = (1 << l1) - 1;
+        uint32_t start = 0, count = 0;
+        if (cx >= 0 && cy >= 0 && cz >= 0 && cx <= last && cy <= last && cz <= last)
+            if (!find_cell(g, cell_key(l1, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz), start, count))
+                count = 0;
+        sm.span_start[tid] = start;
+        sm.span_off[tid]   = count; // counts for now; tile_phase_plan turns them into a prefix
+    }
+}
+
+// phase 1 (one thread): compact the non-empty spans, prefix their sizes, choose the axes
+template <int S>
+PCPX_HD void tile_phase_plan(const GridView& g, const TileParams& tp, const TileSmem& sm,
+                             uint32_t tile_first)
+{
+    uint32_t occ[3] = {0u, 0u, 0u}; // bit i of occ[axis]: some covering cell at coordinate i holds points
+    uint32_t n = 0, total = 0;
+    for (int s = 0; s < kTileSpans; ++s)
+    {
+        uint32_t const cnt = sm.span_off[s], st = sm.span_start[s];
+        if (cnt == 0)
+            continue;
+        occ[0] |= 1u << (s & 3), occ[1] |= 1u << ((s >> 2) & 3), occ[2] |= 1u << (s >> 4);
+        sm.span_start[n] = st;
+        sm.span_off[n]   = total;
+        total += cnt;
+        ++n;
+    }
+    sm.span_off[n] = total;
+    auto pop4 = [](uint32_t m) { return (m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u); };
+    uint32_t const ex = pop4(occ[0]), ey = pop4(occ[1]), ez = pop4(occ[2]);
+    // c = the thinnest axis (ties: z, then y), a = the widest of the other two (ties: the lower)
+    int c = 2;
+    if (ey < ez)
+        c = 1;
+    if (ex < (c == 2 ? ez : ey))
+        c = 0;
+    int a = c == 0 ? 1 : 0, b = c == 2 ? 1 : 2;
+    uint32_t const ea = a == 0 ? ex : ey, eb = b == 1 ? ey : ez;
+    if (eb > ea)
+    {
+        int const t = a;
+        a = b, b = t;
+    }
+    TileGeom& tg = *sm.geom;
+    tg.ax[0] = a, tg.ax[1] = b, tg.ax[2] = c;
+    float4 const f     = load_pt(g.pts + tile_first);
+    QueryCell const qc = query_cell(g, f.x, f.y, f.z);
+    int const sh       = g.lcap - (tp.level - kTileShift);
+    int32_t const tx = (int32_t)(qc.ux >> sh), ty = (int32_t)(qc.uy >> sh), tz = (int32_t)(qc.uz >> sh);
+    tg.r0[0] = kTileCells * axis_of_i(tx, ty, tz, a) - 1;
+    tg.r0[1] = kTileCells * axis_of_i(tx, ty, tz, b) - 1;
+    tg.r0[2] = kTileCells * axis_of_i(tx, ty, tz, c) - 1;
+    tg.n_spans   = n;
+    tg.raw_total = total;
+    tg.n_points  = 0;
+    tg.fallback  = 0;
+}
+
+// Visits the points of the covering spans: thread `tid` takes raw indices tid, tid + nthreads, ...
+// (its span pointer only moves forward).
+template <class F>
+PCPX_HD void tile_for_raw(const GridView& g, const TileSmem& sm, int tid, int nthreads, F&& f)
+{
+    uint32_t const total = sm.geom->raw_total;
+    uint32_t sp          = 0;
+    for (uint32_t i = (uint32_t)tid; i < total; i += (uint32_t)nthreads)
+    {
+        while (i >= sm.span_off[sp + 1])
+            ++sp;
+        f(load_pt(g.pts + sm.span_start[sp] + (i - sm.span_off[sp])));
+    }
+}
+
+// phase 2: bin counts (F[bin + 1] += 1)
+template <int S>
+PCPX_HD void tile_phase_count(const GridView& g, const TileParams& tp, const TileSmem& sm, int tid,
+                              int nthreads)
+{
+    TileGeom const tg = *sm.geom;
+    tile_for_raw(g, sm, tid, nthreads, [&](float4 const& p) {
+        int const bin = tile_bin<S>(g, tp, tg, p);
+        if (bin >= 0)
+            tile_atomic_inc(sm.F + bin + 1);
+    });
+}
+
+// phase 3a / 3b / 3c: exclusive scan of the counts, kTileScanLanes chunks
+template <int S>
+PCPX_HD void tile_phase_scan_a(const TileSmem& sm, int tid)
+{
+    constexpr int bins = TileDims<S>::bins, chunk = (bins + kTileScanLanes - 1) / kTileScanLanes;
+    if (tid >= kTileScanLanes)
+        return;
+    uint32_t s = 0;
+    for (int i = tid * chunk; i < (tid + 1) * chunk && i < bins; ++i)
+        s += sm.F[i + 1];
+    sm.partial[tid] = s;
+}
+PCPX_HD void tile_phase_scan_b(const TileParams& tp, const TileSmem& sm)
+{
+    uint32_t run = 0;
+    for (int i = 0; i < kTileScanLanes; ++i)
+    {
+        uint32_t const v = sm.partial[i];
+        sm.partial[i]    = run;
+        run += v;
+    }
+    sm.geom->n_points = run;
+    if (run > tp.max_points)
+        sm.geom->fallback = 1;
+}
+template <int S>
+PCPX_HD void tile_phase_scan_c(const TileSmem& sm, int tid)
+{
+    constexpr int bins = TileDims<S>::bins, chunk = (bins + kTileScanLanes - 1) / kTileScanLanes;
+    if (tid >= kTileScanLanes)
+        return;
+    uint32_t run = sm.partial[tid];
+    for (int i = tid * chunk; i < (tid + 1) * chunk && i < bins; ++i)
+    {
+        uint32_t const v = sm.F[i + 1];
+        sm.F[i + 1]      = run; // start of bin i, turned into its end (= start of bin i + 1) by the placement
+        run += v;
+    }
+}
+
+// phase 4: placement.  F[bin + 1] walks from the start of the bin to its end, after which
+// F[i] is the start of bin i for every i (F[0] = 0 was never touched).
+template <int S>
+PCPX_HD void tile_phase_place(const GridView& g, const TileParams& tp, const TileSmem& sm, int tid,
+                              int nthreads)
+{
+    TileGeom const tg = *sm.geom;
+    tile_for_raw(g, sm, tid, nthreads, [&](float4 const& p) {
+        int const bin = tile_bin<S>(g, tp, tg, p);
+        if (bin >= 0)
+            sm.P[tile_atomic_inc(sm.F + bin + 1)] = p;
+    });
+    if (tid == 0)
+        for (uint32_t j = 0; j < kTilePad; ++j)
+            sm.P[tg.n_points + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// phase 5: the placement order inside a bin depends on the order the atomics were served in;
+// sorting every bin by original index makes the staged order — and with it every result bit —
+// a function of the input alone.
+template <int S>
+PCPX_HD void tile_phase_sort_bins(const TileSmem& sm, int tid, int nthreads)
+{
+    for (int bin = tid; bin < TileDims<S>::bins; bin += nthreads)
+    {
+        uint32_t const lo = sm.F[bin], hi = sm.F[bin + 1];
+        for (uint32_t i = lo + 1; i < hi; ++i)
+        {
+            float4 const v   = sm.P[i];
+            uint32_t const w = f2u(v.w);
+            uint32_t j       = i;
+            while (j > lo && f2u(sm.P[j - 1].w) > w)
+            {
+                sm.P[j] = sm.P[j - 1];
+                --j;
+            }
+            sm.P[j] = v;
+        }
+    }
+}
+
+// ---- the per-query search --------------------------------------------------------------------
+template <int KL>
+struct TileList
+{
+    uint32_t a[KL];
+
+    PCPX_HD void reset()
+    {
+#pragma unroll
+        for (int j = 0; j < KL; ++j)
+            a[j] = kKeyEmpty;
+    }
+    // two candidates at once (see TopD::insert2): 2 min + one 3-input max per slot
+    PCPX_HD void insert2(uint32_t k0, uint32_t k1)
+    {
+        uint32_t const lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
+#pragma unroll
+        for (int j = KL - 1; j >= 2; --j)
+        {
+            uint32_t const x = a[j] < lo ? a[j] : lo, y = a[j - 1] < hi ? a[j - 1] : hi;
+            uint32_t const m = x > y ? x : y;
+            a[j]             = m > a[j - 2] ? m : a[j - 2];
+        }
+        if (KL >= 2)
+        {
+            uint32_t const x = a[KL >= 2 ? 1 : 0] < lo ? a[KL >= 2 ? 1 : 0] : lo,
+                           y = a[0] < hi ? a[0] : hi;
+            a[KL >= 2 ? 1 : 0] = x > y ? x : y;
+        }
+        a[0] = a[0] < lo ? a[0] : lo;
+    }
+    PCPX_HD uint32_t get(uint32_t j) const // a[j] without dynamic register indexing
+    {
+        uint32_t r = a[0];
+#pragma unroll
+        for (int i = 1; i < KL; ++i)
+            r = j == (uint32_t)i ? a[i] : r;
+        return r;
+    }
+};
+
+// key of one candidate: truncated distance bits | staged position; kKeyEmpty when the point lies
+// in the exclusion box (common/vector3d_queries.hpp:31-35,59-63: strict <, all three axes)
+PCPX_HD uint32_t tile_key(const float4& c, uint32_t pos, float qx, float qy, float qz, float eps,
+                          float excl_thr, uint32_t mask)
+{
+    float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
+    float const d2 = sqdist_x(dx, dy, dz);
+    if (d2 < excl_thr) // necessary for the box test; rare (the query itself, near-duplicates)
+        if (fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps)
+            return kKeyEmpty;
+    return (f2u(d2) & ~mask) | pos;
+}
+
+PCPX_HD int tile_zigzag(int i) { return (i & 1) ? (i + 1) >> 1 : -(i >> 1); } // 0, +1, -1, +2, -2, ...
+
+// Returns true when the list holds the final answer (first k keys = the k nearest eligible
+// points, membership exact).
+template <int KL, int S>
+PCPX_HD bool tile_search(const GridView& g, const TileParams& tp, const TileGeom& tg,
+                         const float4* P, const uint32_t* F, float qx, float qy, float qz,
+                         uint32_t k, float eps, TileList<KL>& top, uint32_t* n_cand)
+{
+    using D = TileDims<S>;
+    int const A = tg.ax[0], B = tg.ax[1], C = tg.ax[2];
+    float const ta = (axis_of(qx, qy, qz, A) - axis_of(g.ox, g.oy, g.oz, A)) * tp.bins_per_len -
+                     (float)(tg.r0[0] * S);
+    float const tb = (axis_of(qx, qy, qz, B) - axis_of(g.ox, g.oy, g.oz, B)) * tp.bins_per_len -
+                     (float)(tg.r0[1] * S);
+    float const tc = (axis_of(qx, qy, qz, C) - axis_of(g.ox, g.oy, g.oz, C)) * tp.cells_per_len -
+                     (float)tg.r0[2];
+    int ib = (int)floorf(tb), ic = (int)floorf(tc);
+    ib = ib < 0 ? 0 : (ib > D::nb - 1 ? D::nb - 1 : ib);
+    ic = ic < 0 ? 0 : (ic > D::nc - 1 ? D::nc - 1 : ic);
+    // the scan ball must stay inside the staged region
+    float const gab = fminf(fminf(ta, (float)D::na - ta), fminf(tb, (float)D::nb - tb)) - tp.delta_bins;
+    float const gc  = fminf(tc, (float)D::nc - tc) - tp.delta_cells;
+    float rscan     = fminf(fminf(gab * tp.len_per_bin, gc * tp.h), tp.scan_cap * tp.h);
+    rscan           = rscan > 0.f ? rscan : 0.f;
+    float const r2scan  = rscan * rscan * 0.999999f;
+    float r2            = r2scan;
+    float const excl    = 3.0001f * eps * eps;
+    uint32_t const mask = tp.key_mask;
+    uint32_t cand       = 0;
+    top.reset();
+    for (int jc = 0; jc <= 2 * tp.rows_c; ++jc)
+    {
+        int const dc = tile_zigzag(jc), rc = ic + dc;
+        if ((unsigned)rc >= (unsigned)D::nc)
+            continue;
+        float const gapc = dc > 0 ? (float)rc - tc : (dc < 0 ? tc - (float)(rc + 1) : 0.f);
+        float lbc        = (gapc - tp.delta_cells) * tp.h;
+        lbc              = lbc > 0.f ? lbc : 0.f;
+        float const lbc2 = lbc * lbc;
+        if (lbc2 > r2 * 1.00001f)
+            continue;
+        for (int jb = 0; jb <= 2 * tp.rows_b; ++jb)
+        {
+            int const db = tile_zigzag(jb), rb = ib + db;
+            if ((unsigned)rb >= (unsigned)D::nb)
+                continue;
+            float const gapb = db > 0 ? (float)rb - tb : (db < 0 ? tb - (float)(rb + 1) : 0.f);
+            float lbb        = (gapb - tp.delta_bins) * tp.len_per_bin;
+            lbb              = lbb > 0.f ? lbb : 0.f;
+            float const rem  = r2 * 1.00001f - (lbb * lbb + lbc2);
+            if (rem < 0.f)
+                continue;
+            float const reach = sqrtf(rem) * tp.bins_per_len + tp.delta_bins;
+            int alo = (int)floorf(ta - reach), ahi = (int)floorf(ta + reach);
+            alo = alo < 0 ? 0 : alo;
+            ahi = ahi > D::na - 1 ? D::na - 1 : ahi;
+            if (alo > ahi)
+                continue;
+            int const base    = (rc * D::nb + rb) * D::na;
+            uint32_t const lo = F[base + alo], hi = F[base + ahi + 1];
+            for (uint32_t p = lo; p < hi; p += 2)
+            {
+                float4 const c0 = P[p], c1 = P[p + 1]; // P is padded: p + 1 is readable
+                uint32_t const k0 = tile_key(c0, p, qx, qy, qz, eps, excl, mask);
+                uint32_t const k1 =
+                    p + 1 < hi ? tile_key(c1, p + 1, qx, qy, qz, eps, excl, mask) : kKeyEmpty;
+                top.insert2(k0, k1);
+            }
+            cand += hi - lo;
+            // the ball shrinks to the (KL-1)-th smallest distance seen (upper end of its
+            // truncation bucket); NaN while the list is not full: fminf keeps r2
+            r2 = fminf(r2, u2f(top.a[KL - 2] | mask));
+        }
+    }
+    if (n_cand)
+        *n_cand = cand;
+    uint32_t const kk = top.get(k - 1), kn = top.get(k);
+    // final: k eligible points found, the k-th lies inside the scanned ball, and the (k+1)-th
+    // differs from it in the kept bits (membership unambiguous)
+    return kk != kKeyEmpty && u2f(kk | mask) <= r2scan && ((kk ^ kn) & ~mask) != 0u;
+}
+
+// ---- epilogues over the k winners --------------------------------------------------------------
+
+// PCA normal (+ centroid) as normal_two_pass does it: moments about the query point.
+template <int KL>
+PCPX_HD void tile_normal(const float4* P, const TileList<KL>& top, uint32_t k, uint32_t mask,
+                         float qx, float qy, float qz, float* n3, float* c3)
+{
+    float s1x = 0.f, s1y = 0.f, s1z = 0.f;
+    Sym3 s2{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < KL; ++j)
+        if ((uint32_t)j < k)
+        {
+            float4 const c = P[top.a[j] & mask];
+            float const dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
+            s1x += dx, s1y += dy, s1z += dz;
+            s2.xx += dx * dx, s2.xy += dx * dy, s2.xz += dx * dz;
+            s2.yy += dy * dy, s2.yz += dy * dz, s2.zz += dz * dz;
+        }
+    float const inv = 1.f / (float)k;
+    float const mx = s1x * inv, my = s1y * inv, mz = s1z * inv;
+    Sym3 m;
+    m.xx = s2.xx - s1x * mx, m.xy = s2.xy - s1x * my, m.xz = s2.xz - s1x * mz;
+    m.yy = s2.yy - s1y * my, m.yz = s2.yz - s1y * mz, m.zz = s2.zz - s1z * mz;
+    smallest_eigenvector(m, n3[0], n3[1], n3[2], nullptr);
+    c3[0] = qx + mx, c3[1] = qy + my, c3[2] = qz + mz;
+}
+
+// Calls f(slot, d2, original index) for the k winners in ascending (exact d2, original index)
+// order.  The list is sorted by TRUNCATED distance, so exact order can differ only inside runs of
+// keys that agree in the kept bits; an element displaced by one such neighbour is put right on
+// the fly, anything longer returns false (the query then goes to the retry queue; what was
+// emitted is overwritten).
+template <int KL, class F>
+PCPX_HD bool tile_emit_sorted(const float4* P, const TileList<KL>& top, uint32_t k, uint32_t mask,
+                              float qx, float qy, float qz, F&& f)
+{
+    float hd = 0.f, ld = -1.f; // held back / last emitted
+    uint32_t hid = 0, lid = 0, slot = 0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < KL; ++j)
+        if ((uint32_t)j < k)
+        {
+            float4 const c    = P[top.a[j] & mask];
+            float const d2    = sqdist_x(fsub_x(c.x, qx), fsub_x(c.y, qy), fsub_x(c.z, qz));
+            uint32_t const id = f2u(c.w);
+            if (j == 0)
+            {
+                hd = d2, hid = id;
+                continue;
+            }
+            bool const before_held = d2 < hd || (d2 == hd && id < hid);
+            float const ed         = before_held ? d2 : hd;
+            uint32_t const eid     = before_held ? id : hid;
+            ok = ok && !(ed < ld || (ed == ld && eid < lid && slot > 0));
+            f(slot++, ed, eid);
+            ld = ed, lid = eid;
+            if (!before_held)
+                hd = d2, hid = id;
+        }
+    ok = ok && !(hd < ld || (hd == ld && hid < lid && slot > 0));
+    f(slot, hd, hid);
+    return ok;
+}
+
+} // namespace pcpx

@@ -17,6 +17,7 @@
 #include "normals_core.cuh"
 #include "radius_core.cuh"
 #include "smoothing_core.cuh"
+#include "tile_core.cuh"
 #include "tree_core.cuh"
 
 using namespace pcpx;
@@ -531,3 +532,148 @@ void emu_wlop_step(void* hp, const float* vj_sorted, void* hq, const float* wi_s
 }
 
 } // extern "C"
+
+
+// ---- the tile path (tile_core.cuh): the phases of tile_knn_kernel run sequentially over the
+// threads of one emulated CTA per tile.  mode: 0 = kNN rows, 1 = mean distance, 2 = normals.
+// `done[row]` = 1 when the tile pass gave the final answer (the product sends the rest to the
+// retry queue).  stats: [0] tiles, [1] fallback tiles, [2] queries not final, [3] candidates,
+// [4] largest staged region, [5] queries not final because the emitted order was ambiguous.
+template <int KL, int S>
+static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, uint32_t max_points,
+                      float scan_cap, int nthreads, uint32_t* idx, float* d2, uint32_t* cnt,
+                      float* nrm, float* ctr, float* means, uint8_t* done, uint64_t* stats)
+{
+    GridView const& g   = ix->g;
+    TileParams const tp = make_tile_params<S>(g, level, max_points, scan_cap);
+    std::vector<float4> P(max_points + kTilePad);
+    std::vector<uint32_t> F(TileDims<S>::bins + 1), span_start(kTileSpans), span_off(kTileSpans + 1),
+        partial(kTileScanLanes);
+    TileGeom geom;
+    TileSmem sm{P.data(), F.data(), span_start.data(), span_off.data(), partial.data(), &geom};
+    int const sh = g.lcap - (level - kTileShift);
+    auto tile_of = [&](uint32_t i) {
+        QueryCell c = query_cell(g, ix->pts[i].x, ix->pts[i].y, ix->pts[i].z);
+        return morton3(c.ux >> sh, c.uy >> sh, c.uz >> sh);
+    };
+    uint32_t s0 = 0;
+    while (s0 < g.n)
+    {
+        uint32_t s1 = s0 + 1;
+        uint64_t const code = tile_of(s0);
+        while (s1 < g.n && tile_of(s1) == code)
+            ++s1;
+        stats[0]++;
+        for (int t = 0; t < nthreads; ++t)
+            tile_phase_lookup<S>(g, tp, sm, s0, t, nthreads);
+        tile_phase_plan<S>(g, tp, sm, s0);
+        for (int t = 0; t < nthreads; ++t)
+            tile_phase_count<S>(g, tp, sm, t, nthreads);
+        for (int t = 0; t < nthreads; ++t)
+            tile_phase_scan_a<S>(sm, t);
+        tile_phase_scan_b(tp, sm);
+        stats[4] = std::max<uint64_t>(stats[4], geom.n_points);
+        if (geom.fallback)
+        {
+            stats[1]++;
+            stats[2] += s1 - s0;
+            s0 = s1;
+            continue;
+        }
+        for (int t = 0; t < nthreads; ++t)
+            tile_phase_scan_c<S>(sm, t);
+        // serve the placement "atomics" in a scrambled thread order: results must not depend on it
+        for (int t = nthreads - 1; t >= 0; --t)
+            tile_phase_place<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
+        for (int t = 0; t < nthreads; ++t)
+            tile_phase_sort_bins<S>(sm, t, nthreads);
+        for (uint32_t t = s0; t < s1; ++t)
+        {
+            float4 const q     = ix->pts[t];
+            uint32_t const row = f2u(q.w);
+            TileList<KL> top;
+            uint32_t cand = 0;
+            bool ok = tile_search<KL, S>(g, tp, geom, sm.P, sm.F, q.x, q.y, q.z, k, eps, top, &cand);
+            stats[3] += cand;
+            if (ok && mode == 2)
+            {
+                float n3[3], c3[3];
+                tile_normal<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z, n3, c3);
+                for (int a = 0; a < 3; ++a)
+                {
+                    nrm[3 * (size_t)row + a] = n3[a];
+                    if (ctr)
+                        ctr[3 * (size_t)row + a] = c3[a];
+                }
+            }
+            else if (ok && mode == 0)
+            {
+                ok = tile_emit_sorted<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z,
+                                          [&](uint32_t slot, float dd, uint32_t id) {
+                                              idx[(size_t)row * k + slot] = id;
+                                              if (d2)
+                                                  d2[(size_t)row * k + slot] = dd;
+                                          });
+                if (ok && cnt)
+                    cnt[row] = k;
+                if (!ok)
+                    stats[5]++;
+            }
+            else if (ok)
+            {
+                float sum = 0.f;
+                ok = tile_emit_sorted<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z,
+                                          [&](uint32_t, float dd, uint32_t) { sum = sum + sqrtf(dd); });
+                means[row] = sum / (float)k;
+                if (!ok)
+                    stats[5]++;
+            }
+            done[row] = ok;
+            if (!ok)
+                stats[2]++;
+        }
+        s0 = s1;
+    }
+}
+
+static int tile_list_size_for(uint32_t k)
+{
+    static const int sizes[] = {5, 9, 13, 16, 21, 25, 31, 33};
+    for (int s : sizes)
+        if ((uint32_t)s >= k + 1)
+            return s;
+    return 0;
+}
+
+extern "C" int emu_tile(void* h, uint32_t k, double eps, int mode, int sub, int level,
+                        uint32_t max_points, double scan_cap, int nthreads, uint32_t* idx,
+                        float* d2, uint32_t* cnt, float* nrm, float* ctr, float* means,
+                        uint8_t* done, uint64_t* stats)
+{
+    EmuIndex* ix = static_cast<EmuIndex*>(h);
+    if (level < kTileShift || level > ix->g.lfine)
+        return -2;
+#define EMU_TILE(KLV)                                                                          \
+    case KLV:                                                                                  \
+        if (sub == 1)                                                                          \
+            tile_impl<KLV, 1>(ix, k, (float)eps, mode, level, max_points, (float)scan_cap,     \
+                              nthreads, idx, d2, cnt, nrm, ctr, means, done, stats);           \
+        else                                                                                   \
+            tile_impl<KLV, 2>(ix, k, (float)eps, mode, level, max_points, (float)scan_cap,     \
+                              nthreads, idx, d2, cnt, nrm, ctr, means, done, stats);           \
+        break;
+    switch (tile_list_size_for(k))
+    {
+        EMU_TILE(5)
+        EMU_TILE(9)
+        EMU_TILE(13)
+        EMU_TILE(16)
+        EMU_TILE(21)
+        EMU_TILE(25)
+        EMU_TILE(31)
+        EMU_TILE(33)
+    default: return -5;
+    }
+#undef EMU_TILE
+    return 0;
+}

@@ -57,6 +57,9 @@ class Emu:
                               C.c_int, _u32p, _f32p, _u32p, _u64p, _u32p]
         L.emu_normals.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_uint32, C.c_double,
                                   C.c_double, C.c_int, _f32p, _f32p, _f32p, _u32p]
+        L.emu_tile.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_int,
+                               C.c_uint32, C.c_double, C.c_int, _u32p, _f32p, _u32p, _f32p, _f32p,
+                               _f32p, _u8p, _u64p]
         L.emu_radius.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, C.c_float, _u32p, _u64p,
                                  _u32p]
         L.emu_density_keep.argtypes = [C.c_void_p, C.c_float, C.c_uint32, _u8p]
@@ -183,6 +186,30 @@ class EmuIndex:
                                 _ptr(ties, _u32p))
         assert rc == 0
         return nrm, ctr, means, int(ties[0])
+
+    def tile(self, k, mode, level, sub=2, eps=1e-5, max_points=1024, scan_cap=1.0, nthreads=128):
+        """The tile path (tile_core.cuh) over the indexed points themselves; mode 0 = kNN rows,
+        1 = mean distance, 2 = normals.  Returns a dict with the outputs, `done` (rows the tile
+        pass finished; the product sends the rest to the retry queue) and `stats`."""
+        n = self.n
+        idx = np.full((n, k), 0xFFFFFFFF, np.uint32)
+        d2 = np.full((n, k), np.inf, np.float32)
+        cnt = np.zeros(n, np.uint32)
+        nrm = np.zeros((n, 3), np.float32)
+        ctr = np.zeros((n, 3), np.float32)
+        means = np.zeros(n, np.float32)
+        done = np.zeros(n, np.uint8)
+        st = np.zeros(6, np.uint64)
+        rc = self.L.emu_tile(self.h, k, eps, mode, sub, level, max_points, scan_cap, nthreads,
+                             _ptr(idx, _u32p), _ptr(d2, _f32p), _ptr(cnt, _u32p),
+                             _ptr(nrm, _f32p), _ptr(ctr, _f32p), _ptr(means, _f32p),
+                             _ptr(done, _u8p), _ptr(st, _u64p))
+        assert rc == 0, rc
+        return dict(idx=idx, d2=d2, cnt=cnt, normals=nrm, centroids=ctr, means=means,
+                    done=done.astype(bool),
+                    stats=dict(tiles=int(st[0]), fallback_tiles=int(st[1]), not_final=int(st[2]),
+                               candidates=int(st[3]), max_region=int(st[4]),
+                               order_ambiguous=int(st[5])))
 
     def radius_count(self, queries, r, radii=None):
         q = _f32(queries)

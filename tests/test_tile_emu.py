@@ -1,0 +1,117 @@
+"""CPU-only check of the tile path (point-cloud-processing_b200/csrc/tile_core.cuh): tests/emu runs
+the SAME staging phases and per-query search the tile kernel runs, one emulated CTA per tile, with
+the placement "atomics" served in a scrambled thread order.  Every row the tile pass declares final
+must be bit-equal to the exact (d2, original index) search — itself pinned to the oracle and the
+reference fixtures by test_emu_parity.py — and rows it does not finish must be flagged (the
+product sends those to the retry queue)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+synth = importlib.import_module("point-cloud-processing_b200.synth")
+FIX = os.path.join(os.path.dirname(__file__), "golden", "ref_fixtures.npz")
+PAD = 0xFFFFFFFF
+
+
+def clouds():
+    rng = np.random.default_rng(5)
+    plane = synth.noisy_plane(60_000, seed=7)
+    sphere = synth.noisy_sphere(40_000, seed=42)
+    mix = synth.noise_mix(50_000, seed=11)
+    # exact ties: a jittered lattice snapped to a coarse float grid, plus exact duplicates
+    g = np.stack(np.meshgrid(np.arange(40), np.arange(40), np.arange(3), indexing="ij"), -1)
+    lattice = (g.reshape(-1, 3) * np.float32(0.25)).astype(np.float32)
+    dup = np.concatenate([plane[:20_000], plane[:2_000] + np.float32(3e-6), plane[:500]])
+    tilted = plane[:50_000] @ np.array([[0.8, 0.0, 0.6], [0.0, 1.0, 0.0], [-0.6, 0.0, 0.8]],
+                                       np.float32).T
+    cube = rng.uniform(-1, 1, (30_000, 3)).astype(np.float32)
+    return dict(plane=plane, sphere=sphere, mix=mix, lattice=lattice, dup=dup,
+                tilted=np.ascontiguousarray(tilted), cube=cube)
+
+
+@pytest.fixture(scope="module")
+def cloud_set():
+    return clouds()
+
+
+def tile_levels(ix, k):
+    info = ix.info()
+    lv = ix.plan(k)["level"]
+    return sorted({max(2, min(info["lfine"], l)) for l in (lv, lv - 1)})
+
+
+@pytest.mark.parametrize("name", ["plane", "sphere", "mix", "lattice", "dup", "tilted", "cube"])
+def test_tile_rows_are_exact(emu, cloud_set, name):
+    xyz = cloud_set[name]
+    ix = emu.index(xyz)
+    if ix.info()["lfine"] < 2:
+        pytest.skip("cloud too small for a tile level")
+    for k in (1, 8, 15, 30):
+        ridx, rd2, rcnt, _ = ix.knn(None, k, exact_only=True)
+        rnrm, rctr, rmean, _ = ix.normals(None, k, want_means=True, exact_only=True)
+        for level in tile_levels(ix, k):
+            for sub in (1, 2):
+                r = ix.tile(k, 0, level, sub=sub, max_points=4096)
+                d = r["done"]
+                assert np.array_equal(r["idx"][d], ridx[d]), (name, k, level, sub)
+                assert np.array_equal(r["d2"][d], rd2[d]), (name, k, level, sub)
+                assert np.all(r["cnt"][d] == k)
+                assert np.all(rcnt[d] == k)
+                m = ix.tile(k, 1, level, sub=sub, max_points=4096)
+                assert np.array_equal(m["means"][m["done"]], rmean[m["done"]]), (name, k, level, sub)
+                if k >= 3:
+                    nr = ix.tile(k, 2, level, sub=sub, max_points=4096)
+                    dn = nr["done"]
+                    cos = np.abs((nr["normals"][dn] * rnrm[dn]).sum(1))
+                    # same neighbour set; moments taken about the query point in both
+                    assert np.all(1 - cos[np.isfinite(cos)] <= 1e-4) or name in ("lattice", "cube")
+                    assert np.allclose(nr["centroids"][dn], rctr[dn], atol=1e-5 * np.abs(xyz).max())
+
+
+def test_tile_finishes_most_of_a_surface(emu, cloud_set):
+    for name, k in (("plane", 15), ("sphere", 15), ("tilted", 8)):
+        ix = emu.index(cloud_set[name])
+        r = ix.tile(k, 0, ix.plan(k)["level"], sub=2, max_points=4096)
+        assert r["stats"]["fallback_tiles"] == 0
+        assert r["done"].mean() > 0.9, (name, r["stats"])
+
+
+def test_tile_scan_cap_and_fallback(emu, cloud_set):
+    xyz = cloud_set["plane"]
+    ix = emu.index(xyz)
+    k = 15
+    level = ix.plan(k)["level"]
+    ridx, rd2, _, _ = ix.knn(None, k, exact_only=True)
+    for cap in (0.75, 1.0, 1.5, 2.0):
+        r = ix.tile(k, 0, level, sub=2, scan_cap=cap, max_points=4096)
+        d = r["done"]
+        assert np.array_equal(r["idx"][d], ridx[d]) and np.array_equal(r["d2"][d], rd2[d]), cap
+    # a region that does not fit the staging capacity: the whole tile is handed on
+    r = ix.tile(k, 0, level, sub=2, max_points=128)
+    assert r["stats"]["fallback_tiles"] > 0
+    d = r["done"]
+    assert np.array_equal(r["idx"][d], ridx[d])
+    # thread count of the emulated CTA must not matter
+    a = ix.tile(k, 0, level, sub=2, nthreads=32)
+    b = ix.tile(k, 0, level, sub=2, nthreads=256)
+    assert np.array_equal(a["done"], b["done"]) and np.array_equal(a["idx"], b["idx"])
+
+
+@pytest.mark.parametrize("name", ["sphere", "plane", "lattice", "dup"])
+def test_tile_against_reference_fixtures(emu, name):
+    fix = np.load(FIX)
+    xyz = fix[name + "_xyz"]
+    ix = emu.index(xyz)
+    if ix.info()["lfine"] < 2:
+        pytest.skip("cloud too small for a tile level")
+    for k in (1, 8, 15):
+        want = fix["%s_self_k%d_idx" % (name, k)].astype(np.int64)
+        wd2 = fix["%s_self_k%d_d2" % (name, k)]
+        level = max(2, ix.plan(k)["level"])
+        r = ix.tile(k, 0, level, sub=2, max_points=4096)
+        d = r["done"] & (want[:, k - 1] >= 0)
+        got = r["idx"].astype(np.int64)
+        assert np.array_equal(got[d], want[d]), (name, k)
+        assert np.array_equal(r["d2"][d], wd2[d]), (name, k)
