@@ -401,6 +401,10 @@ int pcpx_set_tuning(const char* name, double value)
             tuning().success_margin = (float)value;
         else if (!std::strcmp(name, "tile"))
             tuning().tile = (int)value;
+        else if (!std::strcmp(name, "tile_alg"))
+            tuning().tile_alg = (int)value;
+        else if (!std::strcmp(name, "tile_first_cap"))
+            tuning().tile_first_cap = (int)value;
         else if (!std::strcmp(name, "tile_sub"))
             tuning().tile_sub = (int)value;
         else if (!std::strcmp(name, "tile_cap"))

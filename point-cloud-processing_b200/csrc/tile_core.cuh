@@ -46,6 +46,8 @@ constexpr int kTileSpans      = 64;                  // 4^3 cells at (main level
 constexpr int kTileScanLanes  = 32;                  // threads that scan the bin counts
 constexpr uint32_t kKeyEmpty  = 0xFFFFFFFFu;
 constexpr uint32_t kTilePad   = 2;                   // readable entries behind the staged points
+constexpr int kTileCandCap    = 64;                  // candidates one query can list
+constexpr uint32_t kNoSelf    = 0xFFFFFFFFu;
 
 template <int S>
 struct TileDims
@@ -68,6 +70,7 @@ struct TileParams
     float delta_bins;    // g.delta in (a, b) bin units: slack of every float-evaluated bin bound
     float delta_cells;   // g.delta in cell units
     float scan_cap;      // largest scan radius, in units of h
+    uint32_t first_cap;  // batched form: candidates listed before the ball is first shrunk
 };
 
 template <int S>
@@ -90,6 +93,7 @@ inline TileParams make_tile_params(const GridView& g, int level, uint32_t max_po
     tp.scan_cap      = scan_cap;
     tp.rows_b        = (int)ceilf(scan_cap * (float)S);
     tp.rows_c        = (int)ceilf(scan_cap);
+    tp.first_cap     = 32;
     return tp;
 }
 
@@ -113,6 +117,12 @@ struct TileSmem
     uint32_t* span_off;   // kTileSpans + 1 (prefix over the compacted spans)
     uint32_t* partial;    // kTileScanLanes
     TileGeom* geom;
+    // the batched form of the search (tile_list_candidates / tile_select)
+    uint32_t* rowmask;    // nc words: bit ib of word ic = row (ic, ib) holds points
+    uint32_t* seg_off;    // kTileCells * kTileCells * S + 1: prefix over the tile's row segments
+    uint16_t* qlist;      // staged positions of the tile's own points (the queries), bin order
+    uint16_t* cl;         // kTileCandCap x nthreads candidate positions, [j * nthreads + tid]
+    uint32_t* gpos;       // max_points: position of every staged point in the sorted global array
 };
 
 PCPX_HD float axis_of(float x, float y, float z, int ax) { return ax == 0 ? x : (ax == 1 ? y : z); }
@@ -174,6 +184,8 @@ PCPX_HD void tile_phase_lookup(const GridView& g, const TileParams& tp, const Ti
 {
     for (int i = tid; i <= TileDims<S>::bins; i += nthreads)
         sm.F[i] = 0u;
+    if (sm.rowmask && tid < TileDims<S>::nc)
+        sm.rowmask[tid] = 0u;
     if (tid < kTileSpans)
     {
         float4 const f     = load_pt(g.pts + tile_first);
@@ -254,7 +266,8 @@ PCPX_HD void tile_for_raw(const GridView& g, const TileSmem& sm, int tid, int nt
     {
         while (i >= sm.span_off[sp + 1])
             ++sp;
-        f(load_pt(g.pts + sm.span_start[sp] + (i - sm.span_off[sp])));
+        uint32_t const gi = sm.span_start[sp] + (i - sm.span_off[sp]);
+        f(load_pt(g.pts + gi), gi);
     }
 }
 
@@ -264,7 +277,7 @@ PCPX_HD void tile_phase_count(const GridView& g, const TileParams& tp, const Til
                               int nthreads)
 {
     TileGeom const tg = *sm.geom;
-    tile_for_raw(g, sm, tid, nthreads, [&](float4 const& p) {
+    tile_for_raw(g, sm, tid, nthreads, [&](float4 const& p, uint32_t) {
         int const bin = tile_bin<S>(g, tp, tg, p);
         if (bin >= 0)
             tile_atomic_inc(sm.F + bin + 1);
@@ -318,10 +331,15 @@ PCPX_HD void tile_phase_place(const GridView& g, const TileParams& tp, const Til
                               int nthreads)
 {
     TileGeom const tg = *sm.geom;
-    tile_for_raw(g, sm, tid, nthreads, [&](float4 const& p) {
+    tile_for_raw(g, sm, tid, nthreads, [&](float4 const& p, uint32_t gi) {
         int const bin = tile_bin<S>(g, tp, tg, p);
         if (bin >= 0)
-            sm.P[tile_atomic_inc(sm.F + bin + 1)] = p;
+        {
+            uint32_t const pos = tile_atomic_inc(sm.F + bin + 1);
+            sm.P[pos]          = p;
+            if (sm.gpos)
+                sm.gpos[pos] = gi;
+        }
     });
     if (tid == 0)
         for (uint32_t j = 0; j < kTilePad; ++j)
@@ -339,15 +357,20 @@ PCPX_HD void tile_phase_sort_bins(const TileSmem& sm, int tid, int nthreads)
         uint32_t const lo = sm.F[bin], hi = sm.F[bin + 1];
         for (uint32_t i = lo + 1; i < hi; ++i)
         {
-            float4 const v   = sm.P[i];
-            uint32_t const w = f2u(v.w);
-            uint32_t j       = i;
+            float4 const v    = sm.P[i];
+            uint32_t const gv = sm.gpos ? sm.gpos[i] : 0u;
+            uint32_t const w  = f2u(v.w);
+            uint32_t j        = i;
             while (j > lo && f2u(sm.P[j - 1].w) > w)
             {
                 sm.P[j] = sm.P[j - 1];
+                if (sm.gpos)
+                    sm.gpos[j] = sm.gpos[j - 1];
                 --j;
             }
             sm.P[j] = v;
+            if (sm.gpos)
+                sm.gpos[j] = gv;
         }
     }
 }
@@ -487,6 +510,295 @@ PCPX_HD bool tile_search(const GridView& g, const TileParams& tp, const TileGeom
     // final: k eligible points found, the k-th lies inside the scanned ball, and the (k+1)-th
     // differs from it in the kept bits (membership unambiguous)
     return kk != kKeyEmpty && u2f(kk | mask) <= r2scan && ((kk ^ kn) & ~mask) != 0u;
+}
+
+
+// =============================================================================================
+// Batched form of the per-query search.
+//
+// tile_search above interleaves geometry, loads and list updates, and its lanes run the nested
+// row / candidate loops in lock-step: a warp pays max-over-lanes of every row, and the two-at-a-time
+// sorted insert costs 1.5 min/max per list slot and candidate on the ALU pipe (measured: half of
+// the lanes idle in that loop, 91 instructions per pair of candidates).  The batched form splits
+// the work:
+//   Q1  tile_list_candidates: the geometry only — rows, bin ranges — and the staged positions of
+//       the candidates go to a per-thread list in shared memory (a 4-instruction loop body);
+//   Q2  tile_select: a REGULAR loop over that list, eight candidates at a time: keys, a 19-exchange
+//       sorting network over the eight, and a bitonic merge into the sorted register list
+//       (13.75 min/max per candidate for a 16-entry list instead of 24), no exclusion test (the
+//       query's own staged position is left out when the list is made; a foreign point inside
+//       the exclusion box shows up as a smallest key below 3 eps^2 and sends the query to the
+//       retry queue).
+// =============================================================================================
+
+// phase 6 (after the bins are sorted): which rows hold points, and the tile's row segments
+template <int S>
+PCPX_HD void tile_phase_rows(const TileSmem& sm, int tid, int nthreads)
+{
+    using D = TileDims<S>;
+    for (int r = tid; r < D::nb * D::nc; r += nthreads)
+    {
+        int const ic = r / D::nb, ib = r - ic * D::nb;
+        if (sm.F[(r + 1) * D::na] > sm.F[r * D::na])
+        {
+#ifdef __CUDA_ARCH__
+            atomicOr(sm.rowmask + ic, 1u << ib);
+#else
+            sm.rowmask[ic] |= 1u << ib;
+#endif
+        }
+    }
+    if (tid == 0)
+    {
+        // the tile's own points: rows ic in [1, 1 + 4), ib in [S, 5 S), bins ia in [S, 5 S)
+        uint32_t run = 0;
+        int seg      = 0;
+        for (int ic = 1; ic <= kTileCells; ++ic)
+            for (int ib = S; ib < S + kTileCells * S; ++ib, ++seg)
+            {
+                int const base  = (ic * D::nb + ib) * D::na;
+                sm.seg_off[seg] = run;
+                run += sm.F[base + S + kTileCells * S] - sm.F[base + S];
+            }
+        sm.seg_off[seg] = run;
+    }
+}
+
+// phase 7: the query list (staged positions of the tile's own points, row-major bin order)
+template <int S>
+PCPX_HD void tile_phase_qlist(const TileSmem& sm, int tid, int nthreads)
+{
+    using D            = TileDims<S>;
+    constexpr int segs = kTileCells * kTileCells * S;
+    for (int seg = tid; seg < segs; seg += nthreads)
+    {
+        int const ic = 1 + seg / (kTileCells * S), ib = S + seg % (kTileCells * S);
+        int const base    = (ic * D::nb + ib) * D::na;
+        uint32_t const lo = sm.F[base + S], hi = sm.F[base + S + kTileCells * S];
+        uint32_t w        = sm.seg_off[seg];
+        for (uint32_t p = lo; p < hi; ++p)
+            sm.qlist[w++] = (uint16_t)p;
+    }
+}
+
+PCPX_HD float tile_sqrt(float x) // only ever widens a bin range: an approximation is fine
+{
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
+// Per-query state of the candidate listing: the listing stops when the list is full and resumes
+// where it stopped, so a query's candidates can be worked off in several rounds (and the ball
+// shrinks between rounds).
+struct TileCursor
+{
+    float ta, tb, tc; // position of the query in bin / cell units, relative to the region
+    float r2scan;     // squared radius of the ball that will have been scanned at the end
+    float r2;         // current squared radius (shrinks once the list is full)
+    int ib, ic;
+    int jc, jb;          // next row to visit
+    uint32_t p_resume;   // position inside that row, 0 = from its start
+    bool done;
+};
+
+template <int S>
+PCPX_HD TileCursor tile_cursor(const GridView& g, const TileParams& tp, const TileGeom& tg, float qx,
+                               float qy, float qz)
+{
+    using D = TileDims<S>;
+    int const A = tg.ax[0], B = tg.ax[1], C = tg.ax[2];
+    TileCursor cu;
+    cu.ta = (axis_of(qx, qy, qz, A) - axis_of(g.ox, g.oy, g.oz, A)) * tp.bins_per_len -
+            (float)(tg.r0[0] * S);
+    cu.tb = (axis_of(qx, qy, qz, B) - axis_of(g.ox, g.oy, g.oz, B)) * tp.bins_per_len -
+            (float)(tg.r0[1] * S);
+    cu.tc = (axis_of(qx, qy, qz, C) - axis_of(g.ox, g.oy, g.oz, C)) * tp.cells_per_len -
+            (float)tg.r0[2];
+    int ib = (int)floorf(cu.tb), ic = (int)floorf(cu.tc);
+    cu.ib = ib < 0 ? 0 : (ib > D::nb - 1 ? D::nb - 1 : ib);
+    cu.ic = ic < 0 ? 0 : (ic > D::nc - 1 ? D::nc - 1 : ic);
+    // the scan ball must stay inside the staged region
+    float const gab =
+        fminf(fminf(cu.ta, (float)D::na - cu.ta), fminf(cu.tb, (float)D::nb - cu.tb)) - tp.delta_bins;
+    float const gc = fminf(cu.tc, (float)D::nc - cu.tc) - tp.delta_cells;
+    float rscan    = fminf(fminf(gab * tp.len_per_bin, gc * tp.h), tp.scan_cap * tp.h);
+    rscan          = rscan > 0.f ? rscan : 0.f;
+    cu.r2scan      = rscan * rscan * 0.999999f;
+    cu.r2          = cu.r2scan;
+    cu.jc = 0, cu.jb = 0, cu.p_resume = 0u;
+    cu.done = false;
+    return cu;
+}
+
+// Q1.  Writes the staged positions of the points in the bins the current ball touches (the
+// query's own position `self` left out) to cl[j * stride], j = 0 .. count - 1, rows nearest
+// first, until `cap` entries are listed or every row has been visited (cu.done).
+template <int S>
+PCPX_HD uint32_t tile_list_candidates(const TileParams& tp, const uint32_t* F,
+                                      const uint32_t* rowmask, TileCursor& cu, uint32_t self,
+                                      uint16_t* cl, int stride, uint32_t cap)
+{
+    using D        = TileDims<S>;
+    float const r2 = cu.r2 * 1.00001f;
+    uint32_t cnt   = 0;
+    // where the previous round stopped: applies to the first row visited now and to no other
+    uint32_t resume = cu.p_resume;
+    cu.p_resume     = 0u;
+    for (; cu.jc <= 2 * tp.rows_c; ++cu.jc, cu.jb = 0, resume = 0u)
+    {
+        int const dc = tile_zigzag(cu.jc), rc = cu.ic + dc;
+        if ((unsigned)rc >= (unsigned)D::nc)
+            continue;
+        uint32_t const rm = rowmask[rc];
+        if (rm == 0u)
+            continue;
+        float const gapc = dc > 0 ? (float)rc - cu.tc : (dc < 0 ? cu.tc - (float)(rc + 1) : 0.f);
+        float lbc        = (gapc - tp.delta_cells) * tp.h;
+        lbc              = lbc > 0.f ? lbc : 0.f;
+        float const remc = r2 - lbc * lbc;
+        if (remc < 0.f)
+            continue;
+        for (; cu.jb <= 2 * tp.rows_b; ++cu.jb)
+        {
+            uint32_t const pr = resume;
+            resume            = 0u;
+            int const db = tile_zigzag(cu.jb), rb = cu.ib + db;
+            if ((unsigned)rb >= (unsigned)D::nb || !((rm >> rb) & 1u))
+                continue;
+            float const gapb =
+                db > 0 ? (float)rb - cu.tb : (db < 0 ? cu.tb - (float)(rb + 1) : 0.f);
+            float lbb       = (gapb - tp.delta_bins) * tp.len_per_bin;
+            lbb             = lbb > 0.f ? lbb : 0.f;
+            float const rem = remc - lbb * lbb;
+            if (rem < 0.f)
+                continue;
+            float const reach = tile_sqrt(rem) * (tp.bins_per_len * 1.000002f) + tp.delta_bins;
+            int alo = (int)floorf(cu.ta - reach), ahi = (int)floorf(cu.ta + reach);
+            alo = alo < 0 ? 0 : alo;
+            ahi = ahi > D::na - 1 ? D::na - 1 : ahi;
+            if (alo > ahi)
+                continue;
+            int const base    = (rc * D::nb + rb) * D::na;
+            uint32_t const hi = F[base + ahi + 1];
+            uint32_t p        = F[base + alo];
+            p                 = pr > p ? pr : p;
+            for (; p < hi; ++p)
+                if (p != self)
+                {
+                    if (cnt == cap)
+                    {
+                        cu.p_resume = p;
+                        return cnt;
+                    }
+                    cl[cnt * (uint32_t)stride] = (uint16_t)p;
+                    ++cnt;
+                }
+        }
+    }
+    cu.done = true;
+    return cnt;
+}
+
+#define PCPX_CE(x, y)                                                                          \
+    do                                                                                         \
+    {                                                                                          \
+        uint32_t const lo_ = (x) < (y) ? (x) : (y), hi_ = (x) < (y) ? (y) : (x);               \
+        (x) = lo_, (y) = hi_;                                                                  \
+    } while (0)
+
+// 19 exchanges (optimal for 8 inputs)
+PCPX_HD void tile_sort8(uint32_t* b)
+{
+    PCPX_CE(b[0], b[1]); PCPX_CE(b[2], b[3]); PCPX_CE(b[4], b[5]); PCPX_CE(b[6], b[7]);
+    PCPX_CE(b[0], b[2]); PCPX_CE(b[1], b[3]); PCPX_CE(b[4], b[6]); PCPX_CE(b[5], b[7]);
+    PCPX_CE(b[1], b[2]); PCPX_CE(b[5], b[6]); PCPX_CE(b[0], b[4]); PCPX_CE(b[3], b[7]);
+    PCPX_CE(b[1], b[5]); PCPX_CE(b[2], b[6]);
+    PCPX_CE(b[1], b[4]); PCPX_CE(b[3], b[6]);
+    PCPX_CE(b[2], b[4]); PCPX_CE(b[3], b[5]);
+    PCPX_CE(b[3], b[4]);
+}
+
+// The KL smallest of (sorted list a[KL]) + (sorted batch b[8]), sorted: the element-wise minimum
+// of the ascending list and the descending (padded) batch is a bitonic sequence that holds them;
+// a bitonic merge sorts it.  KL must be a power of two >= 8.
+template <int KL>
+PCPX_HD void tile_merge8(uint32_t* a, const uint32_t* b)
+{
+    static_assert((KL & (KL - 1)) == 0 && KL >= 8, "list size must be a power of two >= 8");
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        a[KL - 8 + i] = a[KL - 8 + i] < b[7 - i] ? a[KL - 8 + i] : b[7 - i];
+#pragma unroll
+    for (int s = KL / 2; s >= 1; s >>= 1)
+#pragma unroll
+        for (int i = 0; i < KL; ++i)
+            if ((i & s) == 0)
+                PCPX_CE(a[i], a[i + s]);
+}
+
+// Q2.  `top` must be reset by the caller.
+template <int KL>
+PCPX_HD void tile_select(const float4* P, const uint16_t* cl, int stride, uint32_t count,
+                         float qx, float qy, float qz, uint32_t mask, TileList<KL>& top)
+{
+    for (uint32_t j0 = 0; j0 < count; j0 += 8)
+    {
+        uint32_t b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            uint32_t const j   = j0 + (uint32_t)i;
+            uint32_t const pos = cl[(j < count ? j : 0u) * (uint32_t)stride];
+            float4 const c     = P[pos];
+            float const d2 = sqdist_x(fsub_x(c.x, qx), fsub_x(c.y, qy), fsub_x(c.z, qz));
+            b[i]           = j < count ? ((f2u(d2) & ~mask) | pos) : kKeyEmpty;
+        }
+        tile_sort8(b);
+        tile_merge8<KL>(top.a, b);
+    }
+}
+
+// The whole search of one query: rounds of (list up to a cap, select), the ball shrinking to the
+// k-th key's bucket between rounds.  The first round is short (the rows nearest to the query), so
+// that the farther rows are already listed against a tight ball.
+template <int KL, int S>
+PCPX_HD void tile_search_batched(const TileParams& tp, const float4* P, const uint32_t* F,
+                                 const uint32_t* rowmask, TileCursor& cu, uint32_t self,
+                                 uint16_t* cl, int stride, float qx, float qy, float qz,
+                                 uint32_t k, uint32_t first_cap, TileList<KL>& top,
+                                 uint32_t* n_cand)
+{
+    top.reset();
+    uint32_t cap = first_cap, total = 0;
+    do
+    {
+        uint32_t const cnt = tile_list_candidates<S>(tp, F, rowmask, cu, self, cl, stride, cap);
+        tile_select<KL>(P, cl, stride, cnt, qx, qy, qz, tp.key_mask, top);
+        cu.r2 = fminf(cu.r2, u2f(top.get(k - 1) | tp.key_mask)); // NaN while the list is not full
+        cap   = (uint32_t)kTileCandCap;
+        total += cnt;
+    } while (!cu.done);
+    if (n_cand)
+        *n_cand = total;
+}
+
+// final: k eligible points found, the k-th inside the scanned ball, the (k+1)-th different from
+// it in the kept bits, and no foreign point inside the exclusion box (its key would be the
+// smallest; the query's own position was never listed)
+template <int KL>
+PCPX_HD bool tile_is_final(const TileList<KL>& top, uint32_t k, uint32_t mask, float r2scan,
+                           float eps)
+{
+    uint32_t const kk = top.get(k - 1), kn = top.get(k);
+    bool ok = kk != kKeyEmpty && u2f(kk | mask) <= r2scan && ((kk ^ kn) & ~mask) != 0u;
+    if (eps > 0.f)
+        ok = ok && !(u2f(top.a[0] & ~mask) < 3.0001f * eps * eps);
+    return ok;
 }
 
 // ---- epilogues over the k winners --------------------------------------------------------------

@@ -539,18 +539,30 @@ void emu_wlop_step(void* hp, const float* vj_sorted, void* hq, const float* wi_s
 // `done[row]` = 1 when the tile pass gave the final answer (the product sends the rest to the
 // retry queue).  stats: [0] tiles, [1] fallback tiles, [2] queries not final, [3] candidates,
 // [4] largest staged region, [5] queries not final because the emitted order was ambiguous.
-template <int KL, int S>
+static uint32_t g_emu_first_cap = 32;
+extern "C" void emu_tile_first_cap(uint32_t v) { g_emu_first_cap = v; }
+
+template <int KL, int S, bool batched>
 static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, uint32_t max_points,
                       float scan_cap, int nthreads, uint32_t* idx, float* d2, uint32_t* cnt,
                       float* nrm, float* ctr, float* means, uint8_t* done, uint64_t* stats)
 {
     GridView const& g   = ix->g;
-    TileParams const tp = make_tile_params<S>(g, level, max_points, scan_cap);
+    TileParams tp = make_tile_params<S>(g, level, max_points, scan_cap);
+    tp.first_cap  = g_emu_first_cap;
     std::vector<float4> P(max_points + kTilePad);
     std::vector<uint32_t> F(TileDims<S>::bins + 1), span_start(kTileSpans), span_off(kTileSpans + 1),
         partial(kTileScanLanes);
     TileGeom geom;
     TileSmem sm{P.data(), F.data(), span_start.data(), span_off.data(), partial.data(), &geom};
+    constexpr int segs = kTileCells * kTileCells * S;
+    std::vector<uint32_t> rowmask(TileDims<S>::nc), seg_off(segs + 1), gpos(max_points);
+    std::vector<uint16_t> qlist(max_points), clist((size_t)kTileCandCap * nthreads);
+    if (batched)
+    {
+        sm.rowmask = rowmask.data(), sm.seg_off = seg_off.data(), sm.gpos = gpos.data();
+        sm.qlist = qlist.data(), sm.cl = clist.data();
+    }
     int const sh = g.lcap - (level - kTileShift);
     auto tile_of = [&](uint32_t i) {
         QueryCell c = query_cell(g, ix->pts[i].x, ix->pts[i].y, ix->pts[i].z);
@@ -587,13 +599,38 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
             tile_phase_place<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
         for (int t = 0; t < nthreads; ++t)
             tile_phase_sort_bins<S>(sm, t, nthreads);
-        for (uint32_t t = s0; t < s1; ++t)
+        uint32_t nq = s1 - s0;
+        if (batched)
         {
-            float4 const q     = ix->pts[t];
+            for (int t = 0; t < nthreads; ++t)
+                tile_phase_rows<S>(sm, t, nthreads);
+            for (int t = 0; t < nthreads; ++t)
+                tile_phase_qlist<S>(sm, t, nthreads);
+            if (sm.seg_off[segs] != nq)
+                stats[1] += 1u << 20; // inconsistent query list: shows up as an absurd count
+        }
+        for (uint32_t i = 0; i < nq; ++i)
+        {
+            uint32_t const pos = batched ? sm.qlist[i] : 0u;
+            float4 const q     = batched ? sm.P[pos] : ix->pts[s0 + i];
             uint32_t const row = f2u(q.w);
+            if (batched && (sm.gpos[pos] < s0 || sm.gpos[pos] >= s1 ||
+                            f2u(ix->pts[sm.gpos[pos]].w) != row))
+                stats[1] += 1u << 20;
             TileList<KL> top;
             uint32_t cand = 0;
-            bool ok = tile_search<KL, S>(g, tp, geom, sm.P, sm.F, q.x, q.y, q.z, k, eps, top, &cand);
+            bool ok;
+            if constexpr (batched)
+            {
+                int const tid = (int)(i % (uint32_t)nthreads);
+                TileCursor cu = tile_cursor<S>(g, tp, geom, q.x, q.y, q.z);
+                tile_search_batched<KL, S>(tp, sm.P, sm.F, sm.rowmask, cu,
+                                           eps > 0.f ? pos : kNoSelf, sm.cl + tid, nthreads, q.x,
+                                           q.y, q.z, k, tp.first_cap, top, &cand);
+                ok = tile_is_final<KL>(top, k, tp.key_mask, cu.r2scan, eps);
+            }
+            else
+                ok = tile_search<KL, S>(g, tp, geom, sm.P, sm.F, q.x, q.y, q.z, k, eps, top, &cand);
             stats[3] += cand;
             if (ok && mode == 2)
             {
@@ -645,7 +682,7 @@ static int tile_list_size_for(uint32_t k)
     return 0;
 }
 
-extern "C" int emu_tile(void* h, uint32_t k, double eps, int mode, int sub, int level,
+extern "C" int emu_tile(void* h, uint32_t k, double eps, int mode, int sub, int alg, int level,
                         uint32_t max_points, double scan_cap, int nthreads, uint32_t* idx,
                         float* d2, uint32_t* cnt, float* nrm, float* ctr, float* means,
                         uint8_t* done, uint64_t* stats)
@@ -653,25 +690,38 @@ extern "C" int emu_tile(void* h, uint32_t k, double eps, int mode, int sub, int 
     EmuIndex* ix = static_cast<EmuIndex*>(h);
     if (level < kTileShift || level > ix->g.lfine)
         return -2;
-#define EMU_TILE(KLV)                                                                          \
+#define EMU_TILE(KLV, BATCHED)                                                                 \
     case KLV:                                                                                  \
         if (sub == 1)                                                                          \
-            tile_impl<KLV, 1>(ix, k, (float)eps, mode, level, max_points, (float)scan_cap,     \
-                              nthreads, idx, d2, cnt, nrm, ctr, means, done, stats);           \
+            tile_impl<KLV, 1, BATCHED>(ix, k, (float)eps, mode, level, max_points,             \
+                                       (float)scan_cap, nthreads, idx, d2, cnt, nrm, ctr,      \
+                                       means, done, stats);                                    \
         else                                                                                   \
-            tile_impl<KLV, 2>(ix, k, (float)eps, mode, level, max_points, (float)scan_cap,     \
-                              nthreads, idx, d2, cnt, nrm, ctr, means, done, stats);           \
+            tile_impl<KLV, 2, BATCHED>(ix, k, (float)eps, mode, level, max_points,             \
+                                       (float)scan_cap, nthreads, idx, d2, cnt, nrm, ctr,      \
+                                       means, done, stats);                                    \
         break;
+    if (alg == 2)
+    {
+        switch (k + 1 <= 8 ? 8 : (k + 1 <= 16 ? 16 : (k + 1 <= 32 ? 32 : 0)))
+        {
+            EMU_TILE(8, true)
+            EMU_TILE(16, true)
+            EMU_TILE(32, true)
+        default: return -5;
+        }
+        return 0;
+    }
     switch (tile_list_size_for(k))
     {
-        EMU_TILE(5)
-        EMU_TILE(9)
-        EMU_TILE(13)
-        EMU_TILE(16)
-        EMU_TILE(21)
-        EMU_TILE(25)
-        EMU_TILE(31)
-        EMU_TILE(33)
+        EMU_TILE(5, false)
+        EMU_TILE(9, false)
+        EMU_TILE(13, false)
+        EMU_TILE(16, false)
+        EMU_TILE(21, false)
+        EMU_TILE(25, false)
+        EMU_TILE(31, false)
+        EMU_TILE(33, false)
     default: return -5;
     }
 #undef EMU_TILE

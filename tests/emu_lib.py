@@ -57,7 +57,7 @@ class Emu:
                               C.c_int, _u32p, _f32p, _u32p, _u64p, _u32p]
         L.emu_normals.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_uint32, C.c_double,
                                   C.c_double, C.c_int, _f32p, _f32p, _f32p, _u32p]
-        L.emu_tile.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_int,
+        L.emu_tile.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_uint32, C.c_double, C.c_int, _u32p, _f32p, _u32p, _f32p, _f32p,
                                _f32p, _u8p, _u64p]
         L.emu_radius.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, C.c_float, _u32p, _u64p,
@@ -187,7 +187,8 @@ class EmuIndex:
         assert rc == 0
         return nrm, ctr, means, int(ties[0])
 
-    def tile(self, k, mode, level, sub=2, eps=1e-5, max_points=1024, scan_cap=1.0, nthreads=128):
+    def tile(self, k, mode, level, sub=2, eps=1e-5, max_points=1024, scan_cap=1.0, nthreads=128,
+             alg=2):
         """The tile path (tile_core.cuh) over the indexed points themselves; mode 0 = kNN rows,
         1 = mean distance, 2 = normals.  Returns a dict with the outputs, `done` (rows the tile
         pass finished; the product sends the rest to the retry queue) and `stats`."""
@@ -200,7 +201,7 @@ class EmuIndex:
         means = np.zeros(n, np.float32)
         done = np.zeros(n, np.uint8)
         st = np.zeros(6, np.uint64)
-        rc = self.L.emu_tile(self.h, k, eps, mode, sub, level, max_points, scan_cap, nthreads,
+        rc = self.L.emu_tile(self.h, k, eps, mode, sub, alg, level, max_points, scan_cap, nthreads,
                              _ptr(idx, _u32p), _ptr(d2, _f32p), _ptr(cnt, _u32p),
                              _ptr(nrm, _f32p), _ptr(ctr, _f32p), _ptr(means, _f32p),
                              _ptr(done, _u8p), _ptr(st, _u64p))

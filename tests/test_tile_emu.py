@@ -52,17 +52,17 @@ def test_tile_rows_are_exact(emu, cloud_set, name):
         ridx, rd2, rcnt, _ = ix.knn(None, k, exact_only=True)
         rnrm, rctr, rmean, _ = ix.normals(None, k, want_means=True, exact_only=True)
         for level in tile_levels(ix, k):
-            for sub in (1, 2):
-                r = ix.tile(k, 0, level, sub=sub, max_points=4096)
+            for sub, alg in ((1, 1), (2, 1), (1, 2), (2, 2)):
+                r = ix.tile(k, 0, level, sub=sub, alg=alg, max_points=4096)
                 d = r["done"]
                 assert np.array_equal(r["idx"][d], ridx[d]), (name, k, level, sub)
                 assert np.array_equal(r["d2"][d], rd2[d]), (name, k, level, sub)
                 assert np.all(r["cnt"][d] == k)
                 assert np.all(rcnt[d] == k)
-                m = ix.tile(k, 1, level, sub=sub, max_points=4096)
+                m = ix.tile(k, 1, level, sub=sub, alg=alg, max_points=4096)
                 assert np.array_equal(m["means"][m["done"]], rmean[m["done"]]), (name, k, level, sub)
                 if k >= 3:
-                    nr = ix.tile(k, 2, level, sub=sub, max_points=4096)
+                    nr = ix.tile(k, 2, level, sub=sub, alg=alg, max_points=4096)
                     dn = nr["done"]
                     cos = np.abs((nr["normals"][dn] * rnrm[dn]).sum(1))
                     # same neighbour set; moments taken about the query point in both
@@ -85,9 +85,18 @@ def test_tile_scan_cap_and_fallback(emu, cloud_set):
     level = ix.plan(k)["level"]
     ridx, rd2, _, _ = ix.knn(None, k, exact_only=True)
     for cap in (0.75, 1.0, 1.5, 2.0):
-        r = ix.tile(k, 0, level, sub=2, scan_cap=cap, max_points=4096)
+        for alg in (1, 2):
+            r = ix.tile(k, 0, level, sub=2, alg=alg, scan_cap=cap, max_points=4096)
+            d = r["done"]
+            assert np.array_equal(r["idx"][d], ridx[d]) and np.array_equal(r["d2"][d], rd2[d]), cap
+    # batched form: the size of the first round only changes the work, never the rows
+    for first in (8, 16, 64):
+        emu.L.emu_tile_first_cap(first)
+        r = ix.tile(k, 0, level, sub=2, alg=2, max_points=4096)
         d = r["done"]
-        assert np.array_equal(r["idx"][d], ridx[d]) and np.array_equal(r["d2"][d], rd2[d]), cap
+        assert d.mean() > 0.99
+        assert np.array_equal(r["idx"][d], ridx[d]) and np.array_equal(r["d2"][d], rd2[d]), first
+    emu.L.emu_tile_first_cap(32)
     # a region that does not fit the staging capacity: the whole tile is handed on
     r = ix.tile(k, 0, level, sub=2, max_points=128)
     assert r["stats"]["fallback_tiles"] > 0

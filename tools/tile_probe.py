@@ -32,8 +32,15 @@ def main():
     n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 15
     cloud = sys.argv[3] if len(sys.argv) > 3 else "noisy_plane"
-    variants = [dict(tile=0), dict(tile=1, tile_sub=2, tile_cap=1.0), dict(tile=1, tile_sub=1, tile_cap=1.0),
-                dict(tile=1, tile_sub=2, tile_cap=1.25), dict(tile=1, tile_sub=2, tile_cap=1.5)]
+    variants = [dict(tile=0),
+                dict(tile=1, tile_alg=1, tile_sub=2, tile_cap=1.0),
+                dict(tile=1, tile_alg=2, tile_sub=2, tile_cap=1.0, tile_first_cap=32),
+                dict(tile=1, tile_alg=2, tile_sub=2, tile_cap=1.0, tile_first_cap=64),
+                dict(tile=1, tile_alg=2, tile_sub=2, tile_cap=1.0, tile_first_cap=24),
+                dict(tile=1, tile_alg=2, tile_sub=1, tile_cap=1.0, tile_first_cap=32),
+                dict(tile=1, tile_alg=2, tile_sub=2, tile_cap=1.25, tile_first_cap=32)]
+    if os.environ.get("PCPX_PROBE_VARIANTS"):
+        variants = [variants[0]] + json.loads(os.environ["PCPX_PROBE_VARIANTS"])
     xyz = getattr(pcpx.synth, cloud)(n)
     d_xyz = torch.from_numpy(xyz).cuda()
     d_nrm = torch.empty((n, 3), dtype=torch.float32, device="cuda")
