@@ -7,6 +7,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PCPX_LIB", os.path.join(HERE, "lib", "libpcpx.so"))  # PCPX_LIB: experimental builds
+if os.environ.get("PCPX_LIB"):  # an experimental build next to the product (build.py --out=...)
+    LIB_PATH = os.environ["PCPX_LIB"]
 NO_NEIGHBOUR = 0xFFFFFFFF
 
 

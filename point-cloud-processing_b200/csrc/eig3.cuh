@@ -84,4 +84,79 @@ PCPX_HD void smallest_eigenvector(Sym3 m, float& nx, float& ny, float& nz, float
     }
 }
 
+// Closed form of the same result for the fused kernels (the Jacobi sweeps above cost ~1000
+// instructions per query and 300 of code): the smallest eigenvalue of the scaled matrix by the
+// trigonometric solution of the characteristic cubic, polished by two Newton steps taken from
+// just left of it (p(l) = l^3 - c2 l^2 + c1 l - c0 is negative, increasing and concave left of
+// its smallest root, so the iterates rise monotonically to it), then the eigenvector as the
+// largest cross product of two rows of (A - l0 I).  An error d in l0 tilts the vector by
+// ~ d / (l1 - l0); with d ~ 1e-6 (fp32 cancellation in the determinant of the scaled matrix) that
+// is far inside the 1e-4 |cos| tolerance wherever the normal is defined at all (relative
+// eigengap > 1e-3).  A (near-)double smallest eigenvalue makes every cross product vanish; such
+// matrices, and anything non-finite, take the Jacobi path.
+PCPX_HD void smallest_eigenvector_fast(Sym3 m, float& nx, float& ny, float& nz)
+{
+    float scale = fmaxf(fmaxf(fabsf(m.xx), fabsf(m.yy)), fabsf(m.zz));
+    scale       = fmaxf(scale, fmaxf(fmaxf(fabsf(m.xy), fabsf(m.xz)), fabsf(m.yz)));
+    if (!(scale > 0.f) || !(scale < INFINITY))
+    {
+        nx = 0.f, ny = 0.f, nz = 1.f;
+        return;
+    }
+    float const inv = 1.f / scale;
+    float const a00 = m.xx * inv, a01 = m.xy * inv, a02 = m.xz * inv;
+    float const a11 = m.yy * inv, a12 = m.yz * inv, a22 = m.zz * inv;
+    float const c2 = a00 + a11 + a22;
+    float const c1 = (a00 * a11 - a01 * a01) + (a00 * a22 - a02 * a02) + (a11 * a22 - a12 * a12);
+    float const c0 = a00 * (a11 * a22 - a12 * a12) - a01 * (a01 * a22 - a12 * a02) +
+                     a02 * (a01 * a12 - a11 * a02);
+    float const q   = c2 * (1.f / 3.f);
+    float const b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+    float const p2  = b00 * b00 + b11 * b11 + b22 * b22 + 2.f * (a01 * a01 + a02 * a02 + a12 * a12);
+    float const p   = sqrtf(p2 * (1.f / 6.f));
+    float const ip  = p > 1e-20f ? 1.f / p : 0.f;
+    float const detb = b00 * (b11 * b22 - a12 * a12) - a01 * (a01 * b22 - a12 * a02) +
+                       a02 * (a01 * a12 - b11 * a02);
+    float r = 0.5f * detb * ip * ip * ip;
+    r       = fminf(1.f, fmaxf(-1.f, r));
+    float const phi = acosf(r) * (1.f / 3.f);
+#ifdef __CUDA_ARCH__
+    float const cs = __cosf(phi + 2.0943951f);
+#else
+    float const cs = cosf(phi + 2.0943951f);
+#endif
+    float l = q + 2.f * p * cs - 2e-5f; // just left of the smallest root
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+    {
+        float const pl = ((l - c2) * l + c1) * l - c0;
+        float const dp = (3.f * l - 2.f * c2) * l + c1;
+        float const st = dp > 1e-12f ? pl / dp : 0.f;
+        l              = l - fminf(st, 0.f); // p <= 0 left of the root: steps only ever go right
+    }
+    float const r0x = a00 - l, r1y = a11 - l, r2z = a22 - l;
+    // rows r0 = (r0x, a01, a02), r1 = (a01, r1y, a12), r2 = (a02, a12, r2z)
+    float const ax = a01 * a12 - a02 * r1y, ay = a02 * a01 - r0x * a12, az = r0x * r1y - a01 * a01; // r0 x r1
+    float const bx = a01 * r2z - a02 * a12, by = a02 * a02 - r0x * r2z, bz = r0x * a12 - a01 * a02; // r0 x r2
+    float const cx = r1y * r2z - a12 * a12, cy = a12 * a02 - a01 * r2z, cz = a01 * a12 - r1y * a02; // r1 x r2
+    float const na = ax * ax + ay * ay + az * az, nb = bx * bx + by * by + bz * bz,
+                nc = cx * cx + cy * cy + cz * cz;
+    float ex = ax, ey = ay, ez = az, best = na;
+    if (nb > best)
+        ex = bx, ey = by, ez = bz, best = nb;
+    if (nc > best)
+        ex = cx, ey = cy, ez = cz, best = nc;
+    if (!(best > 1e-7f)) // (near-)double eigenvalue, or NaN
+    {
+        smallest_eigenvector(m, nx, ny, nz, nullptr);
+        return;
+    }
+#ifdef __CUDA_ARCH__
+    float const nrm = rsqrtf(best);
+#else
+    float const nrm = 1.f / sqrtf(best);
+#endif
+    nx = ex * nrm, ny = ey * nrm, nz = ez * nrm;
+}
+
 } // namespace pcpx

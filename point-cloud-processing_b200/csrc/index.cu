@@ -136,14 +136,18 @@ __device__ __forceinline__ int boundary_level(const GridView& g, const float4* p
 }
 
 __global__ void __launch_bounds__(kBlock) level_histogram_kernel(
-    GridView g, uint32_t* __restrict__ hist /* [kMaxLevel + 2] */)
+    GridView g, uint32_t* __restrict__ hist /* [kMaxLevel + 2] */, uint8_t* __restrict__ bnd)
 {
     __shared__ uint32_t sh[kMaxLevel + 2];
     if (threadIdx.x < kMaxLevel + 2)
         sh[threadIdx.x] = 0;
     __syncthreads();
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < g.n; i += gridDim.x * kBlock)
-        atomicAdd(&sh[boundary_level(g, g.pts, i)], 1u);
+    {
+        int const b = boundary_level(g, g.pts, i);
+        bnd[i]      = (uint8_t)b; // kept: the table build and the tile lists read it
+        atomicAdd(&sh[b], 1u);
+    }
     __syncthreads();
     if (threadIdx.x < kMaxLevel + 2 && sh[threadIdx.x])
         atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
@@ -176,12 +180,13 @@ __device__ __forceinline__ uint32_t find_slot(const HashSlot* table, uint32_t si
     }
 }
 
-__global__ void __launch_bounds__(kBlock) table_insert_kernel(GridView g, HashSlot* table)
+__global__ void __launch_bounds__(kBlock) table_insert_kernel(GridView g, HashSlot* table,
+                                                              const uint8_t* __restrict__ bnd)
 {
     uint32_t const i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= g.n)
         return;
-    int const b = boundary_level(g, g.pts, i);
+    int const b = bnd[i];
     if (b > g.lfine)
         return;
     float4 const p    = g.pts[i];
@@ -196,12 +201,13 @@ __global__ void __launch_bounds__(kBlock) table_insert_kernel(GridView g, HashSl
 }
 
 // The cell that point i - 1 belongs to ends where point i opens a new one.
-__global__ void __launch_bounds__(kBlock) table_count_kernel(GridView g, HashSlot* table)
+__global__ void __launch_bounds__(kBlock) table_count_kernel(GridView g, HashSlot* table,
+                                                             const uint8_t* __restrict__ bnd)
 {
     uint32_t const i = blockIdx.x * kBlock + threadIdx.x + 1; // 1 .. n
     if (i > g.n)
         return;
-    int const b = i == g.n ? 0 : boundary_level(g, g.pts, i);
+    int const b = i == g.n ? 0 : bnd[i];
     if (b > g.lfine)
         return;
     float4 const p    = g.pts[i - 1];
@@ -489,8 +495,9 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
         {
             DevBuf<uint32_t> d_lh(kMaxLevel + 2);
             PCPX_CUDA(cudaMemsetAsync(d_lh.get(), 0, d_lh.bytes(), ix.stream));
+            ix.bnd.alloc(g.n);
             level_histogram_kernel<<<std::min<uint32_t>(blocks_for(g.n, kBlock * 4), 148u * 8u),
-                                     kBlock, 0, ix.stream>>>(g, d_lh.get());
+                                     kBlock, 0, ix.stream>>>(g, d_lh.get(), ix.bnd.get());
             PCPX_CHECK_LAUNCH();
             ++launches;
             PCPX_CUDA(cudaMemcpyAsync(lh.data(), d_lh.get(), d_lh.bytes(), cudaMemcpyDeviceToHost,
@@ -539,9 +546,11 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
     PCPX_CUDA(cudaMemsetAsync(ix.table.get(), 0xFF, ix.table.bytes(), ix.stream));
     if (g.n)
     {
-        table_insert_kernel<<<blocks_for(g.n, kBlock), kBlock, 0, ix.stream>>>(g, ix.table.get());
+        table_insert_kernel<<<blocks_for(g.n, kBlock), kBlock, 0, ix.stream>>>(g, ix.table.get(),
+                                                                               ix.bnd.get());
         PCPX_CHECK_LAUNCH();
-        table_count_kernel<<<blocks_for(g.n, kBlock), kBlock, 0, ix.stream>>>(g, ix.table.get());
+        table_count_kernel<<<blocks_for(g.n, kBlock), kBlock, 0, ix.stream>>>(g, ix.table.get(),
+                                                                              ix.bnd.get());
         PCPX_CHECK_LAUNCH();
         launches += 2;
     }

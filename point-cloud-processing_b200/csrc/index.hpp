@@ -18,11 +18,13 @@ struct pcpx_index
     pcpx::GridView grid{}; // device pointers into the buffers below
     pcpx::DevBuf<float4> pts;          // n_input entries, Morton order; w = original index
     pcpx::DevBuf<pcpx::HashSlot> table; // all levels
+    pcpx::DevBuf<uint8_t> bnd;          // n_indexed entries: coarsest level at which sorted point i opens a new cell
     pcpx_timings timings{-1.f, -1.f, -1.f, -1.f, -1.f, 0u, 0u};
     std::mutex mtx; // one call at a time per index (calls serialise on `stream`)
     // tile list of one level (query.cu: ensure_tile_list), built on first use and kept:
     // tile_starts[i] = first sorted position of tile i, tile_starts[n_tiles] = n_indexed
     mutable pcpx::DevBuf<uint32_t> tile_starts, tile_count, tile_scratch;
+    mutable pcpx::DevBuf<uint64_t> tile_xyz; // tile coordinates (tile_core.cuh: tile_pack)
     mutable int tile_level         = -1;
     mutable uint32_t tile_capacity = 0;
 
@@ -31,7 +33,7 @@ struct pcpx_index
         if (stream)
             cudaStreamDestroy(stream);
     }
-    size_t device_bytes() const { return pts.bytes() + table.bytes(); }
+    size_t device_bytes() const { return pts.bytes() + table.bytes() + bnd.bytes(); }
 };
 
 namespace pcpx {

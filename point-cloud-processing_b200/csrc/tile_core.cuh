@@ -42,11 +42,10 @@ namespace pcpx {
 constexpr int kTileShift      = 2;                   // tile = cell at (main level - 2)
 constexpr int kTileCells      = 1 << kTileShift;     // main-level cells per tile and axis
 constexpr int kRegionCells    = kTileCells + 2;      // + one cell of halo on every side
-constexpr int kTileSpans      = 64;                  // 4^3 cells at (main level - 1) cover the region
-constexpr int kTileScanLanes  = 32;                  // threads that scan the bin counts
+constexpr int kRegionCellCount = kRegionCells * kRegionCells * kRegionCells; // 216
 constexpr uint32_t kKeyEmpty  = 0xFFFFFFFFu;
 constexpr uint32_t kTilePad   = 2;                   // readable entries behind the staged points
-constexpr int kTileCandCap    = 64;                  // candidates one query can list
+constexpr int kTileCandCap    = 32;                  // candidates one query lists per round
 constexpr uint32_t kNoSelf    = 0xFFFFFFFFu;
 
 template <int S>
@@ -71,6 +70,7 @@ struct TileParams
     float delta_cells;   // g.delta in cell units
     float scan_cap;      // largest scan radius, in units of h
     uint32_t first_cap;  // batched form: candidates listed before the ball is first shrunk
+    int threads;         // threads of the CTA
 };
 
 template <int S>
@@ -93,7 +93,8 @@ inline TileParams make_tile_params(const GridView& g, int level, uint32_t max_po
     tp.scan_cap      = scan_cap;
     tp.rows_b        = (int)ceilf(scan_cap * (float)S);
     tp.rows_c        = (int)ceilf(scan_cap);
-    tp.first_cap     = 32;
+    tp.first_cap     = (uint32_t)kTileCandCap;
+    tp.threads       = 96;
     return tp;
 }
 
@@ -102,8 +103,7 @@ struct TileGeom
 {
     int32_t r0[3];      // region origin in main-level cells along a, b, c (may be -1)
     int32_t ax[3];      // world axis (0 = x, 1 = y, 2 = z) of a, b, c
-    uint32_t n_spans;   // non-empty spans among the 64
-    uint32_t raw_total; // points in those spans (a superset of the region)
+    uint32_t n_occ;     // region cells that hold points
     uint32_t n_points;  // points of the region (staged)
     int32_t fallback;   // the region does not fit: every query of the tile goes to the retry queue
 };
@@ -113,9 +113,9 @@ struct TileSmem
 {
     float4* P;            // max_points + kTilePad, bin order
     uint32_t* F;          // bins + 1: start of every bin (F[bins] = n_points)
-    uint32_t* span_start; // kTileSpans
-    uint32_t* span_off;   // kTileSpans + 1 (prefix over the compacted spans)
-    uint32_t* partial;    // kTileScanLanes
+    uint32_t* cstart;     // kRegionCellCount: span of every region cell in the sorted array ...
+    uint32_t* ccount;     // kRegionCellCount: ... cell id = (z * 6 + y) * 6 + x, world axes
+    uint8_t* occ;         // kRegionCellCount: ids of the cells that hold points, ascending
     TileGeom* geom;
     // the batched form of the search (tile_list_candidates / tile_select)
     uint32_t* rowmask;    // nc words: bit ib of word ic = row (ic, ib) holds points
@@ -124,6 +124,15 @@ struct TileSmem
     uint16_t* cl;         // kTileCandCap x nthreads candidate positions, [j * nthreads + tid]
     uint32_t* gpos;       // max_points: position of every staged point in the sorted global array
 };
+
+// tile coordinates (cell coordinates at the tile level), 21 bits each
+PCPX_HD uint64_t tile_pack(uint32_t x, uint32_t y, uint32_t z)
+{
+    return (uint64_t)x | ((uint64_t)y << 21) | ((uint64_t)z << 42);
+}
+PCPX_HD uint32_t tile_x(uint64_t t) { return (uint32_t)t & 0x1FFFFFu; }
+PCPX_HD uint32_t tile_y(uint64_t t) { return (uint32_t)(t >> 21) & 0x1FFFFFu; }
+PCPX_HD uint32_t tile_z(uint64_t t) { return (uint32_t)(t >> 42) & 0x1FFFFFu; }
 
 PCPX_HD float axis_of(float x, float y, float z, int ax) { return ax == 0 ? x : (ax == 1 ? y : z); }
 PCPX_HD int32_t axis_of_i(int32_t x, int32_t y, int32_t z, int ax)
@@ -144,89 +153,88 @@ PCPX_HD uint32_t quantise_sub(float x, float o, float scale, int lcap)
     return (uint32_t)t;
 }
 
-PCPX_HD uint32_t tile_atomic_inc(uint32_t* p)
-{
-#ifdef __CUDA_ARCH__
-    return atomicAdd(p, 1u);
-#else
-    return (*p)++;
-#endif
-}
-
-// bin of a point in the tile's local grid, -1 when its cell lies outside the region
-template <int S>
-PCPX_HD int tile_bin(const GridView& g, const TileParams& tp, const TileGeom& tg, const float4& p)
-{
-    using D      = TileDims<S>;
-    int const sh = g.lcap - tp.level;
-    int const a = tg.ax[0], b = tg.ax[1], c = tg.ax[2];
-    uint32_t const ua =
-        quantise_sub<S>(axis_of(p.x, p.y, p.z, a), axis_of(g.ox, g.oy, g.oz, a), g.scale, g.lcap);
-    uint32_t const ub =
-        quantise_sub<S>(axis_of(p.x, p.y, p.z, b), axis_of(g.ox, g.oy, g.oz, b), g.scale, g.lcap);
-    uint32_t const uc =
-        quantise(axis_of(p.x, p.y, p.z, c), axis_of(g.ox, g.oy, g.oz, c), g.scale, g.lcap);
-    int const ia = (int)(ua >> sh) - tg.r0[0] * S;
-    int const ib = (int)(ub >> sh) - tg.r0[1] * S;
-    int const ic = (int)(uc >> sh) - tg.r0[2];
-    if ((unsigned)ia >= (unsigned)D::na || (unsigned)ib >= (unsigned)D::nb ||
-        (unsigned)ic >= (unsigned)D::nc)
-        return -1;
-    return (ic * D::nb + ib) * D::na + ia;
-}
-
 // ---- staging phases (a barrier between consecutive phases) -----------------------------------
+//
+//   lookup  one table lookup per region cell (216, main level): the spans of exactly the points a
+//           tile query can need;
+//   plan    the occupied cells compacted (device: ballots by the first warp), the thin axis chosen,
+//           the tile handed on when its region does not fit;
+//   count   one thread per occupied cell: how many of its points fall into each of its S x S
+//           sub-bins (every bin belongs to exactly one cell: plain stores, no atomics);
+//   scan    inclusive scan of the bin counts: F[i] = start of bin i;
+//   place   the same thread copies its cell's points to their bins in the order of the sorted
+//           array — the staged order is a function of the input alone.
 
-// phase 0: clear the bin table; the first 64 threads look up the covering cells
+// phase 0: clear the bin table, look up the region cells
 template <int S>
 PCPX_HD void tile_phase_lookup(const GridView& g, const TileParams& tp, const TileSmem& sm,
-                               uint32_t tile_first, int tid, int nthreads)
+                               uint64_t tile_xyz, int tid, int nthreads)
 {
     for (int i = tid; i <= TileDims<S>::bins; i += nthreads)
         sm.F[i] = 0u;
     if (sm.rowmask && tid < TileDims<S>::nc)
         sm.rowmask[tid] = 0u;
-    if (tid < kTileSpans)
+    int const last = (1 << tp.level) - 1;
+    int const x0 = kTileCells * (int)tile_x(tile_xyz) - 1, y0 = kTileCells * (int)tile_y(tile_xyz) - 1,
+              z0 = kTileCells * (int)tile_z(tile_xyz) - 1;
+    for (int c = tid; c < kRegionCellCount; c += nthreads)
     {
-        float4 const f     = load_pt(g.pts + tile_first);
-        QueryCell const qc = query_cell(g, f.x, f.y, f.z);
-        int const l1       = tp.level - 1; // level of the covering cells
-        int const sh       = g.lcap - (tp.level - kTileShift);
-        // covering cell = 2 * tile - 1 + (0..3) per axis
-        int const cx = 2 * (int)(qc.ux >> sh) - 1 + (tid & 3);
-        int const cy = 2 * (int)(qc.uy >> sh) - 1 + ((tid >> 2) & 3);
-        int const cz = 2 * (int)(qc.uz >> sh) - 1 + (tid >> 4);
-        int const last = (1 << l1) - 1;
+        int const cx = x0 + c % kRegionCells, cy = y0 + (c / kRegionCells) % kRegionCells,
+                  cz = z0 + c / (kRegionCells * kRegionCells);
         uint32_t start = 0, count = 0;
         if (cx >= 0 && cy >= 0 && cz >= 0 && cx <= last && cy <= last && cz <= last)
-            if (!find_cell(g, cell_key(l1, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz), start, count))
+            if (!find_cell(g, cell_key(tp.level, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz), start, count))
                 count = 0;
-        sm.span_start[tid] = start;
-        sm.span_off[tid]   = count; // counts for now; tile_phase_plan turns them into a prefix
+        sm.cstart[c] = start;
+        sm.ccount[c] = count;
     }
 }
 
-// phase 1 (one thread): compact the non-empty spans, prefix their sizes, choose the axes
+// phase 1: compact the occupied cells, choose the axes
 template <int S>
-PCPX_HD void tile_phase_plan(const GridView& g, const TileParams& tp, const TileSmem& sm,
-                             uint32_t tile_first)
+PCPX_HD void tile_phase_plan(const TileParams& tp, const TileSmem& sm, uint64_t tile_xyz, int tid)
 {
-    uint32_t occ[3] = {0u, 0u, 0u}; // bit i of occ[axis]: some covering cell at coordinate i holds points
+    uint32_t occ[3] = {0u, 0u, 0u}; // bit i of occ[axis]: some cell at coordinate i holds points
     uint32_t n = 0, total = 0;
-    for (int s = 0; s < kTileSpans; ++s)
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 800
+    if (tid >= 32)
+        return;
+    for (int c0 = 0; c0 < kRegionCellCount; c0 += 32)
     {
-        uint32_t const cnt = sm.span_off[s], st = sm.span_start[s];
+        int const c        = c0 + tid;
+        uint32_t const cnt = c < kRegionCellCount ? sm.ccount[c] : 0u;
+        uint32_t const m   = __ballot_sync(0xFFFFFFFFu, cnt != 0u);
+        if (cnt)
+            sm.occ[n + (uint32_t)__popc(m & ((1u << tid) - 1u))] = (uint8_t)c;
+        n += (uint32_t)__popc(m);
+        total += __reduce_add_sync(0xFFFFFFFFu, cnt);
+        occ[0] |= __reduce_or_sync(0xFFFFFFFFu, cnt ? 1u << (c % kRegionCells) : 0u);
+        occ[1] |= __reduce_or_sync(0xFFFFFFFFu, cnt ? 1u << ((c / kRegionCells) % kRegionCells) : 0u);
+        occ[2] |= __reduce_or_sync(0xFFFFFFFFu, cnt ? 1u << (c / (kRegionCells * kRegionCells)) : 0u);
+    }
+    if (tid != 0)
+        return;
+#else
+    if (tid != 0)
+        return;
+    for (int c = 0; c < kRegionCellCount; ++c)
+    {
+        uint32_t const cnt = sm.ccount[c];
         if (cnt == 0)
             continue;
-        occ[0] |= 1u << (s & 3), occ[1] |= 1u << ((s >> 2) & 3), occ[2] |= 1u << (s >> 4);
-        sm.span_start[n] = st;
-        sm.span_off[n]   = total;
+        occ[0] |= 1u << (c % kRegionCells), occ[1] |= 1u << ((c / kRegionCells) % kRegionCells);
+        occ[2] |= 1u << (c / (kRegionCells * kRegionCells));
+        sm.occ[n++] = (uint8_t)c;
         total += cnt;
-        ++n;
     }
-    sm.span_off[n] = total;
-    auto pop4 = [](uint32_t m) { return (m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u); };
-    uint32_t const ex = pop4(occ[0]), ey = pop4(occ[1]), ez = pop4(occ[2]);
+#endif
+    auto pop = [](uint32_t m) {
+        uint32_t r = 0;
+        for (int i = 0; i < kRegionCells; ++i)
+            r += (m >> i) & 1u;
+        return r;
+    };
+    uint32_t const ex = pop(occ[0]), ey = pop(occ[1]), ez = pop(occ[2]);
     // c = the thinnest axis (ties: z, then y), a = the widest of the other two (ties: the lower)
     int c = 2;
     if (ey < ez)
@@ -242,137 +250,156 @@ PCPX_HD void tile_phase_plan(const GridView& g, const TileParams& tp, const Tile
     }
     TileGeom& tg = *sm.geom;
     tg.ax[0] = a, tg.ax[1] = b, tg.ax[2] = c;
-    float4 const f     = load_pt(g.pts + tile_first);
-    QueryCell const qc = query_cell(g, f.x, f.y, f.z);
-    int const sh       = g.lcap - (tp.level - kTileShift);
-    int32_t const tx = (int32_t)(qc.ux >> sh), ty = (int32_t)(qc.uy >> sh), tz = (int32_t)(qc.uz >> sh);
+    int32_t const tx = (int32_t)tile_x(tile_xyz), ty = (int32_t)tile_y(tile_xyz),
+                  tz = (int32_t)tile_z(tile_xyz);
     tg.r0[0] = kTileCells * axis_of_i(tx, ty, tz, a) - 1;
     tg.r0[1] = kTileCells * axis_of_i(tx, ty, tz, b) - 1;
     tg.r0[2] = kTileCells * axis_of_i(tx, ty, tz, c) - 1;
-    tg.n_spans   = n;
-    tg.raw_total = total;
-    tg.n_points  = 0;
-    tg.fallback  = 0;
+    tg.n_occ    = n;
+    tg.n_points = total;
+    tg.fallback = total > tp.max_points ? 1 : 0;
 }
 
-// Visits the points of the covering spans: thread `tid` takes raw indices tid, tid + nthreads, ...
-// (its span pointer only moves forward).
-template <class F>
-PCPX_HD void tile_for_raw(const GridView& g, const TileSmem& sm, int tid, int nthreads, F&& f)
+// What a thread needs to bin the points of one cell: the first bin of the cell and, for S = 2,
+// which half of the cell a point lies in along a and b.
+template <int S>
+struct TileCellBinner
 {
-    uint32_t const total = sm.geom->raw_total;
-    uint32_t sp          = 0;
-    for (uint32_t i = (uint32_t)tid; i < total; i += (uint32_t)nthreads)
-    {
-        while (i >= sm.span_off[sp + 1])
-            ++sp;
-        uint32_t const gi = sm.span_start[sp] + (i - sm.span_off[sp]);
-        f(load_pt(g.pts + gi), gi);
-    }
-}
+    float oa, ob, scale_s;
+    uint32_t top;
+    int sh, A, B;
+    int wx, wy, wz; // weight of a cell's world coordinates in its first bin's index
 
-// phase 2: bin counts (F[bin + 1] += 1)
+    PCPX_HD TileCellBinner(const GridView& g, const TileParams& tp, const TileGeom& tg)
+    {
+        using D = TileDims<S>;
+        A = tg.ax[0], B = tg.ax[1];
+        oa = axis_of(g.ox, g.oy, g.oz, A), ob = axis_of(g.ox, g.oy, g.oz, B);
+        scale_s = g.scale * (float)S;
+        top     = ((1u << g.lcap) * (uint32_t)S) - 1u;
+        sh      = g.lcap - tp.level;
+        auto weight = [&](int axis) { return A == axis ? S : (B == axis ? S * D::na : D::na * D::nb); };
+        wx = weight(0), wy = weight(1), wz = weight(2);
+    }
+    PCPX_HD int first_bin(int cell) const
+    {
+        return (cell % kRegionCells) * wx + ((cell / kRegionCells) % kRegionCells) * wy +
+               (cell / (kRegionCells * kRegionCells)) * wz;
+    }
+    PCPX_HD uint32_t half(float x, float o) const // low bit of quantise_sub<2>(x) >> sh
+    {
+        float t = (x - o) * scale_s;
+        t       = t > 0.f ? t : 0.f;
+        uint32_t u = (uint32_t)t;
+        u          = u < top ? u : top;
+        return (u >> sh) & 1u;
+    }
+    // 0 .. 3: sub-bin of a point inside its cell (a half + 2 * b half); 0 when S == 1
+    PCPX_HD uint32_t sub(const float4& p) const
+    {
+        if (S == 1)
+            return 0u;
+        return half(axis_of(p.x, p.y, p.z, A), oa) + 2u * half(axis_of(p.x, p.y, p.z, B), ob);
+    }
+};
+
+// phase 2: bin counts (F[bin + 1] = count), one thread per occupied cell
 template <int S>
 PCPX_HD void tile_phase_count(const GridView& g, const TileParams& tp, const TileSmem& sm, int tid,
                               int nthreads)
 {
     TileGeom const tg = *sm.geom;
-    tile_for_raw(g, sm, tid, nthreads, [&](float4 const& p, uint32_t) {
-        int const bin = tile_bin<S>(g, tp, tg, p);
-        if (bin >= 0)
-            tile_atomic_inc(sm.F + bin + 1);
-    });
+    TileCellBinner<S> const binner(g, tp, tg);
+    for (uint32_t j = (uint32_t)tid; j < tg.n_occ; j += (uint32_t)nthreads)
+    {
+        int const cell       = sm.occ[j];
+        uint32_t const start = sm.cstart[cell], count = sm.ccount[cell];
+        int const bin        = binner.first_bin(cell);
+        if (S == 1)
+        {
+            sm.F[bin + 1] = count;
+            continue;
+        }
+        uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        for (uint32_t i = 0; i < count; ++i)
+        {
+            uint32_t const s = binner.sub(load_pt(g.pts + start + i));
+            n0 += s == 0u, n1 += s == 1u, n2 += s == 2u, n3 += s == 3u;
+        }
+        sm.F[bin + 1] = n0, sm.F[bin + 2] = n1;
+        sm.F[bin + TileDims<S>::na + 1] = n2, sm.F[bin + TileDims<S>::na + 2] = n3;
+    }
 }
 
-// phase 3a / 3b / 3c: exclusive scan of the counts, kTileScanLanes chunks
+// phase 3: inclusive scan of the counts in place, after which F[i] is the start of bin i
+// (F[0] = 0, F[bins] = the number of staged points).  Device: the first warp, 27 bins per lane.
 template <int S>
-PCPX_HD void tile_phase_scan_a(const TileSmem& sm, int tid)
+PCPX_HD void tile_phase_scan(const TileSmem& sm, int tid)
 {
-    constexpr int bins = TileDims<S>::bins, chunk = (bins + kTileScanLanes - 1) / kTileScanLanes;
-    if (tid >= kTileScanLanes)
+    constexpr int bins = TileDims<S>::bins;
+#ifdef __CUDA_ARCH__
+    constexpr int chunk = (bins + 31) / 32;
+    if (tid >= 32)
         return;
     uint32_t s = 0;
     for (int i = tid * chunk; i < (tid + 1) * chunk && i < bins; ++i)
         s += sm.F[i + 1];
-    sm.partial[tid] = s;
-}
-PCPX_HD void tile_phase_scan_b(const TileParams& tp, const TileSmem& sm)
-{
-    uint32_t run = 0;
-    for (int i = 0; i < kTileScanLanes; ++i)
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
     {
-        uint32_t const v = sm.partial[i];
-        sm.partial[i]    = run;
-        run += v;
+        uint32_t const up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (tid >= o)
+            incl += up;
     }
-    sm.geom->n_points = run;
-    if (run > tp.max_points)
-        sm.geom->fallback = 1;
-}
-template <int S>
-PCPX_HD void tile_phase_scan_c(const TileSmem& sm, int tid)
-{
-    constexpr int bins = TileDims<S>::bins, chunk = (bins + kTileScanLanes - 1) / kTileScanLanes;
-    if (tid >= kTileScanLanes)
-        return;
-    uint32_t run = sm.partial[tid];
+    uint32_t run = incl - s;
     for (int i = tid * chunk; i < (tid + 1) * chunk && i < bins; ++i)
     {
-        uint32_t const v = sm.F[i + 1];
-        sm.F[i + 1]      = run; // start of bin i, turned into its end (= start of bin i + 1) by the placement
-        run += v;
+        run += sm.F[i + 1];
+        sm.F[i + 1] = run;
     }
+#else
+    if (tid != 0)
+        return;
+    uint32_t run = 0;
+    for (int i = 0; i < bins; ++i)
+    {
+        run += sm.F[i + 1];
+        sm.F[i + 1] = run;
+    }
+#endif
 }
 
-// phase 4: placement.  F[bin + 1] walks from the start of the bin to its end, after which
-// F[i] is the start of bin i for every i (F[0] = 0 was never touched).
+// phase 4: placement, again one thread per occupied cell, its points in the order of the sorted
+// array
 template <int S>
 PCPX_HD void tile_phase_place(const GridView& g, const TileParams& tp, const TileSmem& sm, int tid,
                               int nthreads)
 {
     TileGeom const tg = *sm.geom;
-    tile_for_raw(g, sm, tid, nthreads, [&](float4 const& p, uint32_t gi) {
-        int const bin = tile_bin<S>(g, tp, tg, p);
-        if (bin >= 0)
-        {
-            uint32_t const pos = tile_atomic_inc(sm.F + bin + 1);
-            sm.P[pos]          = p;
-            if (sm.gpos)
-                sm.gpos[pos] = gi;
-        }
-    });
-    if (tid == 0)
-        for (uint32_t j = 0; j < kTilePad; ++j)
-            sm.P[tg.n_points + j] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-// phase 5: the placement order inside a bin depends on the order the atomics were served in;
-// sorting every bin by original index makes the staged order — and with it every result bit —
-// a function of the input alone.
-template <int S>
-PCPX_HD void tile_phase_sort_bins(const TileSmem& sm, int tid, int nthreads)
-{
-    for (int bin = tid; bin < TileDims<S>::bins; bin += nthreads)
+    TileCellBinner<S> const binner(g, tp, tg);
+    for (uint32_t j = (uint32_t)tid; j < tg.n_occ; j += (uint32_t)nthreads)
     {
-        uint32_t const lo = sm.F[bin], hi = sm.F[bin + 1];
-        for (uint32_t i = lo + 1; i < hi; ++i)
+        int const cell       = sm.occ[j];
+        uint32_t const start = sm.cstart[cell], count = sm.ccount[cell];
+        int const bin        = binner.first_bin(cell);
+        uint32_t w0 = sm.F[bin], w1 = 0, w2 = 0, w3 = 0;
+        if (S == 2)
+            w1 = sm.F[bin + 1], w2 = sm.F[bin + TileDims<S>::na], w3 = sm.F[bin + TileDims<S>::na + 1];
+        for (uint32_t i = 0; i < count; ++i)
         {
-            float4 const v    = sm.P[i];
-            uint32_t const gv = sm.gpos ? sm.gpos[i] : 0u;
-            uint32_t const w  = f2u(v.w);
-            uint32_t j        = i;
-            while (j > lo && f2u(sm.P[j - 1].w) > w)
-            {
-                sm.P[j] = sm.P[j - 1];
-                if (sm.gpos)
-                    sm.gpos[j] = sm.gpos[j - 1];
-                --j;
-            }
-            sm.P[j] = v;
+            float4 const p   = load_pt(g.pts + start + i);
+            uint32_t const s = binner.sub(p);
+            uint32_t const pos = s == 0u ? w0 : (s == 1u ? w1 : (s == 2u ? w2 : w3));
+            w0 += s == 0u, w1 += s == 1u, w2 += s == 2u, w3 += s == 3u;
+            sm.P[pos] = p;
             if (sm.gpos)
-                sm.gpos[j] = gv;
+                sm.gpos[pos] = start + i;
         }
     }
+    if (tid == 0)
+        for (uint32_t j = 0; j < kTilePad; ++j)
+            sm.P[tg.n_points + j] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
 }
 
 // ---- the per-query search --------------------------------------------------------------------
@@ -687,17 +714,24 @@ PCPX_HD uint32_t tile_list_candidates(const TileParams& tp, const uint32_t* F,
             uint32_t const hi = F[base + ahi + 1];
             uint32_t p        = F[base + alo];
             p                 = pr > p ? pr : p;
-            for (; p < hi; ++p)
-                if (p != self)
-                {
-                    if (cnt == cap)
-                    {
-                        cu.p_resume = p;
-                        return cnt;
-                    }
-                    cl[cnt * (uint32_t)stride] = (uint16_t)p;
-                    ++cnt;
-                }
+            if (p >= hi)
+                continue;
+            uint32_t const n = hi - p, room = cap - cnt;
+            uint32_t take    = n < room ? n : room;
+            for (uint32_t i = 0; i < take; ++i)
+                cl[(cnt + i) * (uint32_t)stride] = (uint16_t)(p + i);
+            uint32_t const next = p + take;
+            if (self - p < take) // the query itself: the last entry listed now takes its slot
+            {
+                cl[(cnt + (self - p)) * (uint32_t)stride] = (uint16_t)(next - 1u);
+                take -= 1u;
+            }
+            cnt += take;
+            if (next < hi) // the list is full
+            {
+                cu.p_resume = next;
+                return cnt;
+            }
         }
     }
     cu.done = true;
@@ -741,7 +775,8 @@ PCPX_HD void tile_merge8(uint32_t* a, const uint32_t* b)
                 PCPX_CE(a[i], a[i + s]);
 }
 
-// Q2.  `top` must be reset by the caller.
+// Q2.  `top` must be reset by the caller; the list is padded to a multiple of 8 entries with the
+// position of the staged array's pad entry (coordinates +inf: its key sorts behind every point).
 template <int KL>
 PCPX_HD void tile_select(const float4* P, const uint16_t* cl, int stride, uint32_t count,
                          float qx, float qy, float qz, uint32_t mask, TileList<KL>& top)
@@ -752,11 +787,10 @@ PCPX_HD void tile_select(const float4* P, const uint16_t* cl, int stride, uint32
 #pragma unroll
         for (int i = 0; i < 8; ++i)
         {
-            uint32_t const j   = j0 + (uint32_t)i;
-            uint32_t const pos = cl[(j < count ? j : 0u) * (uint32_t)stride];
+            uint32_t const pos = cl[(j0 + (uint32_t)i) * (uint32_t)stride];
             float4 const c     = P[pos];
             float const d2 = sqdist_x(fsub_x(c.x, qx), fsub_x(c.y, qy), fsub_x(c.z, qz));
-            b[i]           = j < count ? ((f2u(d2) & ~mask) | pos) : kKeyEmpty;
+            b[i]           = (f2u(d2) & ~mask) | pos;
         }
         tile_sort8(b);
         tile_merge8<KL>(top.a, b);
@@ -766,20 +800,23 @@ PCPX_HD void tile_select(const float4* P, const uint16_t* cl, int stride, uint32
 // The whole search of one query: rounds of (list up to a cap, select), the ball shrinking to the
 // k-th key's bucket between rounds.  The first round is short (the rows nearest to the query), so
 // that the farther rows are already listed against a tight ball.
-template <int KL, int S>
+template <int KL, int S, int KS>
 PCPX_HD void tile_search_batched(const TileParams& tp, const float4* P, const uint32_t* F,
                                  const uint32_t* rowmask, TileCursor& cu, uint32_t self,
                                  uint16_t* cl, int stride, float qx, float qy, float qz,
-                                 uint32_t k, uint32_t first_cap, TileList<KL>& top,
-                                 uint32_t* n_cand)
+                                 uint32_t k, uint32_t first_cap, uint32_t pad_pos,
+                                 TileList<KL>& top, uint32_t* n_cand)
 {
     top.reset();
     uint32_t cap = first_cap, total = 0;
     do
     {
         uint32_t const cnt = tile_list_candidates<S>(tp, F, rowmask, cu, self, cl, stride, cap);
+        for (uint32_t j = cnt; j < ((cnt + 7u) & ~7u); ++j)
+            cl[j * (uint32_t)stride] = (uint16_t)pad_pos;
         tile_select<KL>(P, cl, stride, cnt, qx, qy, qz, tp.key_mask, top);
-        cu.r2 = fminf(cu.r2, u2f(top.get(k - 1) | tp.key_mask)); // NaN while the list is not full
+        // (NaN while the list is not full: fminf keeps r2)
+        cu.r2 = fminf(cu.r2, u2f((KS > 0 ? top.a[KS > 0 ? KS - 1 : 0] : top.get(k - 1)) | tp.key_mask));
         cap   = (uint32_t)kTileCandCap;
         total += cnt;
     } while (!cu.done);
@@ -790,11 +827,18 @@ PCPX_HD void tile_search_batched(const TileParams& tp, const float4* P, const ui
 // final: k eligible points found, the k-th inside the scanned ball, the (k+1)-th different from
 // it in the kept bits, and no foreign point inside the exclusion box (its key would be the
 // smallest; the query's own position was never listed)
-template <int KL>
+template <int KL, int KS>
 PCPX_HD bool tile_is_final(const TileList<KL>& top, uint32_t k, uint32_t mask, float r2scan,
                            float eps)
 {
-    uint32_t const kk = top.get(k - 1), kn = top.get(k);
+    uint32_t kk = top.a[KS > 0 ? KS - 1 : 0], kn = top.a[KS > 0 ? KS : 0];
+    if (KS == 0)
+    {
+#pragma unroll
+        for (int i = 0; i + 1 < KL; ++i)
+            if (k == (uint32_t)i + 1u)
+                kk = top.a[i], kn = top.a[i + 1];
+    }
     bool ok = kk != kKeyEmpty && u2f(kk | mask) <= r2scan && ((kk ^ kn) & ~mask) != 0u;
     if (eps > 0.f)
         ok = ok && !(u2f(top.a[0] & ~mask) < 3.0001f * eps * eps);
@@ -862,6 +906,72 @@ PCPX_HD bool tile_emit_sorted(const float4* P, const TileList<KL>& top, uint32_t
             if (!before_held)
                 hd = d2, hid = id;
         }
+    ok = ok && !(hd < ld || (hd == ld && hid < lid && slot > 0));
+    f(slot, hd, hid);
+    return ok;
+}
+
+// The k winners' staged positions, out of the register list into the thread's column of `cl`, so
+// that the epilogues are rolled loops instead of KL unrolled copies of their body.
+template <int KL>
+PCPX_HD void tile_store_winners(const TileList<KL>& top, uint32_t mask, uint16_t* cl, int stride)
+{
+#pragma unroll
+    for (int j = 0; j < KL; ++j)
+        cl[j * stride] = (uint16_t)(top.a[j] & mask);
+}
+
+PCPX_HD void tile_normal_rolled(const float4* P, const uint16_t* cl, int stride, uint32_t k,
+                                float qx, float qy, float qz, float* n3, float* c3)
+{
+    float s1x = 0.f, s1y = 0.f, s1z = 0.f;
+    Sym3 s2{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (uint32_t j = 0; j < k; ++j)
+    {
+        float4 const c = P[cl[j * (uint32_t)stride]];
+        float const dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
+        s1x += dx, s1y += dy, s1z += dz;
+        s2.xx += dx * dx, s2.xy += dx * dy, s2.xz += dx * dz;
+        s2.yy += dy * dy, s2.yz += dy * dz, s2.zz += dz * dz;
+    }
+    float const inv = 1.f / (float)k;
+    float const mx = s1x * inv, my = s1y * inv, mz = s1z * inv;
+    Sym3 m;
+    m.xx = s2.xx - s1x * mx, m.xy = s2.xy - s1x * my, m.xz = s2.xz - s1x * mz;
+    m.yy = s2.yy - s1y * my, m.yz = s2.yz - s1y * mz, m.zz = s2.zz - s1z * mz;
+    smallest_eigenvector_fast(m, n3[0], n3[1], n3[2]);
+    c3[0] = qx + mx, c3[1] = qy + my, c3[2] = qz + mz;
+}
+
+// tile_emit_sorted over the stored positions
+template <class F>
+PCPX_HD bool tile_emit_sorted_rolled(const float4* P, const uint16_t* cl, int stride, uint32_t k,
+                                     float qx, float qy, float qz, F&& f)
+{
+    float hd = 0.f, ld = -1.f; // held back / last emitted
+    uint32_t hid = 0, lid = 0, slot = 0;
+    bool ok = true;
+#pragma unroll 1
+    for (uint32_t j = 0; j < k; ++j)
+    {
+        float4 const c    = P[cl[j * (uint32_t)stride]];
+        float const d2    = sqdist_x(fsub_x(c.x, qx), fsub_x(c.y, qy), fsub_x(c.z, qz));
+        uint32_t const id = f2u(c.w);
+        if (j == 0)
+        {
+            hd = d2, hid = id;
+            continue;
+        }
+        bool const before_held = d2 < hd || (d2 == hd && id < hid);
+        float const ed         = before_held ? d2 : hd;
+        uint32_t const eid     = before_held ? id : hid;
+        ok = ok && !(ed < ld || (ed == ld && eid < lid && slot > 0));
+        f(slot++, ed, eid);
+        ld = ed, lid = eid;
+        if (!before_held)
+            hd = d2, hid = id;
+    }
     ok = ok && !(hd < ld || (hd == ld && hid < lid && slot > 0));
     f(slot, hd, hid);
     return ok;

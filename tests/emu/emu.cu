@@ -461,6 +461,16 @@ int emu_density_keep(void* h, float r, uint32_t threshold, uint8_t* keep)
     return 0;
 }
 
+void emu_smallest_eigenvector_fast(const float* cov6, size_t n, float* n3)
+{
+    for (size_t i = 0; i < n; ++i)
+    {
+        const float* c = cov6 + 6 * i;
+        Sym3 m{c[0], c[1], c[2], c[3], c[4], c[5]};
+        smallest_eigenvector_fast(m, n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]);
+    }
+}
+
 void emu_smallest_eigenvector(const float* cov6, float* n3, float* gap)
 {
     Sym3 m{cov6[0], cov6[1], cov6[2], cov6[3], cov6[4], cov6[5]};
@@ -549,12 +559,15 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
 {
     GridView const& g   = ix->g;
     TileParams tp = make_tile_params<S>(g, level, max_points, scan_cap);
-    tp.first_cap  = g_emu_first_cap;
+    tp.first_cap  = std::min<uint32_t>(g_emu_first_cap, (uint32_t)kTileCandCap);
     std::vector<float4> P(max_points + kTilePad);
-    std::vector<uint32_t> F(TileDims<S>::bins + 1), span_start(kTileSpans), span_off(kTileSpans + 1),
-        partial(kTileScanLanes);
+    tp.threads    = nthreads;
+    std::vector<uint32_t> F(TileDims<S>::bins + 1), cstart(kRegionCellCount), ccount(kRegionCellCount);
+    std::vector<uint8_t> occ(kRegionCellCount);
     TileGeom geom;
-    TileSmem sm{P.data(), F.data(), span_start.data(), span_off.data(), partial.data(), &geom};
+    TileSmem sm{};
+    sm.P = P.data(), sm.F = F.data(), sm.cstart = cstart.data(), sm.ccount = ccount.data();
+    sm.occ = occ.data(), sm.geom = &geom;
     constexpr int segs = kTileCells * kTileCells * S;
     std::vector<uint32_t> rowmask(TileDims<S>::nc), seg_off(segs + 1), gpos(max_points);
     std::vector<uint16_t> qlist(max_points), clist((size_t)kTileCandCap * nthreads);
@@ -576,14 +589,12 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
         while (s1 < g.n && tile_of(s1) == code)
             ++s1;
         stats[0]++;
+        QueryCell const fc = query_cell(g, ix->pts[s0].x, ix->pts[s0].y, ix->pts[s0].z);
+        uint64_t const txyz = tile_pack(fc.ux >> sh, fc.uy >> sh, fc.uz >> sh);
         for (int t = 0; t < nthreads; ++t)
-            tile_phase_lookup<S>(g, tp, sm, s0, t, nthreads);
-        tile_phase_plan<S>(g, tp, sm, s0);
+            tile_phase_lookup<S>(g, tp, sm, txyz, t, nthreads);
         for (int t = 0; t < nthreads; ++t)
-            tile_phase_count<S>(g, tp, sm, t, nthreads);
-        for (int t = 0; t < nthreads; ++t)
-            tile_phase_scan_a<S>(sm, t);
-        tile_phase_scan_b(tp, sm);
+            tile_phase_plan<S>(tp, sm, txyz, t);
         stats[4] = std::max<uint64_t>(stats[4], geom.n_points);
         if (geom.fallback)
         {
@@ -592,13 +603,13 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
             s0 = s1;
             continue;
         }
+        // (thread order scrambled: nothing may depend on it)
+        for (int t = nthreads - 1; t >= 0; --t)
+            tile_phase_count<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
         for (int t = 0; t < nthreads; ++t)
-            tile_phase_scan_c<S>(sm, t);
-        // serve the placement "atomics" in a scrambled thread order: results must not depend on it
+            tile_phase_scan<S>(sm, t);
         for (int t = nthreads - 1; t >= 0; --t)
             tile_phase_place<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
-        for (int t = 0; t < nthreads; ++t)
-            tile_phase_sort_bins<S>(sm, t, nthreads);
         uint32_t nq = s1 - s0;
         if (batched)
         {
@@ -624,18 +635,30 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
             {
                 int const tid = (int)(i % (uint32_t)nthreads);
                 TileCursor cu = tile_cursor<S>(g, tp, geom, q.x, q.y, q.z);
-                tile_search_batched<KL, S>(tp, sm.P, sm.F, sm.rowmask, cu,
+                tile_search_batched<KL, S, 0>(tp, sm.P, sm.F, sm.rowmask, cu,
                                            eps > 0.f ? pos : kNoSelf, sm.cl + tid, nthreads, q.x,
-                                           q.y, q.z, k, tp.first_cap, top, &cand);
-                ok = tile_is_final<KL>(top, k, tp.key_mask, cu.r2scan, eps);
+                                           q.y, q.z, k, tp.first_cap, geom.n_points, top, &cand);
+                ok = tile_is_final<KL, 0>(top, k, tp.key_mask, cu.r2scan, eps);
+                if (ok)
+                    tile_store_winners<KL>(top, tp.key_mask, sm.cl + tid, nthreads);
             }
             else
                 ok = tile_search<KL, S>(g, tp, geom, sm.P, sm.F, q.x, q.y, q.z, k, eps, top, &cand);
             stats[3] += cand;
+            int const etid = (int)(i % (uint32_t)nthreads);
+            auto emit = [&](auto&& f) {
+                if constexpr (batched)
+                    return tile_emit_sorted_rolled(sm.P, sm.cl + etid, nthreads, k, q.x, q.y, q.z, f);
+                else
+                    return tile_emit_sorted<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z, f);
+            };
             if (ok && mode == 2)
             {
                 float n3[3], c3[3];
-                tile_normal<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z, n3, c3);
+                if constexpr (batched)
+                    tile_normal_rolled(sm.P, sm.cl + etid, nthreads, k, q.x, q.y, q.z, n3, c3);
+                else
+                    tile_normal<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z, n3, c3);
                 for (int a = 0; a < 3; ++a)
                 {
                     nrm[3 * (size_t)row + a] = n3[a];
@@ -645,12 +668,11 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
             }
             else if (ok && mode == 0)
             {
-                ok = tile_emit_sorted<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z,
-                                          [&](uint32_t slot, float dd, uint32_t id) {
-                                              idx[(size_t)row * k + slot] = id;
-                                              if (d2)
-                                                  d2[(size_t)row * k + slot] = dd;
-                                          });
+                ok = emit([&](uint32_t slot, float dd, uint32_t id) {
+                    idx[(size_t)row * k + slot] = id;
+                    if (d2)
+                        d2[(size_t)row * k + slot] = dd;
+                });
                 if (ok && cnt)
                     cnt[row] = k;
                 if (!ok)
@@ -659,8 +681,7 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
             else if (ok)
             {
                 float sum = 0.f;
-                ok = tile_emit_sorted<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z,
-                                          [&](uint32_t, float dd, uint32_t) { sum = sum + sqrtf(dd); });
+                ok = emit([&](uint32_t, float dd, uint32_t) { sum = sum + sqrtf(dd); });
                 means[row] = sum / (float)k;
                 if (!ok)
                     stats[5]++;

@@ -90,7 +90,7 @@ def test_tile_scan_cap_and_fallback(emu, cloud_set):
             d = r["done"]
             assert np.array_equal(r["idx"][d], ridx[d]) and np.array_equal(r["d2"][d], rd2[d]), cap
     # batched form: the size of the first round only changes the work, never the rows
-    for first in (8, 16, 64):
+    for first in (8, 16, 24):
         emu.L.emu_tile_first_cap(first)
         r = ix.tile(k, 0, level, sub=2, alg=2, max_points=4096)
         d = r["done"]
@@ -103,7 +103,7 @@ def test_tile_scan_cap_and_fallback(emu, cloud_set):
     d = r["done"]
     assert np.array_equal(r["idx"][d], ridx[d])
     # thread count of the emulated CTA must not matter
-    a = ix.tile(k, 0, level, sub=2, nthreads=32)
+    a = ix.tile(k, 0, level, sub=2, nthreads=160)
     b = ix.tile(k, 0, level, sub=2, nthreads=256)
     assert np.array_equal(a["done"], b["done"]) and np.array_equal(a["idx"], b["idx"])
 
