@@ -977,4 +977,40 @@ PCPX_HD bool tile_emit_sorted_rolled(const float4* P, const uint16_t* cl, int st
     return ok;
 }
 
+// Puts the k winners' positions (cl[0 .. k)) into exact ascending (d2, original index) order in
+// place — same one-displacement rule as tile_emit_sorted — so that row outputs can be produced
+// slot by slot afterwards.  Returns false when the order could not be established.
+PCPX_HD bool tile_order_winners(const float4* P, uint16_t* cl, int stride, uint32_t k, float qx,
+                                float qy, float qz)
+{
+    float hd = 0.f, ld = -1.f;
+    uint32_t hid = 0, lid = 0, hpos = 0, slot = 0;
+    bool ok = true;
+#pragma unroll 1
+    for (uint32_t j = 0; j < k; ++j)
+    {
+        uint32_t const pos = cl[j * (uint32_t)stride];
+        float4 const c     = P[pos];
+        float const d2     = sqdist_x(fsub_x(c.x, qx), fsub_x(c.y, qy), fsub_x(c.z, qz));
+        uint32_t const id  = f2u(c.w);
+        if (j == 0)
+        {
+            hd = d2, hid = id, hpos = pos;
+            continue;
+        }
+        bool const before_held = d2 < hd || (d2 == hd && id < hid);
+        float const ed         = before_held ? d2 : hd;
+        uint32_t const eid     = before_held ? id : hid;
+        ok = ok && !(ed < ld || (ed == ld && eid < lid && slot > 0));
+        cl[slot * (uint32_t)stride] = (uint16_t)(before_held ? pos : hpos); // slot < j: already read
+        ++slot;
+        ld = ed, lid = eid;
+        if (!before_held)
+            hd = d2, hid = id, hpos = pos;
+    }
+    ok = ok && !(hd < ld || (hd == ld && hid < lid && slot > 0));
+    cl[slot * (uint32_t)stride] = (uint16_t)hpos;
+    return ok;
+}
+
 } // namespace pcpx

@@ -666,6 +666,23 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
                         ctr[3 * (size_t)row + a] = c3[a];
                 }
             }
+            else if (ok && mode == 0 && batched && k <= 16u)
+            {
+                // the device's row output: winners ordered in place, rows read off the positions
+                ok = tile_order_winners(sm.P, sm.cl + etid, nthreads, k, q.x, q.y, q.z);
+                for (uint32_t j = 0; ok && j < k; ++j)
+                {
+                    float4 const c = sm.P[sm.cl[etid + j * (uint32_t)nthreads]];
+                    idx[(size_t)row * k + j] = f2u(c.w);
+                    if (d2)
+                        d2[(size_t)row * k + j] =
+                            sqdist_x(fsub_x(c.x, q.x), fsub_x(c.y, q.y), fsub_x(c.z, q.z));
+                }
+                if (ok && cnt)
+                    cnt[row] = k;
+                if (!ok)
+                    stats[5]++;
+            }
             else if (ok && mode == 0)
             {
                 ok = emit([&](uint32_t slot, float dd, uint32_t id) {
