@@ -13,17 +13,29 @@ sort -> cell tables) + the fused kNN -> PCA normal kernel over all of its points
   value   normals/s with the cloud already resident in HBM (device pointers in, normals left in
           HBM), whole job over all ranks, bracketed by barrier + synchronize, max over ranks.
   e2e     the same step through the public C ABI with HOST buffers: pinned xyz in (H2D inside
-          the timed region), host normals out (D2H inside).
-  roofline  the dominant kernel (normals_kernel): algorithmic bytes (SURVEY.md §8d gather model:
-          12 + 12 k + 12 = 204 B per normal at k = 15) / its CUDA-event duration on the
-          library's launching stream, against the measured HBM peak in MEASURED_PEAKS.json.
+          the timed region), host normals out (D2H inside).  Clouds are processed as a stream:
+          --e2e-threads host threads (default 2) each run whole blocking calls on their own
+          index, so one cloud's copies overlap another's kernels; `e2e_serial` (extra key) is the
+          same with one thread.
+  roofline  the dominant kernel (the tile kNN -> normal kernel): algorithmic bytes (SURVEY.md §8d
+          gather model: 12 + 12 k + 12 = 204 B per normal at k = 15) / its CUDA-event duration on
+          the library's launching stream, against the measured HBM peak in MEASURED_PEAKS.json.
+          `traffic` is the DRAM bytes of one launch from the committed ncu capture
+          (profiles/normals_kernel_traffic.json), reported only while the kernel sources still
+          hash to what was captured.
   cpu_baseline  the reference's own octree (oracle/_ref, unmodified headers) + the restated
           estimate_normal, on this box's host cores, on a bounded sample (rank 0, N = 1 only).
+  extras  (extra keys, kernel times by CUDA events, each with units_per_s / kernel_ms / frac of
+          its own gather-model roofline): knn_k15, radius_r0.01, build on the same 10 M plane;
+          density_filter_mix (10 M points, 5 % uniform noise); knn_k8_sphere_10M — N = 1 only.
+          For every N: scan100M_k30 (configs[3]: k = 30 normals over a 100 M-point scan cut into
+          N slabs) and, for N > 1, strong (the ONE 10 M-point plane cut into N slabs).
 
-N > 1 ("weak"): every rank owns one 10 M-point slab of an N x 10 M-point plane plus a 0.05-wide
-halo of its neighbours' points; the halo strips are exchanged between neighbouring ranks over
-NCCL inside every timed step (point-cloud-processing_b200/sharding.py: exchange_halo) — the one
-real exchange of the sharded path; value = N x 10 M normals / max-over-ranks time.
+N > 1 ("weak" headline): every rank owns one 10 M-point slab of an N x 10 M-point plane plus a
+0.05-wide halo of its neighbours' points; the halo strips are exchanged between neighbouring
+ranks over NCCL inside every timed step (point-cloud-processing_b200/sharding.py:
+exchange_halo) — the one real exchange of the sharded path; value = N x 10 M normals /
+max-over-ranks time.
 
 --impl reference: times the reference's CPU implementation of the same step (full-size octree
 build + a bounded query sample, extrapolated linearly) on all host threads; rank 0 only.
@@ -59,15 +71,35 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def csrc_hash():
+    """hash of the kernel sources (same recipe as tools/update_traffic.py)"""
+    import hashlib
+
+    d = os.path.join(ROOT, "point-cloud-processing_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        p = os.path.join(d, f)
+        if os.path.isfile(p) and f.endswith((".cu", ".cuh", ".hpp", ".inc")):
+            h.update(f.encode())
+            h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def recorded_traffic():
-    """dram bytes of the dominant kernel from the committed ncu capture, if one was summarised"""
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu capture — only
+    when the capture was taken from the kernel sources that are in the tree now.  Returns
+    (bytes or None, provenance string)."""
     p = os.path.join(ROOT, "profiles", "normals_kernel_traffic.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["dram_bytes_per_launch"])
-        except Exception:
-            return None
-    return None
+    if not os.path.exists(p):
+        return None, "no capture committed"
+    try:
+        rec = json.load(open(p))
+        src = "%s, commit %s, %s" % (rec.get("source"), rec.get("commit"), rec.get("captured_at"))
+        if rec.get("csrc_sha16") != csrc_hash():
+            return None, "STALE capture (kernel sources changed since): " + src
+        return float(rec["dram_bytes_per_launch"]), src
+    except Exception as e:  # noqa: BLE001
+        return None, "unreadable capture: %r" % (e,)
 
 
 class ClockSampler:
@@ -236,6 +268,50 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+def _timed(fn, steps, warmup, barrier, world, dist, torch):
+    """K timed calls of fn bracketed by barrier + synchronize; max over ranks (seconds)"""
+    for _ in range(warmup):
+        fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    barrier()
+    return dt
+
+
+class ShardedCloud:
+    """One rank's slab of a cloud cut along x, resident in HBM, with room behind it for the
+    neighbours' halo strips; local() runs the exchange step and returns the local cloud."""
+
+    def __init__(self, pcpx, torch, dist, pts, slab_lo, slab_hi, halo, rank, world):
+        self.pcpx, self.torch, self.dist = pcpx, torch, dist
+        self.rank, self.world, self.halo = rank, world, halo
+        self.lo, self.hi = float(slab_lo), float(slab_hi)
+        self.n_owned = len(pts)
+        self.h_xyz = torch.from_numpy(pts).pin_memory()
+        extent = max(self.hi - self.lo, 1e-9)
+        # strips hold about n * halo / extent points; twice that (+ slack) is the capacity
+        cap = 0 if world == 1 else int(2 * self.n_owned * halo / extent) + 65536
+        self.buf = torch.empty((self.n_owned + 2 * cap, 3), dtype=torch.float32, device="cuda")
+        self.own = self.buf[: self.n_owned]
+        self.own.copy_(self.h_xyz)
+        self.scratch = pcpx.sharding.HaloScratch(cap, "cuda") if world > 1 else None
+
+    def local(self):
+        if self.world == 1:
+            return self.own
+        return self.pcpx.sharding.exchange_halo(self.own, 0, self.lo, self.hi, self.halo,
+                                                self.rank, self.world, self.dist, buffer=self.buf,
+                                                scratch=self.scratch)[0]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -253,126 +329,266 @@ def run_ours(args):
                                 device_id=torch.device("cuda", local_rank))
     pcpx = importlib.import_module("point-cloud-processing_b200")
     pcpx.lib()  # fail loudly now if the CUDA library is missing
-
-    xyz, L = own_slab(pcpx, rank)
-    n_owned = len(xyz)
-    h_xyz = torch.from_numpy(xyz).pin_memory()
-    # room behind the owned slab for the neighbours' strips: they are received in place
-    slack = 0 if world == 1 else 1_000_000
-    d_buf = torch.empty((n_owned + slack, 3), dtype=torch.float32, device="cuda")
-    d_stage_buf = torch.empty((n_owned + slack, 3), dtype=torch.float32, device="cuda")
-    d_own, d_stage = d_buf[:n_owned], d_stage_buf[:n_owned]
-    d_own.copy_(h_xyz)
-    slab_lo, slab_hi = float(rank * L), float((rank + 1) * L)
-    # strips hold about n * HALO / L points; twice that is the exchange capacity
-    scratch = None
-    if world > 1:
-        scratch = pcpx.sharding.HaloScratch(int(2 * n_owned * HALO / L) + 4096, "cuda")
-
-    def local_cloud(d_points, d_buffer):
-        """N > 1: the exchange step — boundary strips go to the neighbouring ranks over NCCL"""
-        if world == 1:
-            return d_points
-        return pcpx.sharding.exchange_halo(d_points, 0, slab_lo, slab_hi, HALO, rank, world,
-                                           dist, buffer=d_buffer, scratch=scratch)[0]
-
-    n_local = int(local_cloud(d_own, d_buf).shape[0])
-    d_nrm = torch.empty((n_local, 3), dtype=torch.float32, device="cuda")
-    h_nrm = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
-    torch.cuda.synchronize()
+    peak, peak_src = measured_peak_gbs()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(stats=None):
-        d_xyz = local_cloud(d_own, d_buf)
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- the headline: weak, 10 M-point plane per rank --------------------------
+    xyz, L = own_slab(pcpx, rank)
+    cloud = ShardedCloud(pcpx, torch, dist, xyz, rank * L, (rank + 1) * L, HALO, rank, world)
+    n_owned = cloud.n_owned
+    n_local = int(cloud.local().shape[0])
+    d_nrm = torch.empty((n_local + 65536, 3), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+
+    stats = {k_: [] for k_ in ("build_ms", "sort_ms", "kernel_ms", "launches", "retries")}
+
+    def step_resident(cl=cloud, k=K, st=stats, out=d_nrm):
+        d_xyz = cl.local()
         torch.cuda.synchronize()  # the library runs on its own stream
         ix = pcpx.Index(d_xyz, device=local_rank)
         tb = ix.timings()
-        ix.estimate_normals(None, K, out=d_nrm)
+        ix.estimate_normals(None, k, out=out[: ix.n])
         tq = ix.timings()
         ix.close()
-        if stats is not None:
-            stats["build_ms"].append(tb["build_ms"])
-            stats["sort_ms"].append(tb["sort_ms"])
-            stats["kernel_ms"].append(tq["kernel_ms"])
-            stats["launches"].append(tb["kernel_launches"] + tq["kernel_launches"])
-            stats["retries"].append(tq["retry_queries"])
+        if st is not None:
+            st["build_ms"].append(tb["build_ms"])
+            st["sort_ms"].append(tb["sort_ms"])
+            st["kernel_ms"].append(tq["kernel_ms"])
+            st["launches"].append(tb["kernel_launches"] + tq["kernel_launches"])
+            st["retries"].append(tq["retry_queries"])
 
-    def step_e2e():
+    # end to end: pinned host buffers in and out, whole blocking calls, T host threads
+    n_thr = max(1, args.e2e_threads)
+    h_out = [torch.empty((n_local + 65536, 3), dtype=torch.float32).pin_memory() for _ in range(n_thr)]
+    d_stage = None
+    if world > 1:  # N > 1: the owned slab goes up first, then the exchange, then the build
+        d_stage = [ShardedCloud(pcpx, torch, dist, xyz, rank * L, (rank + 1) * L, HALO, rank, world)]
+
+    def e2e_once(t):
         if world == 1:
-            ix = pcpx.Index(h_xyz.numpy(), device=local_rank)  # host pointer: H2D inside
+            ix = pcpx.Index(cloud.h_xyz.numpy(), device=local_rank)  # host pointer: H2D inside
         else:
-            d_stage.copy_(h_xyz, non_blocking=True)  # H2D of the owned slab, then the exchange
-            d_xyz = local_cloud(d_stage, d_stage_buf)
+            c = d_stage[t]
+            c.own.copy_(cloud.h_xyz, non_blocking=True)
+            d_xyz = c.local()
             torch.cuda.synchronize()
             ix = pcpx.Index(d_xyz, device=local_rank)
-        ix.estimate_normals(None, K, out=h_nrm.numpy()[: ix.n])  # host pointer: D2H inside
+        ix.estimate_normals(None, K, out=h_out[t].numpy()[: ix.n])  # host pointer: D2H inside
         ix.close()
 
-    def timed(fn, steps, warmup, stats=None):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            fn() if stats is None else fn(stats)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        barrier()
-        return dt
+    def e2e_run(total_steps, threads):
+        """total_steps clouds through `threads` host threads; the collective exchange of N > 1
+        needs every rank to issue it in the same order, so there the threads take turns under
+        a lock for the exchange part only (one thread when world > 1 keeps it simple)."""
+        if threads == 1 or world > 1:
+            for _ in range(total_steps):
+                e2e_once(0)
+            return
+        per = [total_steps // threads + (1 if i < total_steps % threads else 0) for i in range(threads)]
+        errs = []
 
-    stats = {k_: [] for k_ in ("build_ms", "sort_ms", "kernel_ms", "launches", "retries")}
+        def work(t):
+            try:
+                torch.cuda.set_device(local_rank)
+                for _ in range(per[t]):
+                    e2e_once(t)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if errs:
+            raise errs[0]
+
     with ClockSampler(local_rank) as clocks:
-        dt_res = timed(step_resident, args.steps, args.warmup, stats)
-        dt_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+        dt_res = _timed(step_resident, args.steps, args.warmup, barrier, world, dist, torch)
+        del stats["build_ms"][: args.warmup], stats["sort_ms"][: args.warmup]
+        del stats["kernel_ms"][: args.warmup], stats["retries"][: args.warmup]
+        del stats["launches"][: args.warmup]
+        dt_e2e = _timed(lambda: e2e_run(args.steps, n_thr), 1, 1, barrier, world, dist, torch)
+        dt_e2e_serial = _timed(lambda: e2e_run(max(2, args.steps // 2), 1), 1, 0, barrier, world,
+                               dist, torch)
     total_owned = n_owned * world
     value = total_owned * args.steps / dt_res
     e2e_value = total_owned * args.steps / dt_e2e
+    e2e_serial_value = total_owned * max(2, args.steps // 2) / dt_e2e_serial
 
-    kernel_ms = float(np.mean(stats["kernel_ms"]))
-    if world > 1:
-        t = torch.tensor([kernel_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kernel_ms = float(t.item())
-    peak, peak_src = measured_peak_gbs()
+    kernel_ms = allmax(float(np.mean(stats["kernel_ms"])))
+    traffic, traffic_src = recorded_traffic()
     achieved = ALGORITHMIC_BYTES_PER_NORMAL * n_local / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": recorded_traffic(),
-                "kernel": "knn_main_kernel<15, MODE_NORMALS>", "kernel_ms": kernel_ms,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "tile_knn2_kernel<16, MODE_NORMALS, S=2> (+ tile list, + retry kernel)",
+                "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_NORMAL * n_local,
                 "peak_source": peak_src,
-                "note": "gather-model bytes (12 + 12k + 12 per normal); the kernel is "
-                        "instruction-issue bound, DRAM traffic sits far below this figure"}
+                "note": "gather-model bytes (12 + 12k + 12 per normal, SURVEY.md 8d); kernel_ms "
+                        "is the CUDA-event time of everything the normals call launches"}
 
     # untimed: the halo is wide enough iff every owned point near an inner slab face has its k
     # nearest neighbours inside the local cloud, i.e. at least k + 1 local points (itself
     # included) within its distance to the outer face of the halo
-    halo_ok = True
-    if world > 1:
-        own = xyz
-        d_xyz = local_cloud(d_own, d_buf)
+    def halo_check(cl, own, lo, hi, k):
+        if world == 1:
+            return True
+        d_xyz = cl.local()
         torch.cuda.synchronize()
-        lo_gap = own[:, 0] - np.float32(rank * L - HALO) if rank > 0 else None
-        hi_gap = np.float32((rank + 1) * L + HALO) - own[:, 0] if rank < world - 1 else None
-        gap = np.full(n_owned, np.inf, np.float32)
-        if lo_gap is not None:
-            gap = np.minimum(gap, lo_gap)
-        if hi_gap is not None:
-            gap = np.minimum(gap, hi_gap)
-        near = np.flatnonzero(gap < 4 * HALO)
-        with pcpx.Index(d_xyz, device=local_rank) as ix:
-            cnt = ix.radius_count(own[near], 0.0, radii=(gap[near] * np.float32(0.999)))
-        halo_ok = bool((cnt >= K + 1).all())
-        t = torch.tensor([1 if halo_ok else 0], device="cuda")
+        gap = np.full(len(own), np.inf, np.float32)
+        if rank > 0:
+            gap = np.minimum(gap, own[:, 0] - np.float32(lo - cl.halo))
+        if rank < world - 1:
+            gap = np.minimum(gap, np.float32(hi + cl.halo) - own[:, 0])
+        near = np.flatnonzero(gap < 4 * cl.halo)
+        ok = True
+        if len(near):
+            with pcpx.Index(d_xyz, device=local_rank) as ix:
+                cnt = ix.radius_count(own[near], 0.0, radii=(gap[near] * np.float32(0.999)))
+            ok = bool((cnt >= k + 1).all())
+        t = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        halo_ok = bool(t.item())
+        return bool(t.item())
+
+    halo_ok = halo_check(cloud, xyz, rank * L, (rank + 1) * L, K)
+
+    # ---------------- extra legs ---------------------------------------------------------------
+    extras = {}
+    leg_steps, leg_warm = max(3, args.steps // 2), 2
+
+    def kernel_leg(fn, ix, reps=5):
+        ms = []
+        for _ in range(reps):
+            fn()
+            ms.append(ix.timings()["kernel_ms"])
+        return float(np.median(ms[1:])), float(min(ms[1:]))
+
+    def frac_of(bytes_per_unit, units, ms):
+        return bytes_per_unit * units / (ms * 1e-3) / 1e9 / peak
+
+    if world == 1 and not args.no_extras:
+        n = n_owned
+        d_idx = torch.empty((n, K), dtype=torch.int32, device="cuda")
+        d_d2 = torch.empty((n, K), dtype=torch.float32, device="cuda")
+        d_cnt = torch.empty((n,), dtype=torch.int32, device="cuda")
+        with pcpx.Index(cloud.own, device=local_rank) as ix:
+            info = ix.info()
+            med, best = kernel_leg(lambda: ix.knn(None, K, out_idx=d_idx, out_d2=d_d2,
+                                                  out_count=d_cnt), ix)
+            extras["knn_k15"] = {
+                "workload": "batched kNN k=15 (indices + distances + counts) over the 10M-point plane, "
+                            "queries = the cloud, index resident",
+                "units_per_s": n / (med * 1e-3), "unit": "queries/s", "kernel_ms": med,
+                "best_ms": best, "bytes_per_unit": 12 + 12 * K + 4 * K + 4 * K,
+                "frac": frac_of(12 + 12 * K + 4 * K + 4 * K, n, med)}
+            med, best = kernel_leg(lambda: ix.radius_count(None, 0.01, out_count=d_cnt), ix)
+            mbar = float(d_cnt.to(torch.float64).mean().item())
+            extras["radius_r0.01"] = {
+                "workload": "radius count r=0.01 over the 10M-point plane, queries = the cloud",
+                "units_per_s": n / (med * 1e-3), "unit": "queries/s", "kernel_ms": med,
+                "best_ms": best, "mean_count": mbar, "bytes_per_unit": 12 + 12 * mbar + 4,
+                "frac": frac_of(12 + 12 * mbar + 4, n, med)}
+        build_ms = float(np.mean(stats["build_ms"]))
+        bpp = 136 if info["code_bits"] <= 30 else 276
+        extras["build"] = {
+            "workload": "index build of the 10M-point plane (%d-bit codes), as inside every step" % info["code_bits"],
+            "units_per_s": n / (build_ms * 1e-3), "unit": "points/s", "kernel_ms": build_ms,
+            "sort_ms": float(np.mean(stats["sort_ms"])), "bytes_per_unit": bpp,
+            "frac": frac_of(bpp, n, build_ms)}
+        del d_idx, d_d2
+        # configs[2]: density filter on 10 M points with 5 % uniform noise
+        mix = torch.from_numpy(pcpx.synth.noise_mix(N_POINTS)).cuda()
+        d_mask = torch.empty((N_POINTS,), dtype=torch.uint8, device="cuda")
+        d_keep = torch.empty((N_POINTS, 3), dtype=torch.float32, device="cuda")
+        with pcpx.Index(mix, device=local_rank) as ix:
+            radius = float(ix.mean_knn_distance(K)[1])
+            mean_ms = ix.timings()["kernel_ms"]
+            kept = [0]
+
+            def flt():
+                kept[0] = ix.density_filter(radius, 5, out_mask=d_mask, out_xyz=d_keep)[2]
+
+            med, best = kernel_leg(flt, ix)
+            ix.radius_count(None, radius, out_count=d_cnt)
+            mbar = float(d_cnt.to(torch.float64).mean().item())
+            a_flt = 12 + 12 * mbar + 1 + 12 * kept[0] / N_POINTS
+            extras["density_filter_mix"] = {
+                "workload": "density filter (radius = mean 15-NN distance, threshold 5) on 10M points with 5% uniform noise",
+                "units_per_s": N_POINTS / (med * 1e-3), "unit": "points/s", "kernel_ms": med,
+                "best_ms": best, "radius": radius, "mean_count": mbar, "kept": int(kept[0]),
+                "mean_knn_distance_kernel_ms": mean_ms, "bytes_per_unit": a_flt,
+                "frac": frac_of(a_flt, N_POINTS, med)}
+        del mix, d_mask, d_keep
+        # configs[4], one point of the sweep: kNN k=8 over a 10 M-point noisy sphere
+        sph = torch.from_numpy(pcpx.synth.noisy_sphere(N_POINTS)).cuda()
+        d_idx8 = torch.empty((N_POINTS, 8), dtype=torch.int32, device="cuda")
+        with pcpx.Index(sph, device=local_rank) as ix:
+            sb = ix.info()["build_ms"]
+            med, best = kernel_leg(lambda: ix.knn(None, 8, out_idx=d_idx8, out_d2=None,
+                                                  out_count=d_cnt, want_d2=False), ix)
+            extras["knn_k8_sphere_10M"] = {
+                "workload": "kNN k=8 (indices + counts) over a 10M-point noisy sphere (sigma 0.005), queries = the cloud",
+                "units_per_s": N_POINTS / (med * 1e-3), "unit": "queries/s", "kernel_ms": med,
+                "best_ms": best, "build_ms": sb, "bytes_per_unit": 12 + 12 * 8 + 4 * 8,
+                "frac": frac_of(12 + 12 * 8 + 4 * 8, N_POINTS, med)}
+        del sph, d_idx8, d_cnt
+        torch.cuda.empty_cache()
+
+    def sharded_leg(pts, lo, hi, k, bytes_per_unit, what):
+        cl = ShardedCloud(pcpx, torch, dist, pts, lo, hi, HALO, rank, world)
+        nl = int(cl.local().shape[0])
+        out = torch.empty((nl + 65536, 3), dtype=torch.float32, device="cuda")
+        st = {k_: [] for k_ in ("build_ms", "sort_ms", "kernel_ms", "launches", "retries")}
+        dt = _timed(lambda: step_resident(cl, k, st, out), leg_steps, leg_warm, barrier, world,
+                    dist, torch)
+        total = allsum(cl.n_owned)
+        kms = allmax(float(np.mean(st["kernel_ms"][leg_warm:])))
+        ok = halo_check(cl, pts, lo, hi, k)
+        rec = {"workload": what, "units_per_s": total * leg_steps / dt, "unit": "normals/s",
+               "total_points": int(total), "ms_per_step": dt / leg_steps * 1e3, "kernel_ms": kms,
+               "build_ms": allmax(float(np.mean(st["build_ms"][leg_warm:]))),
+               "bytes_per_unit": bytes_per_unit,
+               "frac": bytes_per_unit * allmax(nl) / (kms * 1e-3) / 1e9 / peak,
+               "halo_sufficient": ok, "n_gpus": world}
+        del cl, out
+        torch.cuda.empty_cache()
+        return rec
+
+    if not args.no_extras:
+        if world > 1:
+            # strong: the ONE seed-7 10 M-point plane, cut into `world` slabs along x
+            full = pcpx.synth.noisy_plane(N_POINTS)
+            edges = pcpx.sharding.slab_edges(0.0, L, world)
+            own = np.ascontiguousarray(full[pcpx.sharding.owner_of(full[:, 0], edges) == rank])
+            del full
+            extras["strong"] = sharded_leg(
+                own, edges[rank], edges[rank + 1], K, ALGORITHMIC_BYTES_PER_NORMAL,
+                "strong scaling: estimate_normals k=15 over the ONE 10M-point noisy plane "
+                "(seed 7) cut into %d slabs; index build + halo exchange + normals per step" % world)
+        pts, side = pcpx.synth.scan_slab(100_000_000, rank / world, (rank + 1) / world)
+        extras["scan100M_k30"] = sharded_leg(
+            pts, side * rank / world, side * (rank + 1) / world, 30, 12 + 12 * 30 + 12,
+            "estimate_normals k=30 over a 100M-point synthetic scan (height field + sphere), "
+            "cut into %d slab(s) along x; index build + halo exchange + normals per step" % world)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -397,7 +613,10 @@ def run_ours(args):
             },
             "e2e": {"value": e2e_value, "unit": "normals/s",
                     "h2d_bytes_per_step": int(n_owned * 12), "d2h_bytes_per_step": int(n_local * 12),
-                    "ms_per_step": dt_e2e / args.steps * 1e3},
+                    "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "host_threads": n_thr if world == 1 else 1},
+            "e2e_serial": {"value": e2e_serial_value, "unit": "normals/s",
+                           "ms_per_step": dt_e2e_serial / max(2, args.steps // 2) * 1e3},
             "gpu_launches": int(np.sum(stats["launches"])),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -408,6 +627,7 @@ def run_ours(args):
             "exact_fallback_queries_per_step": float(np.mean(stats["retries"])),
             "halo_sufficient": halo_ok,
         }
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -423,6 +643,10 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=100_000,
                     help="queries in the CPU reference's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs (knn, radius, filter, sweep point, strong, scan100M)")
+    ap.add_argument("--e2e-threads", type=int, default=2,
+                    help="host threads streaming clouds through the C ABI in the e2e leg (N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

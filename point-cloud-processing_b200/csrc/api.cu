@@ -11,9 +11,9 @@ using namespace pcpx;
 
 // kernels a kNN-shaped call launches: main + retry for the register-list sizes; the heap
 // kernel alone (rows) or followed by the inverse-order and row-reduction kernels (normals, means)
-static uint32_t knn_shaped_launches(uint32_t k, bool rows_only)
+static uint32_t knn_shaped_launches(const pcpx_index& ix, uint32_t k, bool rows_only)
 {
-    return k <= kMaxK ? 2u : (rows_only ? 1u : 3u);
+    return k <= kMaxK ? ix.query_launches : (rows_only ? 1u : 3u);
 }
 
 extern "C" {
@@ -102,7 +102,7 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
         timer.kernel_begin();
         launch_knn(ix, batch.qb, k, (float)eps, idx.d, d2.d, cnt.d, retries.get());
         timer.kernel_end();
-        ix.timings.kernel_launches = knn_shaped_launches(k, true);
+        ix.timings.kernel_launches = knn_shaped_launches(ix, k, true);
         idx.finish(ix.stream), d2.finish(ix.stream), cnt.finish(ix.stream);
         uint32_t h_retries = 0;
         PCPX_CUDA(cudaMemcpyAsync(&h_retries, retries.get(), 4, cudaMemcpyDeviceToHost,
@@ -228,7 +228,7 @@ static void normals_impl(const pcpx_index* index, const float* queries, size_t n
     timer.kernel_begin();
     launch_normals(ix, batch.qb, k, (float)eps, ctr.d, nrm.d, ties.get());
     timer.kernel_end();
-    ix.timings.kernel_launches = knn_shaped_launches(k, false);
+    ix.timings.kernel_launches = knn_shaped_launches(ix, k, false);
     nrm.finish(ix.stream), ctr.finish(ix.stream);
     uint32_t h_ties = 0;
     PCPX_CUDA(cudaMemcpyAsync(&h_ties, ties.get(), 4, cudaMemcpyDeviceToHost, ix.stream));
@@ -327,7 +327,7 @@ int pcpx_mean_knn_distance(const pcpx_index* index, uint32_t k, double eps, floa
         launch_mean_distance(ix, qb, k, (float)eps, means.d);
         launch_mean_reduce(ix, means.d, (uint32_t)n, sum.get(), valid.get());
         timer.kernel_end();
-        ix.timings.kernel_launches = knn_shaped_launches(k, false) + 2u; // + the two-stage reduction
+        ix.timings.kernel_launches = knn_shaped_launches(ix, k, false) + 2u; // + the two-stage reduction
         means.finish(ix.stream);
         double h_sum = 0;
         uint32_t h_valid = 0;

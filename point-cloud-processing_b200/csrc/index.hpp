@@ -25,6 +25,7 @@ struct pcpx_index
     // tile_starts[i] = first sorted position of tile i, tile_starts[n_tiles] = n_indexed
     mutable pcpx::DevBuf<uint32_t> tile_starts, tile_count, tile_scratch;
     mutable pcpx::DevBuf<uint64_t> tile_xyz; // tile coordinates (tile_core.cuh: tile_pack)
+    mutable uint32_t query_launches = 0; // kernels launched by the last kNN-shaped call
     mutable int tile_level         = -1;
     mutable uint32_t tile_capacity = 0;
 

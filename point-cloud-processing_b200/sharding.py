@@ -169,3 +169,82 @@ def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None, bu
         return buffer[:at], n_own
     parts = [own_xyz] + [recv[p] for p in sorted(recv)]
     return torch.cat(parts, 0), n_own
+
+
+def sharded_self_queries(own_xyz, lo, hi, rank, world, dist, k, halo, device, axis=0,
+                         max_rounds=5, group=None):
+    """Slab mode end to end on CUDA tensors: kNN (distances + neighbour coordinates) and PCA
+    normals of the points this rank OWNS, equal to what one index over the whole cloud returns.
+
+    Round 0 exchanges `halo`-wide strips, builds the local index and answers every owned point.
+    A row is final iff its k-th neighbour distance is smaller than the distance to the outer
+    faces of the halo (`halo_is_sufficient`, per row).  While ANY rank has open rows, every rank
+    doubles the strip width, exchanges again, rebuilds, and re-answers only its open rows as
+    external queries against the wider local cloud (the repair round): a halo that is too thin
+    costs a second pass over a few rows instead of an error.
+
+    Returns dict(d2 [n_own, k], nbr_xyz [n_own, k, 3], normals [n_own, 3], rounds, halo)."""
+    import torch
+
+    from . import capi
+
+    n_own = own_xyz.shape[0]
+    inf = float("inf")
+    d2 = torch.empty((n_own, k), dtype=torch.float32, device=own_xyz.device)
+    nbr = torch.empty((n_own, k, 3), dtype=torch.float32, device=own_xyz.device)
+    nrm = torch.empty((n_own, 3), dtype=torch.float32, device=own_xyz.device)
+    open_rows = None
+    rounds = 0
+    width = float(hi) - float(lo)
+    while True:
+        cap = n_own + 16
+        buf = torch.empty((n_own + 2 * cap, 3), dtype=torch.float32, device=own_xyz.device)
+        buf[:n_own].copy_(own_xyz)
+        scratch = HaloScratch(cap, own_xyz.device)
+        local, _ = exchange_halo(buf[:n_own], axis, lo, hi, halo, rank, world, dist, group=group,
+                                 buffer=buf, scratch=scratch)
+        torch.cuda.synchronize()
+        with capi.Index(local, device=device) as ix:
+            if open_rows is None:
+                nl = local.shape[0]
+                idx = torch.empty((nl, k), dtype=torch.int32, device=own_xyz.device)
+                dd = torch.empty((nl, k), dtype=torch.float32, device=own_xyz.device)
+                nn = torch.empty((nl, 3), dtype=torch.float32, device=own_xyz.device)
+                ix.knn(None, k, out_idx=idx, out_d2=dd, out_count=None)
+                ix.estimate_normals(None, k, out=nn)
+                rows = slice(0, n_own)
+                d2.copy_(dd[rows]), nrm.copy_(nn[rows])
+                nbr.copy_(local[idx[rows].long().clamp_(min=0)])
+                check = torch.arange(n_own, device=own_xyz.device)
+            else:
+                q = own_xyz[open_rows].contiguous()
+                m = q.shape[0]
+                idx = torch.empty((max(m, 1), k), dtype=torch.int32, device=own_xyz.device)
+                dd = torch.empty((max(m, 1), k), dtype=torch.float32, device=own_xyz.device)
+                nn = torch.empty((max(m, 1), 3), dtype=torch.float32, device=own_xyz.device)
+                if m:
+                    ix.knn(q, k, out_idx=idx[:m], out_d2=dd[:m], out_count=None)
+                    ix.estimate_normals(q, k, out=nn[:m])
+                    d2[open_rows] = dd[:m]
+                    nrm[open_rows] = nn[:m]
+                    nbr[open_rows] = local[idx[:m].long().clamp_(min=0)]
+                check = open_rows
+        # rows whose k-th neighbour could be beaten by a point beyond the strips
+        c = own_xyz[check, axis].double()
+        reach = d2[check, k - 1].double().sqrt()
+        gap_lo = (c - (lo - halo)) if rank > 0 else torch.full_like(c, inf)
+        gap_hi = ((hi + halo) - c) if rank < world - 1 else torch.full_like(c, inf)
+        bad = ~(reach < torch.minimum(gap_lo, gap_hi))
+        # a strip as wide as the neighbour's whole slab cannot be widened further: the
+        # neighbour's neighbour would have to contribute (not needed for slabs wider than the
+        # k-neighbourhoods, which is what slab mode is for)
+        open_rows = check[bad]
+        flag = torch.tensor([int(open_rows.numel())], device=own_xyz.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        rounds += 1
+        if int(flag.item()) == 0 or rounds >= max_rounds or halo >= width:
+            if int(flag.item()) != 0:
+                raise RuntimeError("slab mode: %d rows still open after %d rounds (halo %g)"
+                                   % (int(flag.item()), rounds, halo))
+            return dict(d2=d2, nbr_xyz=nbr, normals=nrm, rounds=rounds, halo=halo)
+        halo = min(2.0 * halo, width)

@@ -69,3 +69,27 @@ def uniform_cube(n, seed=3, half=100.0):
     (benchmark/spatial_data_structures_benchmark.cpp:381-494)"""
     rng = np.random.default_rng(seed)
     return rng.uniform(-half, half, (n, 3)).astype(np.float32)
+
+
+def scan_slab(n_total, lo_frac, hi_frac, seed=13):
+    """The part of a `scan`-shaped cloud of n_total points whose x lies in
+    [lo_frac, hi_frac) * side, generated without materialising the whole cloud (one rank's share
+    of configs[3]): the height field is sampled directly inside the slab, the sphere's points
+    are drawn in full (5 % of the cloud) and cut.  Same distribution as `scan`, its own sample."""
+    rng = np.random.default_rng([seed, int(lo_frac * 1e6), int(hi_frac * 1e6)])
+    n_sph = n_total // 20
+    n_hf = n_total - n_sph
+    side = 30.0 * np.sqrt(n_total / 1e8) if n_total < 1e8 else 30.0
+    lo, hi = lo_frac * side, hi_frac * side
+    m = int(round(n_hf * (hi_frac - lo_frac)))
+    x = rng.uniform(lo, hi, m)
+    y = rng.uniform(0.0, side, m)
+    z = 0.05 * np.sin(2 * np.pi * x / 5.0) * np.cos(2 * np.pi * y / 5.0) \
+        + 1e-3 * rng.standard_normal(m)
+    hf = np.stack([x, y, z], 1).astype(np.float32)
+    sph = noisy_sphere(n_sph, seed=seed + 1).astype(np.float64) * min(1.0, side / 4.0)
+    sph += np.array([side / 2, side / 2, min(1.0, side / 4.0) + 0.05])
+    sph = sph[(sph[:, 0] >= lo) & (sph[:, 0] < hi)].astype(np.float32)
+    pts = np.concatenate([hf, sph], 0)
+    rng.shuffle(pts, axis=0)
+    return np.ascontiguousarray(pts), side
