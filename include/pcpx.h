@@ -416,6 +416,8 @@ typedef struct pcpx_timings
     float total_ms;     /* whole call on the device incl. H2D / D2H staging */
     uint32_t kernel_launches; /* kernels launched by the last call */
     uint32_t retry_queries;   /* queries that needed the exact tie / expansion slow path */
+    uint32_t deferred_queries; /* kNN-shaped calls: queries the tile pass handed to the per-thread path */
+    uint32_t expanded_queries; /* ... queries that went on to the retry kernel (coarser levels / tree) */
 } pcpx_timings;
 
 int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);

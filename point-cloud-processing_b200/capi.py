@@ -54,6 +54,8 @@ class Timings(C.Structure):
         ("total_ms", C.c_float),
         ("kernel_launches", C.c_uint32),
         ("retry_queries", C.c_uint32),
+        ("deferred_queries", C.c_uint32),
+        ("expanded_queries", C.c_uint32),
     ]
 
 

@@ -389,6 +389,8 @@ int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out)
         if (!out)
             fail(PCPX_ERR_INVALID_ARG, "out is NULL");
         *out = ix.timings;
+        out->deferred_queries = ix.deferred_queries;
+        out->expanded_queries = ix.expanded_queries;
     });
 }
 
@@ -405,6 +407,8 @@ int pcpx_set_tuning(const char* name, double value)
             tuning().tile_alg = (int)value;
         else if (!std::strcmp(name, "tile_first_cap"))
             tuning().tile_first_cap = (int)value;
+        else if (!std::strcmp(name, "tile_min_queries"))
+            tuning().tile_min_queries = (int)value;
         else if (!std::strcmp(name, "tile_sub"))
             tuning().tile_sub = (int)value;
         else if (!std::strcmp(name, "tile_cap"))

@@ -19,15 +19,18 @@ struct pcpx_index
     pcpx::DevBuf<float4> pts;          // n_input entries, Morton order; w = original index
     pcpx::DevBuf<pcpx::HashSlot> table; // all levels
     pcpx::DevBuf<uint8_t> bnd;          // n_indexed entries: coarsest level at which sorted point i opens a new cell
-    pcpx_timings timings{-1.f, -1.f, -1.f, -1.f, -1.f, 0u, 0u};
+    pcpx_timings timings{-1.f, -1.f, -1.f, -1.f, -1.f, 0u, 0u, 0u, 0u};
     std::mutex mtx; // one call at a time per index (calls serialise on `stream`)
     // tile list of one level (query.cu: ensure_tile_list), built on first use and kept:
     // tile_starts[i] = first sorted position of tile i, tile_starts[n_tiles] = n_indexed
     mutable pcpx::DevBuf<uint32_t> tile_starts, tile_count, tile_scratch;
     mutable pcpx::DevBuf<uint64_t> tile_xyz; // tile coordinates (tile_core.cuh: tile_pack)
     mutable uint32_t query_launches = 0; // kernels launched by the last kNN-shaped call
+    mutable uint32_t deferred_queries = 0; // ... queries its tile pass handed to the per-thread path
+    mutable uint32_t expanded_queries = 0; // ... queries that needed the retry kernel (coarser levels)
     mutable int tile_level         = -1;
     mutable uint32_t tile_capacity = 0;
+    mutable uint32_t tile_region   = 0; // staged-region capacity that fits 97 % of the queries' tiles
 
     ~pcpx_index()
     {

@@ -22,7 +22,8 @@ struct Tuning
     // the tile path (tile_core.cuh) for calls whose queries are the indexed points
     int tile           = 1;    // 0: never
     int tile_alg       = 2;    // 1: lock-step scan with sorted insert, 2: candidate list + sorting-network batches
-    int tile_first_cap = 32;   // batched form: candidates listed before the ball is first shrunk (8..64)
+    int tile_first_cap = 0;    // batched form: candidates listed before the ball first shrinks (0: 2 (k + 1))
+    int tile_min_queries = 24; // tiles with fewer points go to the per-thread path unstaged
     int tile_sub       = 2;    // sub-bins per main-level cell along the two in-plane axes (1 or 2)
     float tile_cap     = 1.0f; // largest scan radius in units of the main-level cell
     float tile_margin  = 1.15f; // main level: finest whose ball of one cell side holds margin * (k + 1) points

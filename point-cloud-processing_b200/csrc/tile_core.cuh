@@ -71,6 +71,7 @@ struct TileParams
     float scan_cap;      // largest scan radius, in units of h
     uint32_t first_cap;  // batched form: candidates listed before the ball is first shrunk
     int threads;         // threads of the CTA
+    uint32_t min_queries; // tiles with fewer queries are handed on without staging
 };
 
 template <int S>
@@ -95,6 +96,7 @@ inline TileParams make_tile_params(const GridView& g, int level, uint32_t max_po
     tp.rows_c        = (int)ceilf(scan_cap);
     tp.first_cap     = (uint32_t)kTileCandCap;
     tp.threads       = 96;
+    tp.min_queries   = 0;
     return tp;
 }
 

@@ -172,7 +172,7 @@ def exchange_halo(own_xyz, axis, lo, hi, halo, rank, world, dist, group=None, bu
 
 
 def sharded_self_queries(own_xyz, lo, hi, rank, world, dist, k, halo, device, axis=0,
-                         max_rounds=5, group=None):
+                         max_rounds=8, group=None):
     """Slab mode end to end on CUDA tensors: kNN (distances + neighbour coordinates) and PCA
     normals of the points this rank OWNS, equal to what one index over the whole cloud returns.
 
