@@ -134,22 +134,38 @@ PCPX_HD void smallest_eigenvector_fast(Sym3 m, float& nx, float& ny, float& nz)
         float const st = dp > 1e-12f ? pl / dp : 0.f;
         l              = l - fminf(st, 0.f); // p <= 0 left of the root: steps only ever go right
     }
-    float const r0x = a00 - l, r1y = a11 - l, r2z = a22 - l;
-    // rows r0 = (r0x, a01, a02), r1 = (a01, r1y, a12), r2 = (a02, a12, r2z)
-    float const ax = a01 * a12 - a02 * r1y, ay = a02 * a01 - r0x * a12, az = r0x * r1y - a01 * a01; // r0 x r1
-    float const bx = a01 * r2z - a02 * a12, by = a02 * a02 - r0x * r2z, bz = r0x * a12 - a01 * a02; // r0 x r2
-    float const cx = r1y * r2z - a12 * a12, cy = a12 * a02 - a01 * r2z, cz = a01 * a12 - r1y * a02; // r1 x r2
-    float const na = ax * ax + ay * ay + az * az, nb = bx * bx + by * by + bz * bz,
-                nc = cx * cx + cy * cy + cz * cz;
-    float ex = ax, ey = ay, ez = az, best = na;
-    if (nb > best)
-        ex = bx, ey = by, ez = bz, best = nb;
-    if (nc > best)
-        ex = cx, ey = cy, ez = cz, best = nc;
-    if (!(best > 1e-7f)) // (near-)double eigenvalue, or NaN
+    float ex = 0.f, ey = 0.f, ez = 0.f, best = 0.f;
+    // Two rounds: the root of the cubic is ill-conditioned when l0 and l1 are close (an fp32
+    // error d in p(l) moves the root by d / ((l1 - l0)(l2 - l0))), so the first vector may be
+    // tilted by an angle t; its Rayleigh quotient v^T A v is off by only t^2 (l1 - l0), and the
+    // vector recomputed for THAT value is off by t^2 — the gap cancels.
+#pragma unroll
+    for (int round = 0; round < 2; ++round)
     {
-        smallest_eigenvector(m, nx, ny, nz, nullptr);
-        return;
+        if (round == 1)
+        {
+            float const nrm2 = 1.f / best;
+            float const wx = a00 * ex + a01 * ey + a02 * ez, wy = a01 * ex + a11 * ey + a12 * ez,
+                        wz = a02 * ex + a12 * ey + a22 * ez;
+            l = (ex * wx + ey * wy + ez * wz) * nrm2;
+        }
+        float const r0x = a00 - l, r1y = a11 - l, r2z = a22 - l;
+        // rows r0 = (r0x, a01, a02), r1 = (a01, r1y, a12), r2 = (a02, a12, r2z)
+        float const ax = a01 * a12 - a02 * r1y, ay = a02 * a01 - r0x * a12, az = r0x * r1y - a01 * a01; // r0 x r1
+        float const bx = a01 * r2z - a02 * a12, by = a02 * a02 - r0x * r2z, bz = r0x * a12 - a01 * a02; // r0 x r2
+        float const cx = r1y * r2z - a12 * a12, cy = a12 * a02 - a01 * r2z, cz = a01 * a12 - r1y * a02; // r1 x r2
+        float const na = ax * ax + ay * ay + az * az, nb = bx * bx + by * by + bz * bz,
+                    nc = cx * cx + cy * cy + cz * cz;
+        ex = ax, ey = ay, ez = az, best = na;
+        if (nb > best)
+            ex = bx, ey = by, ez = bz, best = nb;
+        if (nc > best)
+            ex = cx, ey = cy, ez = cz, best = nc;
+        if (!(best > 1e-7f)) // (near-)double eigenvalue, or NaN
+        {
+            smallest_eigenvector(m, nx, ny, nz, nullptr);
+            return;
+        }
     }
 #ifdef __CUDA_ARCH__
     float const nrm = rsqrtf(best);

@@ -124,3 +124,57 @@ def test_tile_against_reference_fixtures(emu, name):
         got = r["idx"].astype(np.int64)
         assert np.array_equal(got[d], want[d]), (name, k)
         assert np.array_equal(r["d2"][d], wd2[d]), (name, k)
+
+
+def test_closed_form_eigenvector(emu):
+    """eig3.cuh: smallest_eigenvector_fast (what the tile kernel's normal epilogue runs) against
+    numpy.linalg.eigh in float64 on scatter matrices of planar, tilted and isotropic
+    neighbourhoods and on matrices with a prescribed small eigengap: 1 - |cos| <= 1e-5 wherever
+    the relative gap exceeds 1e-3 (the north star's tolerance is 1e-4)."""
+    import ctypes as C
+
+    f32p = C.POINTER(C.c_float)
+    emu.L.emu_smallest_eigenvector_fast.argtypes = [f32p, C.c_size_t, f32p]
+    rng = np.random.default_rng(0)
+
+    def run(c6):
+        c = np.ascontiguousarray(c6, np.float32)
+        out = np.zeros((len(c), 3), np.float32)
+        emu.L.emu_smallest_eigenvector_fast(c.ctypes.data_as(f32p), len(c), out.ctypes.data_as(f32p))
+        return out.astype(np.float64)
+
+    def check(c6, tol):
+        c6 = np.asarray(c6, np.float32)
+        A = np.zeros((len(c6), 3, 3))
+        A[:, 0, 0], A[:, 0, 1], A[:, 0, 2] = c6[:, 0], c6[:, 1], c6[:, 2]
+        A[:, 1, 1], A[:, 1, 2], A[:, 2, 2] = c6[:, 3], c6[:, 4], c6[:, 5]
+        A[:, 1, 0], A[:, 2, 0], A[:, 2, 1] = A[:, 0, 1], A[:, 0, 2], A[:, 1, 2]
+        w, v = np.linalg.eigh(A)
+        got = run(c6)
+        assert np.all(np.abs(np.linalg.norm(got, axis=1) - 1) < 1e-5)
+        well = (w[:, 1] - w[:, 0]) / np.maximum(w[:, 2], 1e-300) > 1e-3
+        err = 1 - np.abs((got * v[:, :, 0]).sum(1))
+        assert err[well].max() <= tol, err[well].max()
+
+    def scatter(P):
+        V = (P - P.mean(0)).astype(np.float32)
+        S = V.T @ V
+        return [S[0, 0], S[0, 1], S[0, 2], S[1, 1], S[1, 2], S[2, 2]]
+
+    cases = []
+    for _ in range(4000):
+        flat = np.c_[rng.uniform(-7e-3, 7e-3, (15, 2)), 1e-3 * rng.standard_normal(15)]
+        q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        cases += [scatter(flat), scatter(flat @ q + 5.0), scatter(rng.standard_normal((15, 3)))]
+    check(cases, 1e-5)
+    for gap in (1e-2, 3e-3, 1.05e-3):
+        cases = []
+        for _ in range(4000):
+            q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+            l0 = rng.uniform(0.0, 0.3)
+            S = (q * np.array([l0, l0 + gap, 1.0])) @ q.T
+            cases.append([S[0, 0], S[0, 1], S[0, 2], S[1, 1], S[1, 2], S[2, 2]])
+        check(cases, 1e-5)
+    # degenerate inputs give a unit vector, never NaN
+    got = run([[0, 0, 0, 0, 0, 0], [1, 0, 0, 1, 0, 1], [1, 0, 0, 0, 0, 0], [2, 0, 0, 2, 0, 0]])
+    assert np.all(np.isfinite(got)) and np.allclose(np.linalg.norm(got, axis=1), 1, atol=1e-5)
