@@ -425,12 +425,21 @@ int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
 /* Process-wide tunables (performance only, never results).  Known names:
  *   "success_margin"  a kNN-shaped call first tries the cheapest (level, rings) block whose ball
  *                     is expected to hold success_margin * (k + 1) points (default 1.15).
+ *   "pool_cap_mb"     cap of the per-device cache of freed device blocks, in MiB (default 1024).
  *   "tile"            1 (default): calls whose queries are the indexed points themselves take the
  *                     tile-cooperative kernel (shared-memory staged candidates); 0: never.
  *   "tile_sub"        sub-bins per cell of the tile kernel's local grid, 1 or 2 (default 2).
  *   "tile_cap"        largest scan radius of the tile kernel in cell sides (default 1).
  *   "tile_margin"     like success_margin, for the tile kernel's level (default 1.15). */
 int pcpx_set_tuning(const char* name, double value);
+
+/* Device memory the library keeps for reuse.  Temporaries and destroyed indices go back to a
+ * per-device cache (cudaMalloc / cudaFree synchronise the device and cost up to milliseconds);
+ * the cache is capped — 1 GiB per device by default, PCPX_POOL_CAP_MB in the environment or
+ * pcpx_set_tuning("pool_cap_mb", x) — and blocks beyond the cap are returned to the driver at
+ * once.  pcpx_trim(device) waits for the device to go idle and frees the whole cache, for
+ * applications that share the GPU with other allocators. */
+int pcpx_trim(int device);
 
 /* Search work of a self-kNN over the whole cloud, summed over queries:
  * out4 = { candidate distance evaluations, cell-table lookups, levels tried,

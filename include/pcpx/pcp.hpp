@@ -107,6 +107,37 @@ class basic_point_view_t
 };
 using point_view_t = basic_point_view_t<point_t>;
 
+// common/points/vertex.hpp:30-117: a point view that also carries a 64-bit identifier (the
+// GraphVertex concept of the reference: id() / id(value)); equality is equality of identifiers.
+template <class PointView>
+class basic_point_view_vertex_t : public basic_point_view_t<PointView>
+{
+  public:
+    using id_type     = std::uint64_t;
+    using self_type   = basic_point_view_vertex_t<PointView>;
+    using point_type  = basic_point_view_t<PointView>;
+    using parent_type = point_type;
+
+    id_type id() const { return id_; }
+    void id(id_type value) { id_ = value; }
+
+    basic_point_view_vertex_t()                 = default;
+    basic_point_view_vertex_t(self_type const&) = default;
+    basic_point_view_vertex_t(self_type&&)      = default;
+    self_type& operator=(self_type const&) = default;
+    self_type& operator=(self_type&&) = default;
+    explicit basic_point_view_vertex_t(PointView* point) : parent_type(point), id_(0u) {}
+    explicit basic_point_view_vertex_t(id_type id) : parent_type(), id_(id) {}
+    explicit basic_point_view_vertex_t(PointView* point, id_type id) : parent_type(point), id_(id) {}
+
+    bool operator==(self_type const& other) const { return id_ == other.id_; }
+    bool operator!=(self_type const& other) const { return id_ != other.id_; }
+
+  private:
+    id_type id_ = 0u;
+};
+using vertex_t = basic_point_view_vertex_t<point_t>;
+
 template <class T>
 struct basic_normal_t
 {
@@ -456,18 +487,49 @@ class basic_linked_octree_t : public device_spatial_index<Element>
 
     basic_linked_octree_t(basic_linked_octree_t&&) = default;
 
+    // octree/linked_octree.hpp:71: an empty octree over a given voxel grid, filled by insert()
+    explicit basic_linked_octree_t(params_type const& params) : params_(params), has_params_(true) {}
+
+    // octree/linked_octree.hpp:179-206.  The device index is immutable, so an insertion rebuilds
+    // it over everything inserted so far (a few ms per 10 M points): insert ranges, not single
+    // elements in a loop.  Like the reference, elements outside the voxel grid are rejected
+    // (octree/linked_octree_node.hpp:174) and not counted.
+    template <class ForwardIter, class PointViewMap>
+    std::size_t insert(ForwardIter begin, ForwardIter end, PointViewMap const& point_view)
+    {
+        std::vector<element_type> all = this->elements_;
+        std::size_t inserted          = 0;
+        for (auto it = begin; it != end; ++it)
+            if (!has_params_ || params_.voxel_grid.contains(point_view(*it)))
+            {
+                all.push_back(*it);
+                ++inserted;
+            }
+        if (inserted)
+        {
+            pcpx_index_params prm{};
+            prm.device = -1;
+            if (has_params_)
+                set_voxel_grid(prm, params_);
+            construct(all.begin(), all.end(), point_view, prm);
+        }
+        return inserted;
+    }
+    template <class PointViewMap>
+    bool insert(element_type const& e, PointViewMap const& point_view)
+    {
+        return insert(&e, &e + 1, point_view) == 1u;
+    }
+
     // octree/linked_octree.hpp:83-91: explicit voxel grid — elements outside it are not indexed
     template <class ForwardIter, class PointViewMap>
     explicit basic_linked_octree_t(ForwardIter begin, ForwardIter end,
                                    PointViewMap const& point_view, params_type const& params)
     {
         pcpx_index_params prm{};
-        prm.device         = -1;
-        prm.use_voxel_grid = 1;
-        prm.voxel_min[0] = params.voxel_grid.min.x(), prm.voxel_min[1] = params.voxel_grid.min.y(),
-        prm.voxel_min[2] = params.voxel_grid.min.z();
-        prm.voxel_max[0] = params.voxel_grid.max.x(), prm.voxel_max[1] = params.voxel_grid.max.y(),
-        prm.voxel_max[2] = params.voxel_grid.max.z();
+        prm.device = -1;
+        set_voxel_grid(prm, params);
+        params_ = params, has_params_ = true;
         construct(begin, end, point_view, prm);
     }
 
@@ -532,7 +594,15 @@ class basic_linked_octree_t : public device_spatial_index<Element>
                     hy = 0.5f * (range.max.y() - range.min.y()),
                     hz = 0.5f * (range.max.z() - range.min.z());
         std::vector<float> c{range.min.x() + hx, range.min.y() + hy, range.min.z() + hz};
-        std::vector<float> r{std::sqrt(hx * hx + hy * hy + hz * hz) * 1.0001f + 1e-30f};
+        // the centre is rounded to fp32 (up to half an ulp of its magnitude per axis) and the
+        // device evaluates fp32 distances: absolute slack of a few ulps of the largest
+        // coordinate on top of the relative margin, so that a small box far from the origin
+        // still sees the points in its corners
+        float const big = std::max({std::fabs(range.min.x()), std::fabs(range.max.x()),
+                                    std::fabs(range.min.y()), std::fabs(range.max.y()),
+                                    std::fabs(range.min.z()), std::fabs(range.max.z())});
+        std::vector<float> r{std::sqrt(hx * hx + hy * hy + hz * hz) * 1.0001f + 8.f * 1.1920929e-7f * big +
+                             1e-30f};
         std::vector<std::uint64_t> off;
         std::vector<std::uint32_t> idx;
         this->radius_batch(c, r, off, idx);
@@ -558,6 +628,18 @@ class basic_linked_octree_t : public device_spatial_index<Element>
     }
 
   private:
+    static void set_voxel_grid(pcpx_index_params& prm, params_type const& params)
+    {
+        prm.use_voxel_grid = 1;
+        prm.voxel_min[0] = params.voxel_grid.min.x(), prm.voxel_min[1] = params.voxel_grid.min.y(),
+        prm.voxel_min[2] = params.voxel_grid.min.z();
+        prm.voxel_max[0] = params.voxel_grid.max.x(), prm.voxel_max[1] = params.voxel_grid.max.y(),
+        prm.voxel_max[2] = params.voxel_grid.max.z();
+    }
+
+    params_type params_{};
+    bool has_params_ = false;
+
     template <class ForwardIter, class PointViewMap>
     void construct(ForwardIter begin, ForwardIter end, PointViewMap const& point_view,
                    pcpx_index_params const& prm)
@@ -641,7 +723,12 @@ class basic_linked_kdtree_t : public device_spatial_index<Element>
             c[a] = static_cast<float>(range.min[a]) + h[a];
         }
         std::vector<float> cc{c[0], c[1], c[2]};
-        std::vector<float> r{std::sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]) * 1.0001f + 1e-30f};
+        float big = 0.f; // see the octree's box overload: slack for the rounded centre
+        for (int a = 0; a < 3; ++a)
+            big = std::max({big, std::fabs(static_cast<float>(range.min[a])),
+                            std::fabs(static_cast<float>(range.max[a]))});
+        std::vector<float> r{std::sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]) * 1.0001f +
+                             8.f * 1.1920929e-7f * big + 1e-30f};
         std::vector<std::uint64_t> off;
         std::vector<std::uint32_t> idx;
         this->radius_batch(cc, r, off, idx);

@@ -103,6 +103,7 @@ _SIGNATURES = {
                                      C.c_void_p]),
     "pcpx_last_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "pcpx_set_tuning": (C.c_int, [C.c_char_p, C.c_double]),
+    "pcpx_trim": (C.c_int, [C.c_int]),
     "pcpx_debug_knn_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]),
 }
 
@@ -138,6 +139,11 @@ def _check(rc):
 
 def device_count():
     return lib().pcpx_device_count()
+
+
+def trim(device=0):
+    """free the library's cache of device blocks on `device` (after the device went idle)"""
+    _check(lib().pcpx_trim(int(device)))
 
 
 def set_tuning(name, value):

@@ -401,6 +401,8 @@ int pcpx_set_tuning(const char* name, double value)
             fail(PCPX_ERR_INVALID_ARG, "name is NULL");
         if (!std::strcmp(name, "success_margin"))
             tuning().success_margin = (float)value;
+        else if (!std::strcmp(name, "pool_cap_mb"))
+            DevicePool::instance().set_cap((size_t)std::max(0.0, value) << 20);
         else if (!std::strcmp(name, "tile"))
             tuning().tile = (int)value;
         else if (!std::strcmp(name, "tile_alg"))
@@ -417,6 +419,19 @@ int pcpx_set_tuning(const char* name, double value)
             tuning().tile_margin = (float)value;
         else
             fail(PCPX_ERR_INVALID_ARG, "unknown tuning parameter '%s'", name);
+    });
+}
+
+int pcpx_trim(int device)
+{
+    return guarded([&] {
+        int n = 0;
+        PCPX_CUDA(cudaGetDeviceCount(&n));
+        if (device < 0 || device >= n)
+            fail(PCPX_ERR_INVALID_ARG, "device %d out of range", device);
+        ScopedDevice guard(device);
+        PCPX_CUDA(cudaDeviceSynchronize());
+        DevicePool::instance().trim(device);
     });
 }
 

@@ -145,6 +145,9 @@ int guarded(F&& f)
     }
     catch (Error const& e)
     {
+        // the call's buffers went back to the pool while unwinding: nothing that was already
+        // submitted may still be using them when another thread takes them
+        cudaDeviceSynchronize();
         last_error_storage() = e.msg;
         return e.code;
     }

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -84,6 +85,7 @@ class DevicePool
             {
                 void* p = best->second;
                 size_[p] = best->first;
+                cached_[dev] -= best->first;
                 fl.erase(best);
                 return p;
             }
@@ -104,18 +106,60 @@ class DevicePool
         dev_[p]  = dev;
         return p;
     }
+    // A freed block is kept for reuse only while the device's cache stays under its cap
+    // (default 1 GiB, PCPX_POOL_CAP_MB / pcpx_set_tuning("pool_cap_mb")): the smallest cached
+    // blocks are returned to the driver until the newcomer fits, and a block larger than the cap
+    // itself goes straight back — a destroyed 100 M-point index does not stay resident.
     void release(void* p)
     {
         if (!p)
             return;
-        std::lock_guard<std::mutex> lock(m_);
-        auto it = size_.find(p);
-        if (it == size_.end())
+        std::multimap<size_t, void*> drop;
         {
-            cudaFree(p);
-            return;
+            std::lock_guard<std::mutex> lock(m_);
+            auto it = size_.find(p);
+            if (it == size_.end())
+            {
+                drop.emplace(0, p);
+            }
+            else
+            {
+                int const dev      = dev_[p];
+                size_t const bytes = it->second;
+                auto& fl           = free_[dev];
+                size_t& cached     = cached_[dev];
+                if (bytes > cap_)
+                {
+                    size_.erase(p), dev_.erase(p);
+                    drop.emplace(bytes, p);
+                }
+                else
+                {
+                    while (cached + bytes > cap_ && !fl.empty())
+                    {
+                        auto victim = fl.begin(); // smallest first: large blocks are the costly ones to re-allocate
+                        cached -= victim->first;
+                        size_.erase(victim->second), dev_.erase(victim->second);
+                        drop.insert(*victim);
+                        fl.erase(victim);
+                    }
+                    fl.emplace(bytes, p);
+                    cached += bytes;
+                }
+            }
         }
-        free_[dev_[p]].emplace(it->second, p);
+        for (auto& b : drop)
+            cudaFree(b.second);
+    }
+    void set_cap(size_t bytes)
+    {
+        std::lock_guard<std::mutex> lock(m_);
+        cap_ = bytes;
+    }
+    size_t cached_bytes(int dev)
+    {
+        std::lock_guard<std::mutex> lock(m_);
+        return cached_[dev];
     }
     // hand a block over to the caller (it will be freed with cudaFree by pcpx_free)
     void forget(void* p)
@@ -130,6 +174,7 @@ class DevicePool
         {
             std::lock_guard<std::mutex> lock(m_);
             blocks.swap(free_[dev]);
+            cached_[dev] = 0;
             for (auto& b : blocks)
                 size_.erase(b.second), dev_.erase(b.second);
         }
@@ -138,7 +183,14 @@ class DevicePool
     }
 
   private:
+    DevicePool()
+    {
+        if (const char* e = std::getenv("PCPX_POOL_CAP_MB"))
+            cap_ = (size_t)std::strtoull(e, nullptr, 10) << 20;
+    }
     std::mutex m_;
+    size_t cap_ = (size_t)1 << 30;
+    std::map<int, size_t> cached_;
     std::map<int, std::multimap<size_t, void*>> free_;
     std::map<void*, size_t> size_;
     std::map<void*, int> dev_;

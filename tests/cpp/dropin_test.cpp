@@ -132,6 +132,46 @@ static void octree_range_scenarios()
     REQUIRE(in.size() == 2u && has({-.5f, -.5f, -.5f}) && has({-.4f, -.3f, -.6f}));
 }
 
+// octree/linked_octree.hpp:71,179-206 (empty octree + insert), test/octree/octree_insertion.cpp;
+// common/points/vertex.hpp; and a small box far from the origin (the circumscribed-sphere
+// pre-filter must not lose the points in its corners to the rounding of its centre)
+static void insertion_vertex_and_far_box_scenarios()
+{
+    pcp::linked_octree_t octree(unit_params(1.f));
+    REQUIRE(octree.size() == 0u);
+    std::vector<pcp::point_t> inside{{.1f, .2f, .3f}, {-.5f, .5f, .9f}, {1.f, -1.f, 1.f}},
+        outside{{1.1f, 0.f, 0.f}, {0.f, -1.5f, 0.f}};
+    REQUIRE(octree.insert(inside.begin(), inside.end(), point_map) == 3u);
+    REQUIRE(octree.insert(outside.begin(), outside.end(), point_map) == 0u);
+    REQUIRE(!octree.insert(pcp::point_t{2.f, 2.f, 2.f}, point_map));
+    REQUIRE(octree.insert(pcp::point_t{.11f, .2f, .3f}, point_map));
+    REQUIRE(octree.size() == 4u);
+    auto nn = octree.nearest_neighbours(pcp::point_t{.1f, .2f, .3f}, 1u, point_map);
+    REQUIRE(nn.size() == 1u && pcp::common::are_vectors_equal(nn[0], pcp::point_t{.11f, .2f, .3f}));
+
+    std::vector<pcp::point_t> cloud{{0.f, 0.f, 0.f}, {1.f, 2.f, 3.f}};
+    pcp::vertex_t v0(&cloud[0], 0u), v1(&cloud[1], 7u), v1b(&cloud[0], 7u);
+    REQUIRE(v1.id() == 7u && v1.x() == 1.f && v1.z() == 3.f && v0 != v1 && v1 == v1b);
+    v0.id(9u);
+    v0.y(5.f);
+    REQUIRE(v0.id() == 9u && cloud[0].y() == 5.f);
+
+    // 9 x 9 x 9 lattice, spacing 1e-4, near x = y = z = 100; the box holds a 5 x 5 x 5 sub-lattice
+    std::vector<pcp::point_t> far;
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j)
+            for (int l = 0; l < 9; ++l)
+                far.push_back({100.f + 1e-4f * i, 100.f + 1e-4f * j, 100.f + 1e-4f * l});
+    pcp::linked_octree_t foct(far.cbegin(), far.cend(), point_map);
+    pcp::axis_aligned_bounding_box_t<pcp::point_t> box;
+    box.min = far[(2 * 9 + 2) * 9 + 2], box.max = far[(6 * 9 + 6) * 9 + 6];
+    std::size_t want = 0;
+    for (auto const& p : far)
+        want += box.contains(p);
+    REQUIRE(want >= 125u);
+    REQUIRE(foct.range_search(box, point_map).size() == want);
+}
+
 static void kdtree_scenarios()
 {
     auto const coordinate_map = [](pcp::point_t const& p) {
@@ -461,6 +501,7 @@ int main()
     }
     octree_knn_scenarios();
     octree_range_scenarios();
+    insertion_vertex_and_far_box_scenarios();
     kdtree_scenarios();
     normals_scenarios();
     smoothing_scenarios();
