@@ -428,7 +428,11 @@ int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
  *   "pool_cap_mb"     cap of the per-device cache of freed device blocks, in MiB (default 1024).
  *   "tile"            1 (default): calls whose queries are the indexed points themselves take the
  *                     tile-cooperative kernel (shared-memory staged candidates); 0: never.
- *   "tile_sub"        sub-bins per cell of the tile kernel's local grid, 1 or 2 (default 2).
+ *   "tile_sub"        staged layout of the tile kernel: 1 = whole cells, 2 = 2 x 2 sub-bins per
+ *                     cell, 4 = 4 x 1 sub-bins (default; staged in one pass).
+ *   "warp_retry"      1 (default): queries the first pass hands on are answered one warp per query
+ *                     (octree descent, exact 64-bit keys); 0: per-thread retry kernels.
+ *   "warp_all"        1: every kNN-shaped query takes the warp-per-query search (tests).
  *   "tile_cap"        largest scan radius of the tile kernel in cell sides (default 1).
  *   "tile_margin"     like success_margin, for the tile kernel's level (default 1.15). */
 int pcpx_set_tuning(const char* name, double value);

@@ -405,8 +405,10 @@ int pcpx_set_tuning(const char* name, double value)
             DevicePool::instance().set_cap((size_t)std::max(0.0, value) << 20);
         else if (!std::strcmp(name, "tile"))
             tuning().tile = (int)value;
-        else if (!std::strcmp(name, "tile_alg"))
-            tuning().tile_alg = (int)value;
+        else if (!std::strcmp(name, "warp_retry"))
+            tuning().warp_retry = (int)value;
+        else if (!std::strcmp(name, "warp_all"))
+            tuning().warp_all = (int)value;
         else if (!std::strcmp(name, "tile_first_cap"))
             tuning().tile_first_cap = (int)value;
         else if (!std::strcmp(name, "tile_min_queries"))

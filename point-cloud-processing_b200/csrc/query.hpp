@@ -21,11 +21,12 @@ struct Tuning
     int block_threads  = 128;
     // the tile path (tile_core.cuh) for calls whose queries are the indexed points
     int tile           = 1;    // 0: never
-    int tile_alg       = 2;    // 1: lock-step scan with sorted insert, 2: candidate list + sorting-network batches
     int tile_first_cap = 0;    // batched form: candidates listed before the ball first shrinks (0: 2 (k + 1))
     int tile_min_queries = 24; // tiles with fewer points go to the per-thread path unstaged
-    int tile_sub       = 2;    // sub-bins per main-level cell along the two in-plane axes (1 or 2)
+    int tile_sub       = 2;    // staged layout: 1 = whole cells, 2 = 2 x 2 sub-bins per cell, 4 = 4 x 1; 1 and 4 are staged in one pass
     float tile_cap     = 1.0f; // largest scan radius in units of the main-level cell
+    int warp_retry     = 1;    // what the first pass hands on: 1 = one warp per query (warp_core.cuh), 0 = per-thread retry kernels
+    int warp_all       = 0;    // (tests) every kNN-shaped query by the warp-per-query search
     float tile_margin  = 1.15f; // main level: finest whose ball of one cell side holds margin * (k + 1) points
 };
 Tuning& tuning();

@@ -7,17 +7,23 @@
 // level, i.e. 4x4x4 main-level cells, a contiguous run of the sorted point array — and does the
 // structure work ONCE per tile:
 //
-//   1. 64 table lookups (the 4x4x4 cells one level above the main level that cover the tile plus
-//      one main-level cell of halo on every side) give the spans of every point a tile query can
-//      need;
-//   2. those points are copied into shared memory RE-BINNED into a dense local grid: S x S
-//      sub-bins per main-level cell along two axes (a, b), whole cells along the third (c = the
-//      axis along which the tile's neighbourhood is thinnest), rows along a contiguous — so the
+//   1. 216 table lookups (the 6x6x6 main-level cells: the tile plus one cell of halo on every
+//      side) give the spans of every point a tile query can need;
+//   2. those points are copied into shared memory RE-BINNED into a dense local grid: SA sub-bins
+//      per main-level cell along a, SB along b, whole cells along the third axis (c = the axis
+//      along which the tile's neighbourhood is thinnest), rows along a contiguous — so the
 //      candidates of a query are a handful of contiguous shared-memory ranges, found by two
 //      loads from a 864-entry start table instead of hash probes;
-//   3. one thread per query scans, row by row, only the bins its current search ball touches
-//      (a disc, not a box; the ball shrinks as soon as the list is full), with broadcast /
-//      near-broadcast shared-memory loads, no local memory and no per-thread lists.
+//   3. one thread per query lists, row by row, only the bins its current search ball touches
+//      (a disc, not a box; the ball shrinks as soon as the list is full) and selects the k
+//      nearest with sorting-network batches: no local memory, no per-thread span lists.
+//
+// Layouts (template parameter S): 1 = whole cells (1 x 1), 2 = 2 x 2 sub-bins, 4 = 4 x 1 (four
+// sub-bins along the row axis, whole cells along b).  When SB == 1 a row of bins is a row of
+// CELLS, so the start of every cell in the staged array follows from the cell counts alone: the
+// staging is ONE pass over global memory (a warp per occupied cell, its points ranked into the
+// cell's sub-bins by ballots) instead of count -> scan -> place, and the row table and the query
+// segments are known before a single point has been loaded.
 //
 // The top-k list is KL (>= k + 1) 32-bit keys in registers: (bits(d2) & ~mask) | staged position.
 // d2 >= 0, so unsigned order of the bits is the fp32 order; the low `mask` bits are replaced by
@@ -51,8 +57,14 @@ constexpr uint32_t kNoSelf    = 0xFFFFFFFFu;
 template <int S>
 struct TileDims
 {
-    static constexpr int na = kRegionCells * S, nb = kRegionCells * S, nc = kRegionCells;
+    static_assert(S == 1 || S == 2 || S == 4, "layouts: 1 (1 x 1), 2 (2 x 2), 4 (4 x 1)");
+    static constexpr int SA = S, SB = S == 4 ? 1 : S; // sub-bins per cell along a / along b
+    static constexpr int sub = SA * SB;
+    static constexpr int na = kRegionCells * SA, nb = kRegionCells * SB, nc = kRegionCells;
     static constexpr int bins = na * nb * nc;
+    // rows (fixed b bin and c cell) that hold the tile's own points, i.e. the queries
+    static constexpr int segs = kTileCells * kTileCells * SB;
+    static constexpr bool one_pass = SB == 1;
 };
 
 // per call, computed on the host (make_tile_params)
@@ -63,13 +75,16 @@ struct TileParams
     uint32_t max_points; // capacity of the staged region
     uint32_t key_mask;   // low key bits that carry the staged position
     float h;             // cell side at L
-    float bins_per_len;  // S * 2^L / extent
-    float len_per_bin;   // h / S
+    float bins_per_len;  // SA * 2^L / extent
+    float len_per_bin;   // h / SA
+    float bins_per_len_b; // SB * 2^L / extent
+    float len_per_bin_b; // h / SB
     float cells_per_len; // 2^L / extent
-    float delta_bins;    // g.delta in (a, b) bin units: slack of every float-evaluated bin bound
+    float delta_bins;    // g.delta in a bin units: slack of every float-evaluated bin bound
+    float delta_bins_b;  // ... in b bin units
     float delta_cells;   // g.delta in cell units
     float scan_cap;      // largest scan radius, in units of h
-    uint32_t first_cap;  // batched form: candidates listed before the ball is first shrunk
+    uint32_t first_cap;  // candidates listed before the ball is first shrunk
     int threads;         // threads of the CTA
     uint32_t min_queries; // tiles with fewer queries are handed on without staging
 };
@@ -78,6 +93,7 @@ template <int S>
 inline TileParams make_tile_params(const GridView& g, int level, uint32_t max_points,
                                    float scan_cap)
 {
+    using D = TileDims<S>;
     TileParams tp;
     tp.level         = level;
     tp.max_points    = max_points;
@@ -87,12 +103,15 @@ inline TileParams make_tile_params(const GridView& g, int level, uint32_t max_po
     tp.key_mask      = (1u << bits) - 1u;
     tp.h             = ldexpf(g.extent, -level);
     tp.cells_per_len = ldexpf(1.f, level) / g.extent;
-    tp.bins_per_len  = tp.cells_per_len * (float)S;
-    tp.len_per_bin   = tp.h / (float)S;
+    tp.bins_per_len  = tp.cells_per_len * (float)D::SA;
+    tp.len_per_bin   = tp.h / (float)D::SA;
+    tp.bins_per_len_b = tp.cells_per_len * (float)D::SB;
+    tp.len_per_bin_b = tp.h / (float)D::SB;
     tp.delta_bins    = g.delta * tp.bins_per_len * 1.5f + 1e-6f;
+    tp.delta_bins_b  = g.delta * tp.bins_per_len_b * 1.5f + 1e-6f;
     tp.delta_cells   = g.delta * tp.cells_per_len * 1.5f + 1e-6f;
     tp.scan_cap      = scan_cap;
-    tp.rows_b        = (int)ceilf(scan_cap * (float)S);
+    tp.rows_b        = (int)ceilf(scan_cap * (float)D::SB);
     tp.rows_c        = (int)ceilf(scan_cap);
     tp.first_cap     = (uint32_t)kTileCandCap;
     tp.threads       = 96;
@@ -100,7 +119,7 @@ inline TileParams make_tile_params(const GridView& g, int level, uint32_t max_po
     return tp;
 }
 
-// per tile, written by one thread (tile_plan)
+// per tile, written by one thread (tile_phase_plan)
 struct TileGeom
 {
     int32_t r0[3];      // region origin in main-level cells along a, b, c (may be -1)
@@ -119,10 +138,8 @@ struct TileSmem
     uint32_t* ccount;     // kRegionCellCount: ... cell id = (z * 6 + y) * 6 + x, world axes
     uint8_t* occ;         // kRegionCellCount: ids of the cells that hold points, ascending
     TileGeom* geom;
-    // the batched form of the search (tile_list_candidates / tile_select)
     uint32_t* rowmask;    // nc words: bit ib of word ic = row (ic, ib) holds points
-    uint32_t* seg_off;    // kTileCells * kTileCells * S + 1: prefix over the tile's row segments
-    uint16_t* qlist;      // staged positions of the tile's own points (the queries), bin order
+    uint32_t* seg_off;    // segs + 1: prefix over the tile's own row segments (the queries)
     uint16_t* cl;         // kTileCandCap x nthreads candidate positions, [j * nthreads + tid]
     uint32_t* gpos;       // max_points: position of every staged point in the sorted global array
 };
@@ -141,18 +158,10 @@ PCPX_HD int32_t axis_of_i(int32_t x, int32_t y, int32_t z, int ax)
 {
     return ax == 0 ? x : (ax == 1 ? y : z);
 }
-
-// Fine coordinate with S steps per finest cell.  (x - o) * (scale * 2) == 2 * ((x - o) * scale)
-// exactly, so quantise_sub<2>(x) >> 1 == quantise(x): a point's sub-bin always lies inside the cell
-// the index assigned it to.
-template <int S>
-PCPX_HD uint32_t quantise_sub(float x, float o, float scale, int lcap)
+// weight of world axis `ax` in a region cell id ((z * 6 + y) * 6 + x)
+PCPX_HD int tile_axis_weight(int ax)
 {
-    float t = (x - o) * (scale * (float)S);
-    t       = t > 0.f ? t : 0.f;
-    float m = (float)(((1u << lcap) * (uint32_t)S) - 1u);
-    t       = t < m ? t : m;
-    return (uint32_t)t;
+    return ax == 0 ? 1 : (ax == 1 ? kRegionCells : kRegionCells * kRegionCells);
 }
 
 // ---- staging phases (a barrier between consecutive phases) -----------------------------------
@@ -160,39 +169,197 @@ PCPX_HD uint32_t quantise_sub(float x, float o, float scale, int lcap)
 //   lookup  one table lookup per region cell (216, main level): the spans of exactly the points a
 //           tile query can need;
 //   plan    the occupied cells compacted (device: ballots by the first warp), the thin axis chosen,
-//           the tile handed on when its region does not fit;
-//   count   one thread per occupied cell: how many of its points fall into each of its S x S
-//           sub-bins (every bin belongs to exactly one cell: plain stores, no atomics);
+//           the tile handed on when its region does not fit.  One-pass layouts (SB == 1): the same
+//           warp goes on to scan the cell counts in (c, b, a) order — F[first bin of a cell] = the
+//           cell's start in the staged array —, and derives the row table and the query segments;
+//   then, one-pass layouts:
+//   place   a warp per occupied cell: loads the cell's points (the loads of four cells in flight
+//           at once), ranks them into the cell's sub-bins by ballots, writes them and the
+//           sub-bin starts;
+//   other layouts:
+//   count   one thread per occupied cell: how many of its points fall into each of its sub-bins
+//           (every bin belongs to exactly one cell: plain stores, no atomics);
 //   scan    inclusive scan of the bin counts: F[i] = start of bin i;
 //   place   the same thread copies its cell's points to their bins in the order of the sorted
-//           array — the staged order is a function of the input alone.
+//           array — the staged order is a function of the input alone;
+//   rows    row table and query segments.
 
-// phase 0: clear the bin table, look up the region cells
+// phase 0: look up the region cells (other layouts: and clear the bin table)
 template <int S>
 PCPX_HD void tile_phase_lookup(const GridView& g, const TileParams& tp, const TileSmem& sm,
                                uint64_t tile_xyz, int tid, int nthreads)
 {
-    for (int i = tid; i <= TileDims<S>::bins; i += nthreads)
-        sm.F[i] = 0u;
-    if (sm.rowmask && tid < TileDims<S>::nc)
-        sm.rowmask[tid] = 0u;
+    if (!TileDims<S>::one_pass)
+    {
+        for (int i = tid; i <= TileDims<S>::bins; i += nthreads)
+            sm.F[i] = 0u;
+        if (tid < TileDims<S>::nc)
+            sm.rowmask[tid] = 0u;
+    }
     int const last = (1 << tp.level) - 1;
     int const x0 = kTileCells * (int)tile_x(tile_xyz) - 1, y0 = kTileCells * (int)tile_y(tile_xyz) - 1,
               z0 = kTileCells * (int)tile_z(tile_xyz) - 1;
-    for (int c = tid; c < kRegionCellCount; c += nthreads)
+    // three cells per thread and round: their first probes are in flight together
+    constexpr int U = 3;
+    for (int c0 = tid; c0 < kRegionCellCount; c0 += nthreads * U)
     {
-        int const cx = x0 + c % kRegionCells, cy = y0 + (c / kRegionCells) % kRegionCells,
-                  cz = z0 + c / (kRegionCells * kRegionCells);
-        uint32_t start = 0, count = 0;
-        if (cx >= 0 && cy >= 0 && cz >= 0 && cx <= last && cy <= last && cz <= last)
-            if (!find_cell(g, cell_key(tp.level, (uint32_t)cx, (uint32_t)cy, (uint32_t)cz), start, count))
-                count = 0;
-        sm.cstart[c] = start;
-        sm.ccount[c] = count;
+        uint32_t slot[U], klo[U], khi[U];
+        HashSlot sl[U];
+        bool in[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            int const c  = c0 + u * nthreads;
+            int const cx = x0 + c % kRegionCells, cy = y0 + (c / kRegionCells) % kRegionCells,
+                      cz = z0 + c / (kRegionCells * kRegionCells);
+            in[u] = c < kRegionCellCount && cx >= 0 && cy >= 0 && cz >= 0 && cx <= last &&
+                    cy <= last && cz <= last;
+            uint64_t const key =
+                cell_key(tp.level, (uint32_t)(in[u] ? cx : 0), (uint32_t)(in[u] ? cy : 0),
+                         (uint32_t)(in[u] ? cz : 0));
+            slot[u] = hash_slot(key, g.table_size);
+            klo[u] = (uint32_t)key, khi[u] = (uint32_t)(key >> 32);
+            if (in[u])
+                sl[u] = load_slot(g.table + slot[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            int const c = c0 + u * nthreads;
+            if (c >= kRegionCellCount)
+                continue;
+            uint32_t start = 0, count = 0;
+            if (in[u])
+                for (;;) // linear probing (find_cell), the first probe already loaded
+                {
+                    if (sl[u].key_hi == khi[u] && sl[u].key_lo == klo[u])
+                    {
+                        start = sl[u].start, count = sl[u].count;
+                        break;
+                    }
+                    if (sl[u].key_hi == kEmptyKeyHi)
+                        break;
+                    slot[u] = slot[u] + 1 == g.table_size ? 0u : slot[u] + 1;
+                    sl[u]   = load_slot(g.table + slot[u]);
+                }
+            sm.cstart[c] = start;
+            sm.ccount[c] = count;
+        }
     }
 }
 
-// phase 1: compact the occupied cells, choose the axes
+// One-pass layouts, first warp (device) / one thread (host), after the plan is written: cell
+// starts, row table, query segments.  F[j * SA + s] = start of cell j (j = (ic * 6 + ib) * 6 + ia)
+// for every sub-bin s; the place phase overwrites s >= 1 of the occupied cells.
+template <int S>
+PCPX_HD void tile_plan_prefix(const TileSmem& sm, int lane)
+{
+    using D = TileDims<S>;
+    TileGeom const tg = *sm.geom;
+    if (tg.fallback != 0)
+        return;
+    int const wa = tile_axis_weight(tg.ax[0]), wb = tile_axis_weight(tg.ax[1]),
+              wc = tile_axis_weight(tg.ax[2]);
+    auto count_of = [&](int j) {
+        int const ia = j % kRegionCells, ib = (j / kRegionCells) % kRegionCells,
+                  ic = j / (kRegionCells * kRegionCells);
+        return sm.ccount[ia * wa + ib * wb + ic * wc];
+    };
+#ifdef __CUDA_ARCH__
+    constexpr int per = (kRegionCellCount + 31) / 32;
+    uint32_t cnt[per], s = 0;
+#pragma unroll
+    for (int i = 0; i < per; ++i)
+    {
+        int const j = lane * per + i;
+        cnt[i]      = j < kRegionCellCount ? count_of(j) : 0u;
+        s += cnt[i];
+    }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t const up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o)
+            incl += up;
+    }
+    uint32_t run = incl - s;
+#pragma unroll
+    for (int i = 0; i < per; ++i)
+    {
+        int const j = lane * per + i;
+        if (j < kRegionCellCount)
+        {
+#pragma unroll
+            for (int q = 0; q < D::SA; ++q)
+                sm.F[j * D::SA + q] = run;
+        }
+        run += cnt[i];
+    }
+    if (lane == 31)
+        sm.F[D::bins] = run;
+    __syncwarp();
+    if (lane < D::nc)
+    {
+        uint32_t m = 0;
+        for (int ib = 0; ib < D::nb; ++ib)
+        {
+            int const r = lane * D::nb + ib;
+            if (sm.F[(r + 1) * D::na] > sm.F[r * D::na])
+                m |= 1u << ib;
+        }
+        sm.rowmask[lane] = m;
+    }
+    {
+        uint32_t len = 0;
+        if (lane < D::segs)
+        {
+            int const base = ((1 + lane / kTileCells) * D::nb + 1 + lane % kTileCells) * D::na;
+            len            = sm.F[base + D::SA + kTileCells * D::SA] - sm.F[base + D::SA];
+        }
+        uint32_t sc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t const up = __shfl_up_sync(0xFFFFFFFFu, sc, o);
+            if (lane >= o)
+                sc += up;
+        }
+        if (lane < D::segs)
+            sm.seg_off[lane] = sc - len;
+        if (lane == D::segs - 1)
+            sm.seg_off[D::segs] = sc;
+    }
+#else
+    (void)lane;
+    uint32_t run = 0;
+    for (int j = 0; j < kRegionCellCount; ++j)
+    {
+        for (int q = 0; q < D::SA; ++q)
+            sm.F[j * D::SA + q] = run;
+        run += count_of(j);
+    }
+    sm.F[D::bins] = run;
+    for (int ic = 0; ic < D::nc; ++ic)
+    {
+        uint32_t m = 0;
+        for (int ib = 0; ib < D::nb; ++ib)
+            if (sm.F[(ic * D::nb + ib + 1) * D::na] > sm.F[(ic * D::nb + ib) * D::na])
+                m |= 1u << ib;
+        sm.rowmask[ic] = m;
+    }
+    uint32_t q = 0;
+    for (int seg = 0; seg < D::segs; ++seg)
+    {
+        int const base  = ((1 + seg / kTileCells) * D::nb + 1 + seg % kTileCells) * D::na;
+        sm.seg_off[seg] = q;
+        q += sm.F[base + D::SA + kTileCells * D::SA] - sm.F[base + D::SA];
+    }
+    sm.seg_off[D::segs] = q;
+#endif
+}
+
+// phase 1: compact the occupied cells, choose the axes (+ tile_plan_prefix)
 template <int S>
 PCPX_HD void tile_phase_plan(const TileParams& tp, const TileSmem& sm, uint64_t tile_xyz, int tid)
 {
@@ -214,8 +381,6 @@ PCPX_HD void tile_phase_plan(const TileParams& tp, const TileSmem& sm, uint64_t 
         occ[1] |= __reduce_or_sync(0xFFFFFFFFu, cnt ? 1u << ((c / kRegionCells) % kRegionCells) : 0u);
         occ[2] |= __reduce_or_sync(0xFFFFFFFFu, cnt ? 1u << (c / (kRegionCells * kRegionCells)) : 0u);
     }
-    if (tid != 0)
-        return;
 #else
     if (tid != 0)
         return;
@@ -230,57 +395,71 @@ PCPX_HD void tile_phase_plan(const TileParams& tp, const TileSmem& sm, uint64_t 
         total += cnt;
     }
 #endif
-    auto pop = [](uint32_t m) {
-        uint32_t r = 0;
-        for (int i = 0; i < kRegionCells; ++i)
-            r += (m >> i) & 1u;
-        return r;
-    };
-    uint32_t const ex = pop(occ[0]), ey = pop(occ[1]), ez = pop(occ[2]);
-    // c = the thinnest axis (ties: z, then y), a = the widest of the other two (ties: the lower)
-    int c = 2;
-    if (ey < ez)
-        c = 1;
-    if (ex < (c == 2 ? ez : ey))
-        c = 0;
-    int a = c == 0 ? 1 : 0, b = c == 2 ? 1 : 2;
-    uint32_t const ea = a == 0 ? ex : ey, eb = b == 1 ? ey : ez;
-    if (eb > ea)
+    if (tid == 0)
     {
-        int const t = a;
-        a = b, b = t;
+        auto pop = [](uint32_t m) {
+            uint32_t r = 0;
+            for (int i = 0; i < kRegionCells; ++i)
+                r += (m >> i) & 1u;
+            return r;
+        };
+        uint32_t const ex = pop(occ[0]), ey = pop(occ[1]), ez = pop(occ[2]);
+        // c = the thinnest axis (ties: z, then y), a = the widest of the other two (ties: the lower)
+        int c = 2;
+        if (ey < ez)
+            c = 1;
+        if (ex < (c == 2 ? ez : ey))
+            c = 0;
+        int a = c == 0 ? 1 : 0, b = c == 2 ? 1 : 2;
+        uint32_t const ea = a == 0 ? ex : ey, eb = b == 1 ? ey : ez;
+        if (eb > ea)
+        {
+            int const t = a;
+            a = b, b = t;
+        }
+        TileGeom& tg = *sm.geom;
+        tg.ax[0] = a, tg.ax[1] = b, tg.ax[2] = c;
+        int32_t const tx = (int32_t)tile_x(tile_xyz), ty = (int32_t)tile_y(tile_xyz),
+                      tz = (int32_t)tile_z(tile_xyz);
+        tg.r0[0] = kTileCells * axis_of_i(tx, ty, tz, a) - 1;
+        tg.r0[1] = kTileCells * axis_of_i(tx, ty, tz, b) - 1;
+        tg.r0[2] = kTileCells * axis_of_i(tx, ty, tz, c) - 1;
+        tg.n_occ    = n;
+        tg.n_points = total;
+        tg.fallback = total > tp.max_points ? 1 : 0;
     }
-    TileGeom& tg = *sm.geom;
-    tg.ax[0] = a, tg.ax[1] = b, tg.ax[2] = c;
-    int32_t const tx = (int32_t)tile_x(tile_xyz), ty = (int32_t)tile_y(tile_xyz),
-                  tz = (int32_t)tile_z(tile_xyz);
-    tg.r0[0] = kTileCells * axis_of_i(tx, ty, tz, a) - 1;
-    tg.r0[1] = kTileCells * axis_of_i(tx, ty, tz, b) - 1;
-    tg.r0[2] = kTileCells * axis_of_i(tx, ty, tz, c) - 1;
-    tg.n_occ    = n;
-    tg.n_points = total;
-    tg.fallback = total > tp.max_points ? 1 : 0;
+    if constexpr (TileDims<S>::one_pass)
+    {
+#ifdef __CUDA_ARCH__
+        __syncwarp();
+#endif
+        tile_plan_prefix<S>(sm, tid);
+    }
 }
 
-// What a thread needs to bin the points of one cell: the first bin of the cell and, for S = 2,
-// which half of the cell a point lies in along a and b.
+// What a thread needs to bin the points of one cell: the first bin of the cell and the sub-bin
+// of a point inside its cell.  (x - o) * (scale * SA) == SA * ((x - o) * scale) exactly (SA a
+// power of two), so a point's sub-bin always lies inside the cell the index assigned it to.
 template <int S>
 struct TileCellBinner
 {
-    float oa, ob, scale_s;
-    uint32_t top;
+    using D = TileDims<S>;
+    float oa, ob, scale_a, scale_b;
+    uint32_t top_a, top_b;
     int sh, A, B;
     int wx, wy, wz; // weight of a cell's world coordinates in its first bin's index
 
     PCPX_HD TileCellBinner(const GridView& g, const TileParams& tp, const TileGeom& tg)
     {
-        using D = TileDims<S>;
         A = tg.ax[0], B = tg.ax[1];
         oa = axis_of(g.ox, g.oy, g.oz, A), ob = axis_of(g.ox, g.oy, g.oz, B);
-        scale_s = g.scale * (float)S;
-        top     = ((1u << g.lcap) * (uint32_t)S) - 1u;
+        scale_a = g.scale * (float)D::SA, scale_b = g.scale * (float)D::SB;
+        top_a   = ((1u << g.lcap) * (uint32_t)D::SA) - 1u;
+        top_b   = ((1u << g.lcap) * (uint32_t)D::SB) - 1u;
         sh      = g.lcap - tp.level;
-        auto weight = [&](int axis) { return A == axis ? S : (B == axis ? S * D::na : D::na * D::nb); };
+        auto weight = [&](int axis) {
+            return A == axis ? D::SA : (B == axis ? D::SB * D::na : D::na * D::nb);
+        };
         wx = weight(0), wy = weight(1), wz = weight(2);
     }
     PCPX_HD int first_bin(int cell) const
@@ -288,28 +467,164 @@ struct TileCellBinner
         return (cell % kRegionCells) * wx + ((cell / kRegionCells) % kRegionCells) * wy +
                (cell / (kRegionCells * kRegionCells)) * wz;
     }
-    PCPX_HD uint32_t half(float x, float o) const // low bit of quantise_sub<2>(x) >> sh
+    PCPX_HD static uint32_t part(float x, float o, float scale, uint32_t top, int sh, uint32_t n)
     {
-        float t = (x - o) * scale_s;
+        float t = (x - o) * scale;
         t       = t > 0.f ? t : 0.f;
         uint32_t u = (uint32_t)t;
         u          = u < top ? u : top;
-        return (u >> sh) & 1u;
+        return (u >> sh) & (n - 1u);
     }
-    // 0 .. 3: sub-bin of a point inside its cell (a half + 2 * b half); 0 when S == 1
-    PCPX_HD uint32_t sub(const float4& p) const
+    PCPX_HD uint32_t sub_a(const float4& p) const
     {
-        if (S == 1)
-            return 0u;
-        return half(axis_of(p.x, p.y, p.z, A), oa) + 2u * half(axis_of(p.x, p.y, p.z, B), ob);
+        return D::SA == 1 ? 0u : part(axis_of(p.x, p.y, p.z, A), oa, scale_a, top_a, sh, D::SA);
+    }
+    PCPX_HD uint32_t sub_b(const float4& p) const
+    {
+        return D::SB == 1 ? 0u : part(axis_of(p.x, p.y, p.z, B), ob, scale_b, top_b, sh, D::SB);
+    }
+    // 0 .. SA * SB - 1: sub-bin of a point inside its cell, a fastest
+    PCPX_HD uint32_t sub(const float4& p) const { return sub_a(p) + (uint32_t)D::SA * sub_b(p); }
+    // offset of sub-bin s from the cell's first bin
+    PCPX_HD static int sub_offset(uint32_t s)
+    {
+        return (int)(s % (uint32_t)D::SA) + (int)(s / (uint32_t)D::SA) * D::na;
     }
 };
 
-// phase 2: bin counts (F[bin + 1] = count), one thread per occupied cell
+// One-pass layouts: the place phase.  Device: warp `warp` of `nwarps` takes the occupied cells
+// warp, warp + nwarps, ...; lane i holds point i of the cell.  Host (one emulated thread at a
+// time): thread tid takes the cells tid, tid + nthreads, ... serially; same staged order.
+template <int S>
+PCPX_HD void tile_phase_place_cells(const GridView& g, const TileParams& tp, const TileSmem& sm,
+                                    int tid, int nthreads)
+{
+    using D = TileDims<S>;
+    static_assert(D::one_pass && D::SA <= 4, "cells are rows of bins");
+    TileGeom const tg = *sm.geom;
+    TileCellBinner<S> const binner(g, tp, tg);
+    if (tid == 0)
+        for (uint32_t j = 0; j < kTilePad; ++j)
+            sm.P[tg.n_points + j] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+#ifdef __CUDA_ARCH__
+    int const lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    uint32_t const lt = (1u << lane) - 1u;
+    constexpr int U   = 4;
+    for (uint32_t j0 = (uint32_t)warp; j0 < tg.n_occ; j0 += (uint32_t)(nwarps * U))
+    {
+        float4 p[U];
+        uint32_t start[U], count[U];
+        int bin[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            uint32_t const j = j0 + (uint32_t)(u * nwarps);
+            count[u]         = 0u;
+            if (j < tg.n_occ)
+            {
+                int const cell = sm.occ[j];
+                start[u] = sm.cstart[cell], count[u] = sm.ccount[cell];
+                bin[u]   = binner.first_bin(cell);
+                if ((uint32_t)lane < count[u])
+                    p[u] = load_pt(g.pts + start[u] + lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            if (count[u] == 0u)
+                continue;
+            // first chunk from the registers; longer cells: a counting sweep, then the placing sweep
+            bool const v0     = (uint32_t)lane < count[u];
+            uint32_t const s0 = v0 ? binner.sub_a(p[u]) : 0xFFu;
+            uint32_t m[4]     = {0u, 0u, 0u, 0u}, tot[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int q = 0; q < D::SA; ++q)
+            {
+                m[q]   = __ballot_sync(0xFFFFFFFFu, s0 == (uint32_t)q);
+                tot[q] = (uint32_t)__popc(m[q]);
+            }
+            for (uint32_t c = 32; c < count[u]; c += 32)
+            {
+                bool const v     = c + (uint32_t)lane < count[u];
+                uint32_t const s = v ? binner.sub_a(load_pt(g.pts + start[u] + c + lane)) : 0xFFu;
+#pragma unroll
+                for (int q = 0; q < D::SA; ++q)
+                    tot[q] += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, s == (uint32_t)q));
+            }
+            uint32_t off[4];
+            off[0] = sm.F[bin[u]];
+#pragma unroll
+            for (int q = 1; q < 4; ++q)
+                off[q] = off[q - 1] + tot[q - 1];
+            if (lane >= 1 && lane < D::SA)
+                sm.F[bin[u] + lane] = lane == 1 ? off[1] : (lane == 2 ? off[2] : off[3]);
+            if (v0)
+            {
+                uint32_t const base = s0 == 0u ? off[0] : (s0 == 1u ? off[1] : (s0 == 2u ? off[2] : off[3]));
+                uint32_t const mm   = s0 == 0u ? m[0] : (s0 == 1u ? m[1] : (s0 == 2u ? m[2] : m[3]));
+                uint32_t const pos  = base + (uint32_t)__popc(mm & lt);
+                sm.P[pos]           = p[u];
+                sm.gpos[pos]        = start[u] + (uint32_t)lane;
+            }
+#pragma unroll
+            for (int q = 0; q < D::SA; ++q)
+                off[q] += (uint32_t)__popc(m[q]);
+            for (uint32_t c = 32; c < count[u]; c += 32)
+            {
+                bool const v = c + (uint32_t)lane < count[u];
+                float4 pp    = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v)
+                    pp = load_pt(g.pts + start[u] + c + lane);
+                uint32_t const s = v ? binner.sub_a(pp) : 0xFFu;
+                uint32_t mc[4]   = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int q = 0; q < D::SA; ++q)
+                    mc[q] = __ballot_sync(0xFFFFFFFFu, s == (uint32_t)q);
+                if (v)
+                {
+                    uint32_t const base = s == 0u ? off[0] : (s == 1u ? off[1] : (s == 2u ? off[2] : off[3]));
+                    uint32_t const mm   = s == 0u ? mc[0] : (s == 1u ? mc[1] : (s == 2u ? mc[2] : mc[3]));
+                    uint32_t const pos  = base + (uint32_t)__popc(mm & lt);
+                    sm.P[pos]           = pp;
+                    sm.gpos[pos]        = start[u] + c + (uint32_t)lane;
+                }
+#pragma unroll
+                for (int q = 0; q < D::SA; ++q)
+                    off[q] += (uint32_t)__popc(mc[q]);
+            }
+        }
+    }
+#else
+    for (uint32_t j = (uint32_t)tid; j < tg.n_occ; j += (uint32_t)nthreads)
+    {
+        int const cell       = sm.occ[j];
+        uint32_t const start = sm.cstart[cell], count = sm.ccount[cell];
+        int const bin        = binner.first_bin(cell);
+        uint32_t off[4] = {sm.F[bin], 0u, 0u, 0u}, tot[4] = {0u, 0u, 0u, 0u};
+        for (uint32_t i = 0; i < count; ++i)
+            tot[binner.sub_a(load_pt(g.pts + start + i))]++;
+        for (int q = 1; q < 4; ++q)
+            off[q] = off[q - 1] + tot[q - 1];
+        for (int q = 1; q < D::SA; ++q)
+            sm.F[bin + q] = off[q];
+        for (uint32_t i = 0; i < count; ++i)
+        {
+            float4 const p     = load_pt(g.pts + start + i);
+            uint32_t const pos = off[binner.sub_a(p)]++;
+            sm.P[pos]          = p;
+            sm.gpos[pos]       = start + i;
+        }
+    }
+#endif
+}
+
+// phase 2 (other layouts): bin counts (F[bin + 1] = count), one thread per occupied cell
 template <int S>
 PCPX_HD void tile_phase_count(const GridView& g, const TileParams& tp, const TileSmem& sm, int tid,
                               int nthreads)
 {
+    using D = TileDims<S>;
     TileGeom const tg = *sm.geom;
     TileCellBinner<S> const binner(g, tp, tg);
     for (uint32_t j = (uint32_t)tid; j < tg.n_occ; j += (uint32_t)nthreads)
@@ -317,7 +632,7 @@ PCPX_HD void tile_phase_count(const GridView& g, const TileParams& tp, const Til
         int const cell       = sm.occ[j];
         uint32_t const start = sm.cstart[cell], count = sm.ccount[cell];
         int const bin        = binner.first_bin(cell);
-        if (S == 1)
+        if (D::sub == 1)
         {
             sm.F[bin + 1] = count;
             continue;
@@ -328,13 +643,13 @@ PCPX_HD void tile_phase_count(const GridView& g, const TileParams& tp, const Til
             uint32_t const s = binner.sub(load_pt(g.pts + start + i));
             n0 += s == 0u, n1 += s == 1u, n2 += s == 2u, n3 += s == 3u;
         }
-        sm.F[bin + 1] = n0, sm.F[bin + 2] = n1;
-        sm.F[bin + TileDims<S>::na + 1] = n2, sm.F[bin + TileDims<S>::na + 2] = n3;
+        sm.F[bin + binner.sub_offset(0) + 1] = n0, sm.F[bin + binner.sub_offset(1) + 1] = n1;
+        sm.F[bin + binner.sub_offset(2) + 1] = n2, sm.F[bin + binner.sub_offset(3) + 1] = n3;
     }
 }
 
-// phase 3: inclusive scan of the counts in place, after which F[i] is the start of bin i
-// (F[0] = 0, F[bins] = the number of staged points).  Device: the first warp, 27 bins per lane.
+// phase 3 (other layouts): inclusive scan of the counts in place, after which F[i] is the start
+// of bin i (F[0] = 0, F[bins] = the number of staged points).  Device: the first warp.
 template <int S>
 PCPX_HD void tile_phase_scan(const TileSmem& sm, int tid)
 {
@@ -372,12 +687,13 @@ PCPX_HD void tile_phase_scan(const TileSmem& sm, int tid)
 #endif
 }
 
-// phase 4: placement, again one thread per occupied cell, its points in the order of the sorted
-// array
+// phase 4 (other layouts): placement, again one thread per occupied cell, its points in the
+// order of the sorted array
 template <int S>
 PCPX_HD void tile_phase_place(const GridView& g, const TileParams& tp, const TileSmem& sm, int tid,
                               int nthreads)
 {
+    using D = TileDims<S>;
     TileGeom const tg = *sm.geom;
     TileCellBinner<S> const binner(g, tp, tg);
     for (uint32_t j = (uint32_t)tid; j < tg.n_occ; j += (uint32_t)nthreads)
@@ -386,8 +702,9 @@ PCPX_HD void tile_phase_place(const GridView& g, const TileParams& tp, const Til
         uint32_t const start = sm.cstart[cell], count = sm.ccount[cell];
         int const bin        = binner.first_bin(cell);
         uint32_t w0 = sm.F[bin], w1 = 0, w2 = 0, w3 = 0;
-        if (S == 2)
-            w1 = sm.F[bin + 1], w2 = sm.F[bin + TileDims<S>::na], w3 = sm.F[bin + TileDims<S>::na + 1];
+        if (D::sub == 4)
+            w1 = sm.F[bin + binner.sub_offset(1)], w2 = sm.F[bin + binner.sub_offset(2)],
+            w3 = sm.F[bin + binner.sub_offset(3)];
         for (uint32_t i = 0; i < count; ++i)
         {
             float4 const p   = load_pt(g.pts + start + i);
@@ -395,8 +712,7 @@ PCPX_HD void tile_phase_place(const GridView& g, const TileParams& tp, const Til
             uint32_t const pos = s == 0u ? w0 : (s == 1u ? w1 : (s == 2u ? w2 : w3));
             w0 += s == 0u, w1 += s == 1u, w2 += s == 2u, w3 += s == 3u;
             sm.P[pos] = p;
-            if (sm.gpos)
-                sm.gpos[pos] = start + i;
+            sm.gpos[pos] = start + i;
         }
     }
     if (tid == 0)
@@ -404,163 +720,8 @@ PCPX_HD void tile_phase_place(const GridView& g, const TileParams& tp, const Til
             sm.P[tg.n_points + j] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
 }
 
-// ---- the per-query search --------------------------------------------------------------------
-template <int KL>
-struct TileList
-{
-    uint32_t a[KL];
-
-    PCPX_HD void reset()
-    {
-#pragma unroll
-        for (int j = 0; j < KL; ++j)
-            a[j] = kKeyEmpty;
-    }
-    // two candidates at once (see TopD::insert2): 2 min + one 3-input max per slot
-    PCPX_HD void insert2(uint32_t k0, uint32_t k1)
-    {
-        uint32_t const lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
-#pragma unroll
-        for (int j = KL - 1; j >= 2; --j)
-        {
-            uint32_t const x = a[j] < lo ? a[j] : lo, y = a[j - 1] < hi ? a[j - 1] : hi;
-            uint32_t const m = x > y ? x : y;
-            a[j]             = m > a[j - 2] ? m : a[j - 2];
-        }
-        if (KL >= 2)
-        {
-            uint32_t const x = a[KL >= 2 ? 1 : 0] < lo ? a[KL >= 2 ? 1 : 0] : lo,
-                           y = a[0] < hi ? a[0] : hi;
-            a[KL >= 2 ? 1 : 0] = x > y ? x : y;
-        }
-        a[0] = a[0] < lo ? a[0] : lo;
-    }
-    PCPX_HD uint32_t get(uint32_t j) const // a[j] without dynamic register indexing
-    {
-        uint32_t r = a[0];
-#pragma unroll
-        for (int i = 1; i < KL; ++i)
-            r = j == (uint32_t)i ? a[i] : r;
-        return r;
-    }
-};
-
-// key of one candidate: truncated distance bits | staged position; kKeyEmpty when the point lies
-// in the exclusion box (common/vector3d_queries.hpp:31-35,59-63: strict <, all three axes)
-PCPX_HD uint32_t tile_key(const float4& c, uint32_t pos, float qx, float qy, float qz, float eps,
-                          float excl_thr, uint32_t mask)
-{
-    float const dx = fsub_x(c.x, qx), dy = fsub_x(c.y, qy), dz = fsub_x(c.z, qz);
-    float const d2 = sqdist_x(dx, dy, dz);
-    if (d2 < excl_thr) // necessary for the box test; rare (the query itself, near-duplicates)
-        if (fabsf(dx) < eps && fabsf(dy) < eps && fabsf(dz) < eps)
-            return kKeyEmpty;
-    return (f2u(d2) & ~mask) | pos;
-}
-
-PCPX_HD int tile_zigzag(int i) { return (i & 1) ? (i + 1) >> 1 : -(i >> 1); } // 0, +1, -1, +2, -2, ...
-
-// Returns true when the list holds the final answer (first k keys = the k nearest eligible
-// points, membership exact).
-template <int KL, int S>
-PCPX_HD bool tile_search(const GridView& g, const TileParams& tp, const TileGeom& tg,
-                         const float4* P, const uint32_t* F, float qx, float qy, float qz,
-                         uint32_t k, float eps, TileList<KL>& top, uint32_t* n_cand)
-{
-    using D = TileDims<S>;
-    int const A = tg.ax[0], B = tg.ax[1], C = tg.ax[2];
-    float const ta = (axis_of(qx, qy, qz, A) - axis_of(g.ox, g.oy, g.oz, A)) * tp.bins_per_len -
-                     (float)(tg.r0[0] * S);
-    float const tb = (axis_of(qx, qy, qz, B) - axis_of(g.ox, g.oy, g.oz, B)) * tp.bins_per_len -
-                     (float)(tg.r0[1] * S);
-    float const tc = (axis_of(qx, qy, qz, C) - axis_of(g.ox, g.oy, g.oz, C)) * tp.cells_per_len -
-                     (float)tg.r0[2];
-    int ib = (int)floorf(tb), ic = (int)floorf(tc);
-    ib = ib < 0 ? 0 : (ib > D::nb - 1 ? D::nb - 1 : ib);
-    ic = ic < 0 ? 0 : (ic > D::nc - 1 ? D::nc - 1 : ic);
-    // the scan ball must stay inside the staged region
-    float const gab = fminf(fminf(ta, (float)D::na - ta), fminf(tb, (float)D::nb - tb)) - tp.delta_bins;
-    float const gc  = fminf(tc, (float)D::nc - tc) - tp.delta_cells;
-    float rscan     = fminf(fminf(gab * tp.len_per_bin, gc * tp.h), tp.scan_cap * tp.h);
-    rscan           = rscan > 0.f ? rscan : 0.f;
-    float const r2scan  = rscan * rscan * 0.999999f;
-    float r2            = r2scan;
-    float const excl    = 3.0001f * eps * eps;
-    uint32_t const mask = tp.key_mask;
-    uint32_t cand       = 0;
-    top.reset();
-    for (int jc = 0; jc <= 2 * tp.rows_c; ++jc)
-    {
-        int const dc = tile_zigzag(jc), rc = ic + dc;
-        if ((unsigned)rc >= (unsigned)D::nc)
-            continue;
-        float const gapc = dc > 0 ? (float)rc - tc : (dc < 0 ? tc - (float)(rc + 1) : 0.f);
-        float lbc        = (gapc - tp.delta_cells) * tp.h;
-        lbc              = lbc > 0.f ? lbc : 0.f;
-        float const lbc2 = lbc * lbc;
-        if (lbc2 > r2 * 1.00001f)
-            continue;
-        for (int jb = 0; jb <= 2 * tp.rows_b; ++jb)
-        {
-            int const db = tile_zigzag(jb), rb = ib + db;
-            if ((unsigned)rb >= (unsigned)D::nb)
-                continue;
-            float const gapb = db > 0 ? (float)rb - tb : (db < 0 ? tb - (float)(rb + 1) : 0.f);
-            float lbb        = (gapb - tp.delta_bins) * tp.len_per_bin;
-            lbb              = lbb > 0.f ? lbb : 0.f;
-            float const rem  = r2 * 1.00001f - (lbb * lbb + lbc2);
-            if (rem < 0.f)
-                continue;
-            float const reach = sqrtf(rem) * tp.bins_per_len + tp.delta_bins;
-            int alo = (int)floorf(ta - reach), ahi = (int)floorf(ta + reach);
-            alo = alo < 0 ? 0 : alo;
-            ahi = ahi > D::na - 1 ? D::na - 1 : ahi;
-            if (alo > ahi)
-                continue;
-            int const base    = (rc * D::nb + rb) * D::na;
-            uint32_t const lo = F[base + alo], hi = F[base + ahi + 1];
-            for (uint32_t p = lo; p < hi; p += 2)
-            {
-                float4 const c0 = P[p], c1 = P[p + 1]; // P is padded: p + 1 is readable
-                uint32_t const k0 = tile_key(c0, p, qx, qy, qz, eps, excl, mask);
-                uint32_t const k1 =
-                    p + 1 < hi ? tile_key(c1, p + 1, qx, qy, qz, eps, excl, mask) : kKeyEmpty;
-                top.insert2(k0, k1);
-            }
-            cand += hi - lo;
-            // the ball shrinks to the (KL-1)-th smallest distance seen (upper end of its
-            // truncation bucket); NaN while the list is not full: fminf keeps r2
-            r2 = fminf(r2, u2f(top.a[KL - 2] | mask));
-        }
-    }
-    if (n_cand)
-        *n_cand = cand;
-    uint32_t const kk = top.get(k - 1), kn = top.get(k);
-    // final: k eligible points found, the k-th lies inside the scanned ball, and the (k+1)-th
-    // differs from it in the kept bits (membership unambiguous)
-    return kk != kKeyEmpty && u2f(kk | mask) <= r2scan && ((kk ^ kn) & ~mask) != 0u;
-}
-
-
-// =============================================================================================
-// Batched form of the per-query search.
-//
-// tile_search above interleaves geometry, loads and list updates, and its lanes run the nested
-// row / candidate loops in lock-step: a warp pays max-over-lanes of every row, and the two-at-a-time
-// sorted insert costs 1.5 min/max per list slot and candidate on the ALU pipe (measured: half of
-// the lanes idle in that loop, 91 instructions per pair of candidates).  The batched form splits
-// the work:
-//   Q1  tile_list_candidates: the geometry only — rows, bin ranges — and the staged positions of
-//       the candidates go to a per-thread list in shared memory (a 4-instruction loop body);
-//   Q2  tile_select: a REGULAR loop over that list, eight candidates at a time: keys, a 19-exchange
-//       sorting network over the eight, and a bitonic merge into the sorted register list
-//       (13.75 min/max per candidate for a 16-entry list instead of 24), no exclusion test (the
-//       query's own staged position is left out when the list is made; a foreign point inside
-//       the exclusion box shows up as a smallest key below 3 eps^2 and sends the query to the
-//       retry queue).
-// =============================================================================================
-
-// phase 6 (after the bins are sorted): which rows hold points, and the tile's row segments
+// phase 5 (other layouts, after the bins are placed): which rows hold points, and the tile's
+// row segments
 template <int S>
 PCPX_HD void tile_phase_rows(const TileSmem& sm, int tid, int nthreads)
 {
@@ -579,36 +740,67 @@ PCPX_HD void tile_phase_rows(const TileSmem& sm, int tid, int nthreads)
     }
     if (tid == 0)
     {
-        // the tile's own points: rows ic in [1, 1 + 4), ib in [S, 5 S), bins ia in [S, 5 S)
+        // the tile's own points: rows ic in [1, 1 + 4), ib in [SB, 5 SB), bins ia in [SA, 5 SA)
         uint32_t run = 0;
         int seg      = 0;
         for (int ic = 1; ic <= kTileCells; ++ic)
-            for (int ib = S; ib < S + kTileCells * S; ++ib, ++seg)
+            for (int ib = D::SB; ib < D::SB + kTileCells * D::SB; ++ib, ++seg)
             {
                 int const base  = (ic * D::nb + ib) * D::na;
                 sm.seg_off[seg] = run;
-                run += sm.F[base + S + kTileCells * S] - sm.F[base + S];
+                run += sm.F[base + D::SA + kTileCells * D::SA] - sm.F[base + D::SA];
             }
         sm.seg_off[seg] = run;
     }
 }
 
-// phase 7: the query list (staged positions of the tile's own points, row-major bin order)
+// Staged position of the tile's i-th query (the tile's own points in row-major bin order):
+// the segment by a branch-free binary search over the (non-decreasing) segment starts.
 template <int S>
-PCPX_HD void tile_phase_qlist(const TileSmem& sm, int tid, int nthreads)
+PCPX_HD uint32_t tile_query_pos(const TileSmem& sm, uint32_t i)
 {
-    using D            = TileDims<S>;
-    constexpr int segs = kTileCells * kTileCells * S;
-    for (int seg = tid; seg < segs; seg += nthreads)
-    {
-        int const ic = 1 + seg / (kTileCells * S), ib = S + seg % (kTileCells * S);
-        int const base    = (ic * D::nb + ib) * D::na;
-        uint32_t const lo = sm.F[base + S], hi = sm.F[base + S + kTileCells * S];
-        uint32_t w        = sm.seg_off[seg];
-        for (uint32_t p = lo; p < hi; ++p)
-            sm.qlist[w++] = (uint16_t)p;
-    }
+    using D = TileDims<S>;
+    int seg = 0;
+#pragma unroll
+    for (int step = D::segs / 2; step >= 1; step >>= 1)
+        seg += sm.seg_off[seg + step] <= i ? step : 0;
+    int const ic = 1 + seg / (kTileCells * D::SB), ib = D::SB + seg % (kTileCells * D::SB);
+    return sm.F[(ic * D::nb + ib) * D::na + D::SA] + (i - sm.seg_off[seg]);
 }
+
+// ---- the per-query search --------------------------------------------------------------------
+template <int KL>
+struct TileList
+{
+    uint32_t a[KL];
+
+    PCPX_HD void reset()
+    {
+#pragma unroll
+        for (int j = 0; j < KL; ++j)
+            a[j] = kKeyEmpty;
+    }
+    PCPX_HD uint32_t get(uint32_t j) const // a[j] without dynamic register indexing
+    {
+        uint32_t r = a[0];
+#pragma unroll
+        for (int i = 1; i < KL; ++i)
+            r = j == (uint32_t)i ? a[i] : r;
+        return r;
+    }
+};
+
+PCPX_HD int tile_zigzag(int i) { return (i & 1) ? (i + 1) >> 1 : -(i >> 1); } // 0, +1, -1, +2, -2, ...
+
+// The search of one query is split in two:
+//   Q1  tile_list_candidates: the geometry only — rows, bin ranges — and the staged positions of
+//       the candidates go to a per-thread list in shared memory (a 4-instruction loop body);
+//   Q2  tile_select: a REGULAR loop over that list, eight candidates at a time: keys, a 19-exchange
+//       sorting network over the eight, and a bitonic merge into the sorted register list
+//       (13.75 min/max per candidate for a 16-entry list instead of 24 for a sorted insert), no
+//       exclusion test (the query's own staged position is left out when the list is made; a
+//       foreign point inside the exclusion box shows up as a smallest key below 3 eps^2 and sends
+//       the query to the retry queue).
 
 PCPX_HD float tile_sqrt(float x) // only ever widens a bin range: an approximation is fine
 {
@@ -643,19 +835,20 @@ PCPX_HD TileCursor tile_cursor(const GridView& g, const TileParams& tp, const Ti
     int const A = tg.ax[0], B = tg.ax[1], C = tg.ax[2];
     TileCursor cu;
     cu.ta = (axis_of(qx, qy, qz, A) - axis_of(g.ox, g.oy, g.oz, A)) * tp.bins_per_len -
-            (float)(tg.r0[0] * S);
-    cu.tb = (axis_of(qx, qy, qz, B) - axis_of(g.ox, g.oy, g.oz, B)) * tp.bins_per_len -
-            (float)(tg.r0[1] * S);
+            (float)(tg.r0[0] * D::SA);
+    cu.tb = (axis_of(qx, qy, qz, B) - axis_of(g.ox, g.oy, g.oz, B)) * tp.bins_per_len_b -
+            (float)(tg.r0[1] * D::SB);
     cu.tc = (axis_of(qx, qy, qz, C) - axis_of(g.ox, g.oy, g.oz, C)) * tp.cells_per_len -
             (float)tg.r0[2];
     int ib = (int)floorf(cu.tb), ic = (int)floorf(cu.tc);
     cu.ib = ib < 0 ? 0 : (ib > D::nb - 1 ? D::nb - 1 : ib);
     cu.ic = ic < 0 ? 0 : (ic > D::nc - 1 ? D::nc - 1 : ic);
     // the scan ball must stay inside the staged region
-    float const gab =
-        fminf(fminf(cu.ta, (float)D::na - cu.ta), fminf(cu.tb, (float)D::nb - cu.tb)) - tp.delta_bins;
+    float const ga = fminf(cu.ta, (float)D::na - cu.ta) - tp.delta_bins;
+    float const gb = fminf(cu.tb, (float)D::nb - cu.tb) - tp.delta_bins_b;
     float const gc = fminf(cu.tc, (float)D::nc - cu.tc) - tp.delta_cells;
-    float rscan    = fminf(fminf(gab * tp.len_per_bin, gc * tp.h), tp.scan_cap * tp.h);
+    float rscan    = fminf(fminf(fminf(ga * tp.len_per_bin, gb * tp.len_per_bin_b), gc * tp.h),
+                           tp.scan_cap * tp.h);
     rscan          = rscan > 0.f ? rscan : 0.f;
     cu.r2scan      = rscan * rscan * 0.999999f;
     cu.r2          = cu.r2scan;
@@ -701,7 +894,7 @@ PCPX_HD uint32_t tile_list_candidates(const TileParams& tp, const uint32_t* F,
                 continue;
             float const gapb =
                 db > 0 ? (float)rb - cu.tb : (db < 0 ? cu.tb - (float)(rb + 1) : 0.f);
-            float lbb       = (gapb - tp.delta_bins) * tp.len_per_bin;
+            float lbb       = (gapb - tp.delta_bins_b) * tp.len_per_bin_b;
             lbb             = lbb > 0.f ? lbb : 0.f;
             float const rem = remc - lbb * lbb;
             if (rem < 0.f)
@@ -848,70 +1041,6 @@ PCPX_HD bool tile_is_final(const TileList<KL>& top, uint32_t k, uint32_t mask, f
 }
 
 // ---- epilogues over the k winners --------------------------------------------------------------
-
-// PCA normal (+ centroid) as normal_two_pass does it: moments about the query point.
-template <int KL>
-PCPX_HD void tile_normal(const float4* P, const TileList<KL>& top, uint32_t k, uint32_t mask,
-                         float qx, float qy, float qz, float* n3, float* c3)
-{
-    float s1x = 0.f, s1y = 0.f, s1z = 0.f;
-    Sym3 s2{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < KL; ++j)
-        if ((uint32_t)j < k)
-        {
-            float4 const c = P[top.a[j] & mask];
-            float const dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
-            s1x += dx, s1y += dy, s1z += dz;
-            s2.xx += dx * dx, s2.xy += dx * dy, s2.xz += dx * dz;
-            s2.yy += dy * dy, s2.yz += dy * dz, s2.zz += dz * dz;
-        }
-    float const inv = 1.f / (float)k;
-    float const mx = s1x * inv, my = s1y * inv, mz = s1z * inv;
-    Sym3 m;
-    m.xx = s2.xx - s1x * mx, m.xy = s2.xy - s1x * my, m.xz = s2.xz - s1x * mz;
-    m.yy = s2.yy - s1y * my, m.yz = s2.yz - s1y * mz, m.zz = s2.zz - s1z * mz;
-    smallest_eigenvector(m, n3[0], n3[1], n3[2], nullptr);
-    c3[0] = qx + mx, c3[1] = qy + my, c3[2] = qz + mz;
-}
-
-// Calls f(slot, d2, original index) for the k winners in ascending (exact d2, original index)
-// order.  The list is sorted by TRUNCATED distance, so exact order can differ only inside runs of
-// keys that agree in the kept bits; an element displaced by one such neighbour is put right on
-// the fly, anything longer returns false (the query then goes to the retry queue; what was
-// emitted is overwritten).
-template <int KL, class F>
-PCPX_HD bool tile_emit_sorted(const float4* P, const TileList<KL>& top, uint32_t k, uint32_t mask,
-                              float qx, float qy, float qz, F&& f)
-{
-    float hd = 0.f, ld = -1.f; // held back / last emitted
-    uint32_t hid = 0, lid = 0, slot = 0;
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < KL; ++j)
-        if ((uint32_t)j < k)
-        {
-            float4 const c    = P[top.a[j] & mask];
-            float const d2    = sqdist_x(fsub_x(c.x, qx), fsub_x(c.y, qy), fsub_x(c.z, qz));
-            uint32_t const id = f2u(c.w);
-            if (j == 0)
-            {
-                hd = d2, hid = id;
-                continue;
-            }
-            bool const before_held = d2 < hd || (d2 == hd && id < hid);
-            float const ed         = before_held ? d2 : hd;
-            uint32_t const eid     = before_held ? id : hid;
-            ok = ok && !(ed < ld || (ed == ld && eid < lid && slot > 0));
-            f(slot++, ed, eid);
-            ld = ed, lid = eid;
-            if (!before_held)
-                hd = d2, hid = id;
-        }
-    ok = ok && !(hd < ld || (hd == ld && hid < lid && slot > 0));
-    f(slot, hd, hid);
-    return ok;
-}
 
 // The k winners' staged positions, out of the register list into the thread's column of `cl`, so
 // that the epilogues are rolled loops instead of KL unrolled copies of their body.

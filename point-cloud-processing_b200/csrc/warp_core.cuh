@@ -1,0 +1,241 @@
+// Warp-cooperative exact kNN: one WARP per query, for the queries the fast passes hand on (the
+// tile pass's near misses and tie cases, sparse tiles, outliers; the block search's failures).
+//
+// A thread-per-query search is a serial chain of dependent loads — 27 table probes, a hundred
+// candidates, a second pass — and with a few hundred such queries left the GPU waits 0.2 ms for
+// the slowest thread, twice (queue kernel, then retry kernel).  Here the 32 lanes share one
+// query, so a round of the search is ONE memory latency:
+//
+//   * the octree (levels 0 .. lfine of the cell table) is walked depth-first with a per-warp
+//     stack in shared memory; a step pops up to four cells and looks up their 32 children at
+//     once, one per lane, each with its conservative squared lower bound (same float slack as
+//     every other bound in the library, grid_core.cuh);
+//   * children that are leaves (finest level, or <= 32 points) are scanned together: their points
+//     are spread over the lanes by a prefix over the leaf sizes, 32 candidates per round;
+//   * the current k nearest live as ONE 64-bit (bits(d2), original index) key per lane, sorted
+//     across the warp; a round of 32 candidate keys is sorted by a 15-step shuffle bitonic
+//     network and merged in (min with the reversed batch + 5 merge steps) — rounds in which no
+//     candidate beats the k-th key are skipped after one vote;
+//   * the remaining children go on the stack farthest first, so the nearest is opened next, and
+//     every popped cell is pruned against the k-th distance found so far (a cell whose bound
+//     EQUALS it is still opened: a tie with a smaller index may hide there).
+//
+// The first descent starts from the 3x3x3 block of the query's cell one level above the call's
+// main level — a near miss is final there after two or three rounds (k-th distance strictly
+// inside the block) —, anything else restarts from the root with the k-th distance of the first
+// attempt as its pruning bound.  Keys are exact and totally ordered (distinct original
+// indices), so rows come out in the (d2, original index) order of the parity contract with no
+// tie handling at all.  Device only (shuffles); the GPU parity suite runs every cloud of the
+// oracle tests through it (tuning "warp_all").
+#pragma once
+#include "normals_core.cuh"
+
+namespace pcpx {
+
+constexpr int kWarpStackCap      = 576;
+constexpr uint32_t kWarpLeafSize = 32;
+constexpr uint32_t kFullMask     = 0xFFFFFFFFu;
+
+struct WarpStack
+{
+    uint64_t key[kWarpStackCap]; // cell_key(level, cx, cy, cz)
+    float lb2[kWarpStackCap];
+};
+
+#ifdef __CUDACC__
+
+// compare-exchange with the lane `xm` away: keeps the smaller (or larger) key and its payload
+__device__ __forceinline__ void warp_cex(uint64_t& key, uint32_t& pay, int xm, bool keep_min)
+{
+    uint64_t const ok = __shfl_xor_sync(kFullMask, key, xm);
+    uint32_t const op = __shfl_xor_sync(kFullMask, pay, xm);
+    bool const take   = keep_min ? ok < key : ok > key;
+    key               = take ? ok : key;
+    pay               = take ? op : pay;
+}
+
+// ascending across the lanes
+__device__ __forceinline__ void warp_sort32(uint64_t& key, uint32_t& pay, int lane)
+{
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1)
+            warp_cex(key, pay, j, ((lane & k2) == 0) == ((lane & j) == 0));
+}
+
+// list (ascending across the lanes) <- the 32 smallest of list + batch
+__device__ __forceinline__ void warp_merge32(uint64_t& lkey, uint32_t& lpay, uint64_t bkey,
+                                             uint32_t bpay, int lane)
+{
+    warp_sort32(bkey, bpay, lane);
+    uint64_t const rk = __shfl_sync(kFullMask, bkey, 31 - lane);
+    uint32_t const rp = __shfl_sync(kFullMask, bpay, 31 - lane);
+    if (rk < lkey)
+        lkey = rk, lpay = rp;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1)
+        warp_cex(lkey, lpay, j, (lane & j) == 0);
+}
+
+// conservative squared distance from q to the cell (level, cx, cy, cz): nominal faces in float,
+// every gap reduced by 2 delta (child_axis_bounds of tree_core.cuh, one cell at a time)
+__device__ __forceinline__ float warp_cell_lb2(const GridView& g, float h, uint32_t cx, uint32_t cy,
+                                               uint32_t cz, float qx, float qy, float qz)
+{
+    float const d2x = 2.f * g.delta;
+    float const lx = g.ox + (float)cx * h, ly = g.oy + (float)cy * h, lz = g.oz + (float)cz * h;
+    float dx = fmaxf(fmaxf(lx - qx, qx - (lx + h)), 0.f) - d2x;
+    float dy = fmaxf(fmaxf(ly - qy, qy - (ly + h)), 0.f) - d2x;
+    float dz = fmaxf(fmaxf(lz - qz, qz - (lz + h)), 0.f) - d2x;
+    dx = dx > 0.f ? dx : 0.f, dy = dy > 0.f ? dy : 0.f, dz = dz > 0.f ? dz : 0.f;
+    return fadd_x(fadd_x(fmul_x(dx, dx), fmul_x(dy, dy)), fmul_x(dz, dz));
+}
+
+struct WarpKnn
+{
+    uint64_t key; // lane j: the j-th smallest (bits(d2) << 32 | original index), kEmptyEntry when none
+    uint32_t pos; // its position in the sorted point array
+
+    __device__ __forceinline__ float kth_d2(uint32_t k) const
+    {
+        uint64_t const kk = __shfl_sync(kFullMask, key, (int)k - 1);
+        return kk == kEmptyEntry ? INFINITY : __uint_as_float((uint32_t)(kk >> 32));
+    }
+};
+
+// One descent.  `ckey / clb2 / cvalid`: this lane's cell of the initial batch.  `prune`: squared
+// distance no neighbour can exceed (INFINITY when unknown).  On return the list holds the k
+// nearest eligible points among everything under the initial cells whose bound is <= prune.
+__device__ __forceinline__ void warp_descend(const GridView& g, WarpStack& st, float qx, float qy,
+                                             float qz, uint32_t k, float eps, float prune,
+                                             uint64_t ckey, float clb2, bool cvalid, WarpKnn& top,
+                                             int lane)
+{
+    top.key = kEmptyEntry, top.pos = 0u;
+    int sp  = 0;
+    float tau = prune;
+    for (;;)
+    {
+        // ---- look the batch up ----
+        uint32_t start = 0, count = 0;
+        bool found = false;
+        if (cvalid && clb2 <= tau)
+            found = find_cell(g, ckey, start, count);
+        int const level = (int)(ckey >> 57);
+        bool const room = sp + 32 <= kWarpStackCap;
+        bool const leaf = found && (level >= g.lfine || count <= kWarpLeafSize || !room);
+        bool inner      = found && !leaf;
+        // ---- scan the leaves, 32 candidates per round ----
+        uint32_t const cnt = leaf ? count : 0u;
+        uint32_t incl      = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t const up = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o)
+                incl += up;
+        }
+        uint32_t const excl = incl - cnt, total = __shfl_sync(kFullMask, incl, 31);
+        for (uint32_t base = 0; base < total; base += 32)
+        {
+            uint32_t const f = base + (uint32_t)lane;
+            int src          = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+            {
+                uint32_t const v = __shfl_sync(kFullMask, excl, src + step);
+                src += v <= f ? step : 0;
+            }
+            uint32_t const s = __shfl_sync(kFullMask, start, src), e = __shfl_sync(kFullMask, excl, src);
+            uint64_t bkey = kEmptyEntry;
+            uint32_t bpos = 0u;
+            if (f < total)
+            {
+                bpos           = s + (f - e);
+                float4 const c = __ldg(g.pts + bpos);
+                float const d2 = candidate_d2(c, qx, qy, qz, eps);
+                if (d2 < INFINITY)
+                    bkey = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
+            }
+            uint64_t const kk = __shfl_sync(kFullMask, top.key, (int)k - 1);
+            if (__any_sync(kFullMask, bkey < kk))
+                warp_merge32(top.key, top.pos, bkey, bpos, lane);
+        }
+        tau = fminf(tau, top.kth_d2(k));
+        // ---- the other children: on the stack, farthest first ----
+        inner                = inner && clb2 <= tau;
+        uint32_t const n_in  = (uint32_t)__popc(__ballot_sync(kFullMask, inner));
+        if (n_in != 0u)
+        {
+            // (bound bits + 1, lane) ascending; cells that are not pushed sort first
+            uint64_t sk   = inner ? (((uint64_t)__float_as_uint(clb2) + 1ull) << 32) | (uint64_t)lane
+                                  : (uint64_t)lane;
+            uint32_t none = 0u;
+            warp_sort32(sk, none, lane);
+            // descending: lane j takes rank 31 - j
+            uint64_t const dk = __shfl_sync(kFullMask, sk, 31 - lane);
+            int const from    = (int)(dk & 31u);
+            uint64_t const pk = __shfl_sync(kFullMask, ckey, from);
+            float const pl    = __shfl_sync(kFullMask, clb2, from);
+            if ((uint32_t)lane < n_in)
+                st.key[sp + lane] = pk, st.lb2[sp + lane] = pl;
+            sp += (int)n_in;
+        }
+        __syncwarp();
+        // ---- next batch: the children of the (up to) four nearest open cells ----
+        if (sp == 0)
+            break;
+        int const P = sp < 4 ? sp : 4, p = lane >> 3;
+        cvalid      = p < P;
+        uint64_t pk = 0;
+        float plb   = 0.f;
+        if (cvalid)
+            pk = st.key[sp - 1 - p], plb = st.lb2[sp - 1 - p];
+        sp -= P;
+        __syncwarp();
+        cvalid = cvalid && plb <= tau;
+        int const cl = (int)(pk >> 57) + 1;
+        uint32_t const cx = 2u * (uint32_t)(pk & 0x7FFFFu) + (uint32_t)(lane & 1),
+                       cy = 2u * (uint32_t)((pk >> 19) & 0x7FFFFu) + (uint32_t)((lane >> 1) & 1),
+                       cz = 2u * (uint32_t)((pk >> 38) & 0x7FFFFu) + (uint32_t)((lane >> 2) & 1);
+        ckey = cell_key(cl, cx, cy, cz);
+        clb2 = warp_cell_lb2(g, ldexpf(g.extent, -cl), cx, cy, cz, qx, qy, qz);
+    }
+}
+
+// The whole search of one query by one warp.  Returns true when the first attempt (the block one
+// level above `level`) was final.
+__device__ __forceinline__ bool warp_knn(const GridView& g, WarpStack& st, float qx, float qy,
+                                         float qz, uint32_t k, float eps, int level, WarpKnn& top,
+                                         int lane)
+{
+    QueryCell const qc = query_cell(g, qx, qy, qz);
+    float prune        = INFINITY;
+    int const ls       = level > 0 ? level - 1 : 0;
+    if (ls > 0)
+    {
+        BlockGeom const b = block_geom(g, qc, ls, qx, qy, qz);
+        int const dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+        int const cx = (int)b.cx + dx, cy = (int)b.cy + dy, cz = (int)b.cz + dz;
+        bool const valid = lane < 27 && cx >= 0 && cy >= 0 && cz >= 0 && cx <= (int)b.last &&
+                           cy <= (int)b.last && cz <= (int)b.last;
+        uint64_t const key = cell_key(ls, (uint32_t)(valid ? cx : 0), (uint32_t)(valid ? cy : 0),
+                                      (uint32_t)(valid ? cz : 0));
+        float const lb2 = warp_cell_lb2(g, ldexpf(g.extent, -ls), (uint32_t)(valid ? cx : 0),
+                                        (uint32_t)(valid ? cy : 0), (uint32_t)(valid ? cz : 0), qx,
+                                        qy, qz);
+        warp_descend(g, st, qx, qy, qz, k, eps, INFINITY, key, lb2, valid, top, lane);
+        float const kd2 = top.kth_d2(k);
+        if (kd2 < b.block_lb2) // strictly inside the block: nothing outside can tie
+            return true;
+        prune = kd2;
+    }
+    warp_descend(g, st, qx, qy, qz, k, eps, prune, cell_key(0, 0u, 0u, 0u), 0.f, lane == 0, top,
+                 lane);
+    return false;
+}
+
+#endif // __CUDACC__
+
+} // namespace pcpx

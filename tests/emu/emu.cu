@@ -552,30 +552,28 @@ void emu_wlop_step(void* hp, const float* vj_sorted, void* hq, const float* wi_s
 static uint32_t g_emu_first_cap = 32;
 extern "C" void emu_tile_first_cap(uint32_t v) { g_emu_first_cap = v; }
 
-template <int KL, int S, bool batched>
+template <int KL, int S>
 static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, uint32_t max_points,
                       float scan_cap, int nthreads, uint32_t* idx, float* d2, uint32_t* cnt,
                       float* nrm, float* ctr, float* means, uint8_t* done, uint64_t* stats)
 {
+    using D             = TileDims<S>;
     GridView const& g   = ix->g;
     TileParams tp = make_tile_params<S>(g, level, max_points, scan_cap);
     tp.first_cap  = std::min<uint32_t>(g_emu_first_cap, (uint32_t)kTileCandCap);
     std::vector<float4> P(max_points + kTilePad);
     tp.threads    = nthreads;
-    std::vector<uint32_t> F(TileDims<S>::bins + 1), cstart(kRegionCellCount), ccount(kRegionCellCount);
+    std::vector<uint32_t> F(D::bins + 1), cstart(kRegionCellCount), ccount(kRegionCellCount);
     std::vector<uint8_t> occ(kRegionCellCount);
     TileGeom geom;
     TileSmem sm{};
     sm.P = P.data(), sm.F = F.data(), sm.cstart = cstart.data(), sm.ccount = ccount.data();
     sm.occ = occ.data(), sm.geom = &geom;
-    constexpr int segs = kTileCells * kTileCells * S;
-    std::vector<uint32_t> rowmask(TileDims<S>::nc), seg_off(segs + 1), gpos(max_points);
-    std::vector<uint16_t> qlist(max_points), clist((size_t)kTileCandCap * nthreads);
-    if (batched)
-    {
-        sm.rowmask = rowmask.data(), sm.seg_off = seg_off.data(), sm.gpos = gpos.data();
-        sm.qlist = qlist.data(), sm.cl = clist.data();
-    }
+    constexpr int segs = D::segs;
+    std::vector<uint32_t> rowmask(D::nc), seg_off(segs + 1), gpos(max_points);
+    std::vector<uint16_t> clist((size_t)kTileCandCap * nthreads);
+    sm.rowmask = rowmask.data(), sm.seg_off = seg_off.data(), sm.gpos = gpos.data();
+    sm.cl = clist.data();
     int const sh = g.lcap - (level - kTileShift);
     auto tile_of = [&](uint32_t i) {
         QueryCell c = query_cell(g, ix->pts[i].x, ix->pts[i].y, ix->pts[i].z);
@@ -591,6 +589,9 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
         stats[0]++;
         QueryCell const fc = query_cell(g, ix->pts[s0].x, ix->pts[s0].y, ix->pts[s0].z);
         uint64_t const txyz = tile_pack(fc.ux >> sh, fc.uy >> sh, fc.uz >> sh);
+        // (stale contents must not matter)
+        std::fill(F.begin(), F.end(), 0xDEADu);
+        std::fill(rowmask.begin(), rowmask.end(), D::one_pass ? 0xFFFFFFFFu : 0u);
         for (int t = 0; t < nthreads; ++t)
             tile_phase_lookup<S>(g, tp, sm, txyz, t, nthreads);
         for (int t = 0; t < nthreads; ++t)
@@ -604,61 +605,53 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
             continue;
         }
         // (thread order scrambled: nothing may depend on it)
-        for (int t = nthreads - 1; t >= 0; --t)
-            tile_phase_count<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
-        for (int t = 0; t < nthreads; ++t)
-            tile_phase_scan<S>(sm, t);
-        for (int t = nthreads - 1; t >= 0; --t)
-            tile_phase_place<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
-        uint32_t nq = s1 - s0;
-        if (batched)
+        if constexpr (D::one_pass)
         {
+            for (int t = nthreads - 1; t >= 0; --t)
+                tile_phase_place_cells<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
+        }
+        else
+        {
+            for (int t = nthreads - 1; t >= 0; --t)
+                tile_phase_count<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
+            for (int t = 0; t < nthreads; ++t)
+                tile_phase_scan<S>(sm, t);
+            for (int t = nthreads - 1; t >= 0; --t)
+                tile_phase_place<S>(g, tp, sm, (t * 37) % nthreads, nthreads);
             for (int t = 0; t < nthreads; ++t)
                 tile_phase_rows<S>(sm, t, nthreads);
-            for (int t = 0; t < nthreads; ++t)
-                tile_phase_qlist<S>(sm, t, nthreads);
-            if (sm.seg_off[segs] != nq)
-                stats[1] += 1u << 20; // inconsistent query list: shows up as an absurd count
         }
+        uint32_t nq = s1 - s0;
+        if (sm.seg_off[segs] != nq || sm.F[D::bins] != geom.n_points)
+            stats[1] += 1u << 20; // inconsistent query list: shows up as an absurd count
+        for (int b = 0; b < D::bins; ++b)
+            if (sm.F[b] > sm.F[b + 1])
+                stats[1] += 1u << 20;
         for (uint32_t i = 0; i < nq; ++i)
         {
-            uint32_t const pos = batched ? sm.qlist[i] : 0u;
-            float4 const q     = batched ? sm.P[pos] : ix->pts[s0 + i];
+            uint32_t const pos = tile_query_pos<S>(sm, i);
+            float4 const q     = sm.P[pos];
             uint32_t const row = f2u(q.w);
-            if (batched && (sm.gpos[pos] < s0 || sm.gpos[pos] >= s1 ||
-                            f2u(ix->pts[sm.gpos[pos]].w) != row))
+            if (sm.gpos[pos] < s0 || sm.gpos[pos] >= s1 || f2u(ix->pts[sm.gpos[pos]].w) != row)
                 stats[1] += 1u << 20;
             TileList<KL> top;
             uint32_t cand = 0;
-            bool ok;
-            if constexpr (batched)
-            {
-                int const tid = (int)(i % (uint32_t)nthreads);
-                TileCursor cu = tile_cursor<S>(g, tp, geom, q.x, q.y, q.z);
-                tile_search_batched<KL, S, 0>(tp, sm.P, sm.F, sm.rowmask, cu,
-                                           eps > 0.f ? pos : kNoSelf, sm.cl + tid, nthreads, q.x,
-                                           q.y, q.z, k, tp.first_cap, geom.n_points, top, &cand);
-                ok = tile_is_final<KL, 0>(top, k, tp.key_mask, cu.r2scan, eps);
-                if (ok)
-                    tile_store_winners<KL>(top, tp.key_mask, sm.cl + tid, nthreads);
-            }
-            else
-                ok = tile_search<KL, S>(g, tp, geom, sm.P, sm.F, q.x, q.y, q.z, k, eps, top, &cand);
+            int const tid = (int)(i % (uint32_t)nthreads);
+            TileCursor cu = tile_cursor<S>(g, tp, geom, q.x, q.y, q.z);
+            tile_search_batched<KL, S, 0>(tp, sm.P, sm.F, sm.rowmask, cu, eps > 0.f ? pos : kNoSelf,
+                                          sm.cl + tid, nthreads, q.x, q.y, q.z, k, tp.first_cap,
+                                          geom.n_points, top, &cand);
+            bool ok = tile_is_final<KL, 0>(top, k, tp.key_mask, cu.r2scan, eps);
+            if (ok)
+                tile_store_winners<KL>(top, tp.key_mask, sm.cl + tid, nthreads);
             stats[3] += cand;
-            int const etid = (int)(i % (uint32_t)nthreads);
             auto emit = [&](auto&& f) {
-                if constexpr (batched)
-                    return tile_emit_sorted_rolled(sm.P, sm.cl + etid, nthreads, k, q.x, q.y, q.z, f);
-                else
-                    return tile_emit_sorted<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z, f);
+                return tile_emit_sorted_rolled(sm.P, sm.cl + tid, nthreads, k, q.x, q.y, q.z, f);
             };
             if (ok && mode == 2)
             {
                 float n3[3], c3[3];
-                if constexpr (batched)
-                    tile_normal_rolled(sm.P, sm.cl + etid, nthreads, k, q.x, q.y, q.z, n3, c3);
-                else
-                    tile_normal<KL>(sm.P, top, k, tp.key_mask, q.x, q.y, q.z, n3, c3);
+                tile_normal_rolled(sm.P, sm.cl + tid, nthreads, k, q.x, q.y, q.z, n3, c3);
                 for (int a = 0; a < 3; ++a)
                 {
                     nrm[3 * (size_t)row + a] = n3[a];
@@ -666,13 +659,13 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
                         ctr[3 * (size_t)row + a] = c3[a];
                 }
             }
-            else if (ok && mode == 0 && batched && k <= 16u)
+            else if (ok && mode == 0 && k <= 16u)
             {
                 // the device's row output: winners ordered in place, rows read off the positions
-                ok = tile_order_winners(sm.P, sm.cl + etid, nthreads, k, q.x, q.y, q.z);
+                ok = tile_order_winners(sm.P, sm.cl + tid, nthreads, k, q.x, q.y, q.z);
                 for (uint32_t j = 0; ok && j < k; ++j)
                 {
-                    float4 const c = sm.P[sm.cl[etid + j * (uint32_t)nthreads]];
+                    float4 const c = sm.P[sm.cl[tid + j * (uint32_t)nthreads]];
                     idx[(size_t)row * k + j] = f2u(c.w);
                     if (d2)
                         d2[(size_t)row * k + j] =
@@ -711,55 +704,32 @@ static void tile_impl(EmuIndex* ix, uint32_t k, float eps, int mode, int level, 
     }
 }
 
-static int tile_list_size_for(uint32_t k)
-{
-    static const int sizes[] = {5, 9, 13, 16, 21, 25, 31, 33};
-    for (int s : sizes)
-        if ((uint32_t)s >= k + 1)
-            return s;
-    return 0;
-}
-
 extern "C" int emu_tile(void* h, uint32_t k, double eps, int mode, int sub, int alg, int level,
                         uint32_t max_points, double scan_cap, int nthreads, uint32_t* idx,
                         float* d2, uint32_t* cnt, float* nrm, float* ctr, float* means,
                         uint8_t* done, uint64_t* stats)
 {
     EmuIndex* ix = static_cast<EmuIndex*>(h);
+    (void)alg;
     if (level < kTileShift || level > ix->g.lfine)
         return -2;
-#define EMU_TILE(KLV, BATCHED)                                                                 \
+#define EMU_TILE(KLV)                                                                          \
     case KLV:                                                                                  \
         if (sub == 1)                                                                          \
-            tile_impl<KLV, 1, BATCHED>(ix, k, (float)eps, mode, level, max_points,             \
-                                       (float)scan_cap, nthreads, idx, d2, cnt, nrm, ctr,      \
-                                       means, done, stats);                                    \
+            tile_impl<KLV, 1>(ix, k, (float)eps, mode, level, max_points, (float)scan_cap,     \
+                              nthreads, idx, d2, cnt, nrm, ctr, means, done, stats);           \
+        else if (sub == 2)                                                                     \
+            tile_impl<KLV, 2>(ix, k, (float)eps, mode, level, max_points, (float)scan_cap,     \
+                              nthreads, idx, d2, cnt, nrm, ctr, means, done, stats);           \
         else                                                                                   \
-            tile_impl<KLV, 2, BATCHED>(ix, k, (float)eps, mode, level, max_points,             \
-                                       (float)scan_cap, nthreads, idx, d2, cnt, nrm, ctr,      \
-                                       means, done, stats);                                    \
+            tile_impl<KLV, 4>(ix, k, (float)eps, mode, level, max_points, (float)scan_cap,     \
+                              nthreads, idx, d2, cnt, nrm, ctr, means, done, stats);           \
         break;
-    if (alg == 2)
+    switch (k + 1 <= 8 ? 8 : (k + 1 <= 16 ? 16 : (k + 1 <= 32 ? 32 : 0)))
     {
-        switch (k + 1 <= 8 ? 8 : (k + 1 <= 16 ? 16 : (k + 1 <= 32 ? 32 : 0)))
-        {
-            EMU_TILE(8, true)
-            EMU_TILE(16, true)
-            EMU_TILE(32, true)
-        default: return -5;
-        }
-        return 0;
-    }
-    switch (tile_list_size_for(k))
-    {
-        EMU_TILE(5, false)
-        EMU_TILE(9, false)
-        EMU_TILE(13, false)
-        EMU_TILE(16, false)
-        EMU_TILE(21, false)
-        EMU_TILE(25, false)
-        EMU_TILE(31, false)
-        EMU_TILE(33, false)
+        EMU_TILE(8)
+        EMU_TILE(16)
+        EMU_TILE(32)
     default: return -5;
     }
 #undef EMU_TILE

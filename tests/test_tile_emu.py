@@ -52,7 +52,7 @@ def test_tile_rows_are_exact(emu, cloud_set, name):
         ridx, rd2, rcnt, _ = ix.knn(None, k, exact_only=True)
         rnrm, rctr, rmean, _ = ix.normals(None, k, want_means=True, exact_only=True)
         for level in tile_levels(ix, k):
-            for sub, alg in ((1, 1), (2, 1), (1, 2), (2, 2)):
+            for sub, alg in ((1, 2), (2, 2), (4, 2)):
                 r = ix.tile(k, 0, level, sub=sub, alg=alg, max_points=4096)
                 d = r["done"]
                 assert np.array_equal(r["idx"][d], ridx[d]), (name, k, level, sub)
@@ -73,9 +73,10 @@ def test_tile_rows_are_exact(emu, cloud_set, name):
 def test_tile_finishes_most_of_a_surface(emu, cloud_set):
     for name, k in (("plane", 15), ("sphere", 15), ("tilted", 8)):
         ix = emu.index(cloud_set[name])
-        r = ix.tile(k, 0, ix.plan(k)["level"], sub=2, max_points=4096)
-        assert r["stats"]["fallback_tiles"] == 0
-        assert r["done"].mean() > 0.9, (name, r["stats"])
+        for sub in (2, 4):
+            r = ix.tile(k, 0, ix.plan(k)["level"], sub=sub, max_points=4096)
+            assert r["stats"]["fallback_tiles"] == 0
+            assert r["done"].mean() > 0.9, (name, sub, r["stats"])
 
 
 def test_tile_scan_cap_and_fallback(emu, cloud_set):
@@ -85,8 +86,8 @@ def test_tile_scan_cap_and_fallback(emu, cloud_set):
     level = ix.plan(k)["level"]
     ridx, rd2, _, _ = ix.knn(None, k, exact_only=True)
     for cap in (0.75, 1.0, 1.5, 2.0):
-        for alg in (1, 2):
-            r = ix.tile(k, 0, level, sub=2, alg=alg, scan_cap=cap, max_points=4096)
+        for sub in (2, 4):
+            r = ix.tile(k, 0, level, sub=sub, scan_cap=cap, max_points=4096)
             d = r["done"]
             assert np.array_equal(r["idx"][d], ridx[d]) and np.array_equal(r["d2"][d], rd2[d]), cap
     # batched form: the size of the first round only changes the work, never the rows
@@ -103,8 +104,8 @@ def test_tile_scan_cap_and_fallback(emu, cloud_set):
     d = r["done"]
     assert np.array_equal(r["idx"][d], ridx[d])
     # thread count of the emulated CTA must not matter
-    a = ix.tile(k, 0, level, sub=2, nthreads=160)
-    b = ix.tile(k, 0, level, sub=2, nthreads=256)
+    a = ix.tile(k, 0, level, sub=4, nthreads=160)
+    b = ix.tile(k, 0, level, sub=4, nthreads=256)
     assert np.array_equal(a["done"], b["done"]) and np.array_equal(a["idx"], b["idx"])
 
 
@@ -119,7 +120,7 @@ def test_tile_against_reference_fixtures(emu, name):
         want = fix["%s_self_k%d_idx" % (name, k)].astype(np.int64)
         wd2 = fix["%s_self_k%d_d2" % (name, k)]
         level = max(2, ix.plan(k)["level"])
-        r = ix.tile(k, 0, level, sub=2, max_points=4096)
+        r = ix.tile(k, 0, level, sub=4, max_points=4096)
         d = r["done"] & (want[:, k - 1] >= 0)
         got = r["idx"].astype(np.int64)
         assert np.array_equal(got[d], want[d]), (name, k)

@@ -20,6 +20,8 @@ def main():
     lf = float(sys.argv[4]) if len(sys.argv) > 4 else None
     if lf is not None:
         pcpx.set_tuning("success_margin", lf)
+    for kv in filter(None, os.environ.get("PCPX_TUNING", "").split(",")):  # e.g. tile_sub=2,tile_cap=1.25
+        pcpx.set_tuning(kv.split("=")[0], float(kv.split("=")[1]))
     xyz = getattr(pcpx.synth, os.environ.get('PCPX_CLOUD', 'noisy_plane'))(n)
     d_xyz = torch.from_numpy(xyz).cuda()
     torch.cuda.synchronize()

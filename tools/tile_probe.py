@@ -33,12 +33,9 @@ def main():
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 15
     cloud = sys.argv[3] if len(sys.argv) > 3 else "noisy_plane"
     variants = [dict(tile=0),
-                dict(tile=1, tile_alg=1, tile_sub=2, tile_cap=1.0),
-                dict(tile=1, tile_alg=2, tile_sub=2, tile_cap=1.0, tile_first_cap=32),
-                dict(tile=1, tile_alg=2, tile_sub=2, tile_cap=1.0, tile_first_cap=64),
-                dict(tile=1, tile_alg=2, tile_sub=2, tile_cap=1.0, tile_first_cap=24),
-                dict(tile=1, tile_alg=2, tile_sub=1, tile_cap=1.0, tile_first_cap=32),
-                dict(tile=1, tile_alg=2, tile_sub=2, tile_cap=1.25, tile_first_cap=32)]
+                dict(tile=1, tile_sub=4, tile_cap=1.0),
+                dict(tile=1, tile_sub=2, tile_cap=1.0),
+                dict(tile=1, tile_sub=1, tile_cap=1.0)]
     if os.environ.get("PCPX_PROBE_VARIANTS"):
         variants = [variants[0]] + json.loads(os.environ["PCPX_PROBE_VARIANTS"])
     xyz = getattr(pcpx.synth, cloud)(n)
