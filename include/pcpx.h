@@ -66,7 +66,20 @@ typedef struct pcpx_index_params
     float voxel_max[3];
     uint32_t max_level;  /* finest grid level (cells per axis = 2^level); 0 = auto */
     uint32_t min_cell_occupancy; /* finest stored level keeps mean occupancy >= this; 0 = auto */
-    uint32_t reserved[8];
+    /* Several GPUs behind one handle (replicated index, queries sharded): n_devices >= 2 builds
+     * the SAME index on every listed device (devices[0] is the primary and takes the place of
+     * `device`; the cloud reaches the others by peer copy when xyz is device memory) and every
+     * kNN-shaped call with k <= 32 — pcpx_knn, pcpx_estimate_normals, pcpx_estimate_tangent_planes,
+     * pcpx_mean_knn_distance — is answered by all of them at once: device i takes the i-th
+     * contiguous share of the tile list (queries == NULL) or of the Morton-sorted queries and
+     * writes its rows straight into the primary's output buffer over NVLink (peer access is
+     * required: PCPX_ERR_UNSUPPORTED without it).  Results are bit-identical to a one-device
+     * index.  Every other call runs on the primary alone.  0 or 1: one device.
+     * (Clouds too large for one GPU are cut into slabs with halo strips one level up:
+     * point-cloud-processing_b200/sharding.py over torch.distributed, pcpx_extract_bands.) */
+    uint32_t n_devices;
+    int32_t devices[8];
+    uint32_t reserved[7];
 } pcpx_index_params;
 
 /* Facts about a built index (all filled by pcpx_index_info). */
@@ -82,6 +95,7 @@ typedef struct pcpx_index_info
     uint64_t device_bytes; /* HBM held by the index */
     int32_t device;
     float build_ms; /* device time of the build (CUDA events) */
+    uint32_t n_devices; /* devices that hold a replica of the index (1: the primary only) */
 } pcpx_index_info;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
@@ -425,11 +439,12 @@ int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
 /* Process-wide tunables (performance only, never results).  Known names:
  *   "success_margin"  a kNN-shaped call first tries the cheapest (level, rings) block whose ball
  *                     is expected to hold success_margin * (k + 1) points (default 1.15).
- *   "pool_cap_mb"     cap of the per-device cache of freed device blocks, in MiB (default 1024).
+ *   "pool_cap_mb"     cap of the per-device cache of freed device blocks, in MiB (default: one
+ *                     eighth of the device's memory, at least 1024; 0 restores the default).
  *   "tile"            1 (default): calls whose queries are the indexed points themselves take the
  *                     tile-cooperative kernel (shared-memory staged candidates); 0: never.
- *   "tile_sub"        staged layout of the tile kernel: 1 = whole cells, 2 = 2 x 2 sub-bins per
- *                     cell, 4 = 4 x 1 sub-bins (default; staged in one pass).
+ *   "tile_sub"        staged layout of the tile kernel: 1 = whole cells (staged in one pass),
+ *                     2 = 2 x 2 sub-bins per cell (default).
  *   "warp_retry"      1 (default): queries the first pass hands on are answered one warp per query
  *                     (octree descent, exact 64-bit keys); 0: per-thread retry kernels.
  *   "warp_all"        1: every kNN-shaped query takes the warp-per-query search (tests).
@@ -439,7 +454,8 @@ int pcpx_set_tuning(const char* name, double value);
 
 /* Device memory the library keeps for reuse.  Temporaries and destroyed indices go back to a
  * per-device cache (cudaMalloc / cudaFree synchronise the device and cost up to milliseconds);
- * the cache is capped — 1 GiB per device by default, PCPX_POOL_CAP_MB in the environment or
+ * the cache is capped — one eighth of the device's memory by default (at least 1 GiB),
+ * PCPX_POOL_CAP_MB in the environment or
  * pcpx_set_tuning("pool_cap_mb", x) — and blocks beyond the cap are returned to the driver at
  * once.  pcpx_trim(device) waits for the device to go idle and frees the whole cache, for
  * applications that share the GPU with other allocators. */

@@ -373,8 +373,21 @@ struct index_deleter
 };
 using index_ptr = std::unique_ptr<pcpx_index, index_deleter>;
 
-inline index_ptr make_index(std::vector<float> const& xyz, pcpx_index_params const& prm)
+inline std::vector<int>& device_list()
 {
+    static std::vector<int> devices; // empty: the current device
+    return devices;
+}
+inline index_ptr make_index(std::vector<float> const& xyz, pcpx_index_params const& prm0)
+{
+    pcpx_index_params prm = prm0;
+    std::vector<int> const& devs = device_list();
+    if (prm.n_devices == 0 && !devs.empty())
+    {
+        prm.n_devices = static_cast<std::uint32_t>(devs.size() < 8 ? devs.size() : 8);
+        for (std::uint32_t i = 0; i < prm.n_devices; ++i)
+            prm.devices[i] = devs[i];
+    }
     pcpx_index* raw = nullptr;
     check(pcpx_index_create(xyz.data(), xyz.size() / 3, 12, &prm, &raw), "pcpx_index_create");
     return index_ptr(raw);
@@ -387,6 +400,14 @@ void push_xyz(std::vector<float>& out, PV const& p)
     out.push_back(static_cast<float>(p.z()));
 }
 } // namespace detail
+
+// GPUs used by every tree built from now on (the reference's constructors have nowhere to say
+// it): the index is replicated on all of them and the batched kNN-shaped calls
+// (nearest_neighbours batches, estimate_normals / estimate_tangent_planes with a gpu_knn_map,
+// average_distance_to_neighbors) are sharded over them; devices[0] holds the results.  An empty
+// list (the default) means the current device.  See pcpx_index_params.devices (pcpx.h).
+inline void use_devices(std::vector<int> devices) { detail::device_list() = std::move(devices); }
+inline int device_count() { return pcpx_device_count(); }
 
 // Flat result of a batched kNN: row i holds counts[i] valid original indices, nearest first.
 struct knn_result_t

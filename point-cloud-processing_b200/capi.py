@@ -26,7 +26,9 @@ class IndexParams(C.Structure):
         ("voxel_max", C.c_float * 3),
         ("max_level", C.c_uint32),
         ("min_cell_occupancy", C.c_uint32),
-        ("reserved", C.c_uint32 * 8),
+        ("n_devices", C.c_uint32),
+        ("devices", C.c_int32 * 8),
+        ("reserved", C.c_uint32 * 7),
     ]
 
 
@@ -42,6 +44,7 @@ class IndexInfo(C.Structure):
         ("device_bytes", C.c_uint64),
         ("device", C.c_int32),
         ("build_ms", C.c_float),
+        ("n_devices", C.c_uint32),
     ]
 
 
@@ -280,12 +283,18 @@ class Index:
     """GPU-resident spatial index over a cloud (include/pcpx.h: pcpx_index_create)."""
 
     def __init__(self, xyz, device=-1, voxel_grid=None, max_level=0, min_cell_occupancy=0,
-                 stride_bytes=12):
+                 stride_bytes=12, devices=None):
+        """devices: list of CUDA ordinals — the index is replicated on all of them and kNN-shaped
+        calls are sharded over them (pcpx_index_params.devices); devices[0] is the primary."""
         self._h = None
         n = _count(xyz)
         buf = _Buf(xyz, np.float32)
         prm = IndexParams()
         prm.device = device
+        if devices:
+            prm.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                prm.devices[i] = int(d)
         if voxel_grid is not None:
             prm.use_voxel_grid = 1
             lo, hi = voxel_grid
@@ -324,7 +333,8 @@ class Index:
                     bbox_min=np.array(i.bbox_min[:], np.float32),
                     bbox_max=np.array(i.bbox_max[:], np.float32), code_bits=i.code_bits,
                     finest_level=i.finest_level, n_cells=i.n_cells,
-                    device_bytes=i.device_bytes, device=i.device, build_ms=i.build_ms)
+                    device_bytes=i.device_bytes, device=i.device, build_ms=i.build_ms,
+                    n_devices=i.n_devices)
 
     def timings(self):
         t = Timings()

@@ -1,8 +1,10 @@
 // The C ABI of libpcpx.so (include/pcpx.h): argument checking, host <-> device staging,
 // timing.  All compute is in index.cu / query_body.inc; there is no CPU path.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "api_util.hpp"
@@ -14,6 +16,154 @@ using namespace pcpx;
 static uint32_t knn_shaped_launches(const pcpx_index& ix, uint32_t k, bool rows_only)
 {
     return k <= kMaxK ? ix.query_launches : (rows_only ? 1u : 3u);
+}
+
+// ---- several devices behind one handle (pcpx_index_params.devices) --------------------------
+// The primary index plus one replica per further device.  A sharded call runs `fn(part_index,
+// part)` for every device at once — the caller's thread takes the primary, one host thread per
+// replica — and returns when all have finished (each launcher synchronises its own stream).
+// The first error of any device is re-thrown.
+template <class F>
+static void on_every_device(pcpx_index& ix, F&& fn)
+{
+    size_t const nrep = ix.replicas.size();
+    std::vector<std::thread> threads;
+    std::vector<std::unique_ptr<Error>> errors(nrep);
+    for (size_t r = 0; r < nrep; ++r)
+        threads.emplace_back([&, r] {
+            try
+            {
+                pcpx_index& rep = *ix.replicas[r];
+                std::lock_guard<std::mutex> lock(rep.mtx);
+                ScopedDevice guard(rep.device);
+                fn(rep, (uint32_t)r + 1u);
+            }
+            catch (Error const& e)
+            {
+                errors[r].reset(new Error(e));
+            }
+            catch (std::exception const& e)
+            {
+                errors[r].reset(new Error{PCPX_ERR_CUDA, e.what()});
+            }
+        });
+    std::unique_ptr<Error> mine;
+    try
+    {
+        fn(ix, 0u);
+    }
+    catch (Error const& e)
+    {
+        mine.reset(new Error(e));
+    }
+    for (auto& t : threads)
+        t.join();
+    if (mine)
+        throw *mine;
+    for (auto& e : errors)
+        if (e)
+            throw *e;
+}
+
+// a kNN-shaped call is spread over the replicas when there are any and k fits the register lists
+static bool sharded(const pcpx_index& ix, uint32_t k) { return !ix.replicas.empty() && k <= kMaxK; }
+
+// kernel time of a sharded call: the slowest device (each measures its own stream)
+struct PartTimer
+{
+    std::vector<float> ms;
+    explicit PartTimer(const pcpx_index& ix) : ms(ix.replicas.size() + 1, 0.f) {}
+    template <class F>
+    void run(pcpx_index& part_ix, uint32_t part, F&& launch)
+    {
+        Event a, b;
+        a.record(part_ix.stream);
+        launch();
+        b.record(part_ix.stream);
+        PCPX_CUDA(cudaStreamSynchronize(part_ix.stream));
+        ms[part] = elapsed_ms(a, b);
+    }
+    float slowest() const { return *std::max_element(ms.begin(), ms.end()); }
+};
+
+static void build_replicas(pcpx_index& ix, const float* xyz, size_t n, size_t stride_bytes,
+                           const pcpx_index_params& prm)
+{
+    int ndev = 0;
+    PCPX_CUDA(cudaGetDeviceCount(&ndev));
+    if (prm.n_devices > 8)
+        fail(PCPX_ERR_INVALID_ARG, "n_devices = %u (at most 8)", prm.n_devices);
+    for (uint32_t i = 0; i < prm.n_devices; ++i)
+    {
+        if (prm.devices[i] < 0 || prm.devices[i] >= ndev)
+            fail(PCPX_ERR_INVALID_ARG, "devices[%u] = %d out of range (%d devices)", i,
+                 prm.devices[i], ndev);
+        // (PCPX_TEST_SAME_DEVICE_REPLICAS=1: a device may be listed more than once, so that a
+        // one-GPU box can exercise the sharded code path — tests only, it buys no speed)
+        static bool const allow_dup = std::getenv("PCPX_TEST_SAME_DEVICE_REPLICAS") != nullptr;
+        for (uint32_t j = 0; j < i && !allow_dup; ++j)
+            if (prm.devices[j] == prm.devices[i])
+                fail(PCPX_ERR_INVALID_ARG, "device %d listed twice", prm.devices[i]);
+    }
+    // every replica writes its rows into the primary's buffers (and reads its staged queries)
+    for (uint32_t i = 1; i < prm.n_devices; ++i)
+    {
+        if (prm.devices[i] == ix.device)
+            continue;
+        int can = 0;
+        PCPX_CUDA(cudaDeviceCanAccessPeer(&can, prm.devices[i], ix.device));
+        if (!can)
+            fail(PCPX_ERR_UNSUPPORTED, "device %d cannot access device %d's memory (no peer access)",
+                 prm.devices[i], ix.device);
+        ScopedDevice guard(prm.devices[i]);
+        cudaError_t const e = cudaDeviceEnablePeerAccess(ix.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            fail(PCPX_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", prm.devices[i], ix.device,
+                 cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    size_t const nrep = prm.n_devices - 1;
+    ix.replicas.assign(nrep, nullptr);
+    std::vector<std::thread> threads;
+    std::vector<std::unique_ptr<Error>> errors(nrep);
+    for (size_t r = 0; r < nrep; ++r)
+        threads.emplace_back([&, r] {
+            try
+            {
+                pcpx_index_params p = prm;
+                p.device            = prm.devices[r + 1];
+                p.n_devices         = 0;
+                ScopedDevice guard(p.device);
+                if (!is_device_pointer(xyz))
+                {
+                    // host memory: the replica's build stages it on its own stream
+                    ix.replicas[r] = build_index(xyz, n, stride_bytes, &p);
+                    return;
+                }
+                // device memory (the primary's, usually): one packed copy over NVLink first, so
+                // that the build's gathers stay local.  Stream-ordered: a synchronous cudaMemcpy
+                // would not order the DMA against the build's non-blocking stream.
+                DevBuf<float> local(std::max<size_t>(3 * n, 1));
+                Stream copy_stream;
+                if (n && (stride_bytes == 0 || stride_bytes == 12)) // packed rows: one DMA
+                    PCPX_CUDA(cudaMemcpyAsync(local.get(), xyz, 12 * n, cudaMemcpyDefault,
+                                              copy_stream.s));
+                else if (n)
+                    PCPX_CUDA(cudaMemcpy2DAsync(local.get(), 12, xyz, stride_bytes, 12, n,
+                                                cudaMemcpyDefault, copy_stream.s));
+                PCPX_CUDA(cudaStreamSynchronize(copy_stream.s));
+                ix.replicas[r] = build_index(local.get(), n, 12, &p);
+            }
+            catch (Error const& e)
+            {
+                errors[r].reset(new Error(e));
+            }
+        });
+    for (auto& t : threads)
+        t.join();
+    for (auto& e : errors)
+        if (e)
+            throw *e;
 }
 
 extern "C" {
@@ -38,7 +188,27 @@ int pcpx_index_create(const float* xyz, size_t n, size_t stride_bytes,
         if (!out_index)
             fail(PCPX_ERR_INVALID_ARG, "out_index is NULL");
         *out_index = nullptr;
-        *out_index = build_index(xyz, n, stride_bytes, params);
+        pcpx_index_params prm{};
+        if (params)
+            prm = *params;
+        if (prm.n_devices >= 1)
+            prm.device = prm.devices[0];
+        std::unique_ptr<pcpx_index> ix(build_index(xyz, n, stride_bytes, &prm));
+        if (prm.n_devices >= 2)
+        {
+            // replicas are built while nothing else uses the primary; a failure frees everything
+            try
+            {
+                build_replicas(*ix, xyz, n, stride_bytes, prm);
+            }
+            catch (...)
+            {
+                ScopedDevice guard(ix->device);
+                ix.reset();
+                throw;
+            }
+        }
+        *out_index = ix.release();
     });
 }
 
@@ -71,6 +241,9 @@ int pcpx_index_info_get(const pcpx_index* index, pcpx_index_info* out)
         out->device_bytes = ix.device_bytes();
         out->device       = ix.device;
         out->build_ms     = ix.timings.build_ms;
+        out->n_devices    = (uint32_t)ix.replicas.size() + 1u;
+        for (pcpx_index const* r : ix.replicas)
+            out->build_ms = std::max(out->build_ms, r->timings.build_ms);
     });
 }
 
@@ -99,8 +272,22 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
         cnt.prepare(out_count, nq);
         DevBuf<uint32_t> retries(1);
         PCPX_CUDA(cudaMemsetAsync(retries.get(), 0, 4, ix.stream));
+        PartTimer parts(ix);
         timer.kernel_begin();
-        launch_knn(ix, batch.qb, k, (float)eps, idx.d, d2.d, cnt.d, retries.get());
+        if (sharded(ix, k))
+        {
+            PCPX_CUDA(cudaStreamSynchronize(ix.stream)); // staged queries are in place
+            on_every_device(ix, [&](pcpx_index& dev_ix, uint32_t part) {
+                QueryBatch qb = batch.qb;
+                qb.part = part, qb.parts = (uint32_t)ix.replicas.size() + 1u;
+                parts.run(dev_ix, part, [&] {
+                    launch_knn(dev_ix, qb, k, (float)eps, idx.d, d2.d, cnt.d,
+                               part == 0 ? retries.get() : nullptr);
+                });
+            });
+        }
+        else
+            launch_knn(ix, batch.qb, k, (float)eps, idx.d, d2.d, cnt.d, retries.get());
         timer.kernel_end();
         ix.timings.kernel_launches = knn_shaped_launches(ix, k, true);
         idx.finish(ix.stream), d2.finish(ix.stream), cnt.finish(ix.stream);
@@ -108,6 +295,8 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
         PCPX_CUDA(cudaMemcpyAsync(&h_retries, retries.get(), 4, cudaMemcpyDeviceToHost,
                                   ix.stream));
         timer.done();
+        if (sharded(ix, k))
+            ix.timings.kernel_ms = parts.slowest();
         ix.timings.retry_queries = h_retries;
     });
 }
@@ -225,14 +414,30 @@ static void normals_impl(const pcpx_index* index, const float* queries, size_t n
     ctr.prepare(out_points, nq * 3);
     DevBuf<uint32_t> ties(1);
     PCPX_CUDA(cudaMemsetAsync(ties.get(), 0, 4, ix.stream));
+    PartTimer parts(ix);
     timer.kernel_begin();
-    launch_normals(ix, batch.qb, k, (float)eps, ctr.d, nrm.d, ties.get());
+    if (sharded(ix, k))
+    {
+        PCPX_CUDA(cudaStreamSynchronize(ix.stream)); // staged queries are in place
+        on_every_device(ix, [&](pcpx_index& dev_ix, uint32_t part) {
+            QueryBatch qb = batch.qb;
+            qb.part = part, qb.parts = (uint32_t)ix.replicas.size() + 1u;
+            parts.run(dev_ix, part, [&] {
+                launch_normals(dev_ix, qb, k, (float)eps, ctr.d, nrm.d,
+                               part == 0 ? ties.get() : nullptr);
+            });
+        });
+    }
+    else
+        launch_normals(ix, batch.qb, k, (float)eps, ctr.d, nrm.d, ties.get());
     timer.kernel_end();
     ix.timings.kernel_launches = knn_shaped_launches(ix, k, false);
     nrm.finish(ix.stream), ctr.finish(ix.stream);
     uint32_t h_ties = 0;
     PCPX_CUDA(cudaMemcpyAsync(&h_ties, ties.get(), 4, cudaMemcpyDeviceToHost, ix.stream));
     timer.done();
+    if (sharded(ix, k))
+        ix.timings.kernel_ms = parts.slowest();
     ix.timings.retry_queries = h_ties;
 }
 
@@ -324,7 +529,14 @@ int pcpx_mean_knn_distance(const pcpx_index* index, uint32_t k, double eps, floa
         DevBuf<double> sum(1);
         DevBuf<uint32_t> valid(1);
         timer.kernel_begin();
-        launch_mean_distance(ix, qb, k, (float)eps, means.d);
+        if (sharded(ix, k))
+            on_every_device(ix, [&](pcpx_index& dev_ix, uint32_t part) {
+                QueryBatch q = qb;
+                q.part = part, q.parts = (uint32_t)ix.replicas.size() + 1u;
+                launch_mean_distance(dev_ix, q, k, (float)eps, means.d);
+            });
+        else
+            launch_mean_distance(ix, qb, k, (float)eps, means.d);
         launch_mean_reduce(ix, means.d, (uint32_t)n, sum.get(), valid.get());
         timer.kernel_end();
         ix.timings.kernel_launches = knn_shaped_launches(ix, k, false) + 2u; // + the two-stage reduction

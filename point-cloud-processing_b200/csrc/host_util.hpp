@@ -107,9 +107,11 @@ class DevicePool
         return p;
     }
     // A freed block is kept for reuse only while the device's cache stays under its cap
-    // (default 1 GiB, PCPX_POOL_CAP_MB / pcpx_set_tuning("pool_cap_mb")): the smallest cached
-    // blocks are returned to the driver until the newcomer fits, and a block larger than the cap
-    // itself goes straight back — a destroyed 100 M-point index does not stay resident.
+    // (default: one eighth of the device's memory, at least 1 GiB — a step over a 100 M-point cloud
+    // re-uses ~6 GB of blocks, and a cap below the working set turns every step into
+    // cudaFree + cudaMalloc, both device-synchronising; PCPX_POOL_CAP_MB /
+    // pcpx_set_tuning("pool_cap_mb") set it explicitly): the smallest cached blocks are returned
+    // to the driver until the newcomer fits, and a block larger than the cap goes straight back.
     void release(void* p)
     {
         if (!p)
@@ -128,6 +130,7 @@ class DevicePool
                 size_t const bytes = it->second;
                 auto& fl           = free_[dev];
                 size_t& cached     = cached_[dev];
+                size_t const cap_  = cap_for(dev);
                 if (bytes > cap_)
                 {
                     size_.erase(p), dev_.erase(p);
@@ -188,8 +191,30 @@ class DevicePool
         if (const char* e = std::getenv("PCPX_POOL_CAP_MB"))
             cap_ = (size_t)std::strtoull(e, nullptr, 10) << 20;
     }
+    // (m_ held) explicit cap, or one eighth of the device's memory
+    size_t cap_for(int dev)
+    {
+        if (cap_ != 0)
+            return cap_;
+        auto it = auto_cap_.find(dev);
+        if (it != auto_cap_.end())
+            return it->second;
+        size_t free_b = 0, total_b = 0;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != dev)
+            cudaSetDevice(dev);
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+            total_b = 0, cudaGetLastError();
+        if (cur != dev)
+            cudaSetDevice(cur);
+        size_t const cap = std::max<size_t>((size_t)1 << 30, total_b / 8);
+        auto_cap_[dev]   = cap;
+        return cap;
+    }
     std::mutex m_;
-    size_t cap_ = (size_t)1 << 30;
+    size_t cap_ = 0; // 0: automatic
+    std::map<int, size_t> auto_cap_;
     std::map<int, size_t> cached_;
     std::map<int, std::multimap<size_t, void*>> free_;
     std::map<void*, size_t> size_;
@@ -294,6 +319,19 @@ struct Event
     Event(const Event&)            = delete;
     Event& operator=(const Event&) = delete;
     void record(cudaStream_t s) { PCPX_CUDA(cudaEventRecord(e, s)); }
+};
+
+struct Stream
+{
+    cudaStream_t s = nullptr;
+    Stream() { PCPX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+    ~Stream()
+    {
+        if (s)
+            cudaStreamDestroy(s);
+    }
+    Stream(const Stream&)            = delete;
+    Stream& operator=(const Stream&) = delete;
 };
 
 inline float elapsed_ms(const Event& a, const Event& b)

@@ -1,6 +1,7 @@
 // The GPU-resident index object behind the opaque pcpx_index handle.
 #pragma once
 #include <mutex>
+#include <vector>
 
 #include "grid_core.cuh"
 #include "host_util.hpp"
@@ -31,9 +32,17 @@ struct pcpx_index
     mutable int tile_level         = -1;
     mutable uint32_t tile_capacity = 0;
     mutable uint32_t tile_region   = 0; // staged-region capacity that fits 97 % of the queries' tiles
+    // the same index on further devices (pcpx_index_params.devices[1..]); owned
+    std::vector<pcpx_index*> replicas;
 
     ~pcpx_index()
     {
+        for (pcpx_index* r : replicas)
+        {
+            cudaSetDevice(r->device);
+            delete r;
+        }
+        cudaSetDevice(device);
         if (stream)
             cudaStreamDestroy(stream);
     }

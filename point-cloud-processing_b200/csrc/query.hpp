@@ -13,6 +13,11 @@ struct QueryBatch
     uint32_t stride_f;
     const uint32_t* order;
     uint32_t nq;
+    // device shards (pcpx_index_params.devices): the kNN-shaped launchers answer share `part` of
+    // `parts` — a range of the tile list, or of the sorted queries [t_begin, nq) — and leave the
+    // other rows of the output untouched
+    uint32_t t_begin = 0;
+    uint32_t part = 0, parts = 1;
 };
 
 struct Tuning
@@ -23,7 +28,7 @@ struct Tuning
     int tile           = 1;    // 0: never
     int tile_first_cap = 0;    // batched form: candidates listed before the ball first shrinks (0: 2 (k + 1))
     int tile_min_queries = 24; // tiles with fewer points go to the per-thread path unstaged
-    int tile_sub       = 2;    // staged layout: 1 = whole cells, 2 = 2 x 2 sub-bins per cell, 4 = 4 x 1; 1 and 4 are staged in one pass
+    int tile_sub       = 2;    // staged layout: 1 = whole cells (staged in one pass), 2 = 2 x 2 sub-bins per cell
     float tile_cap     = 1.0f; // largest scan radius in units of the main-level cell
     int warp_retry     = 1;    // what the first pass hands on: 1 = one warp per query (warp_core.cuh), 0 = per-thread retry kernels
     int warp_all       = 0;    // (tests) every kNN-shaped query by the warp-per-query search

@@ -22,10 +22,10 @@
 //
 // The first descent starts from the 3x3x3 block of the query's cell one level above the call's
 // main level — a near miss is final there after two or three rounds (k-th distance strictly
-// inside the block) —, anything else restarts from the root with the k-th distance of the first
-// attempt as its pruning bound.  Keys are exact and totally ordered (distinct original
-// indices), so rows come out in the (d2, original index) order of the parity contract with no
-// tie handling at all.  Device only (shuffles); the GPU parity suite runs every cloud of the
+// inside the block) —; what is not restarts from a block three levels coarser (cells 8 x larger),
+// and so on up to the root, each attempt pruned by the k-th distance of the one before.  Keys are
+// exact and totally ordered (distinct original indices), so rows come out in the (d2, original
+// index) order of the parity contract with no tie handling at all.  Device only (shuffles); the GPU parity suite runs every cloud of the
 // oracle tests through it (tuning "warp_all").
 #pragma once
 #include "normals_core.cuh"
@@ -107,10 +107,12 @@ struct WarpKnn
 // One descent.  `ckey / clb2 / cvalid`: this lane's cell of the initial batch.  `prune`: squared
 // distance no neighbour can exceed (INFINITY when unknown).  On return the list holds the k
 // nearest eligible points among everything under the initial cells whose bound is <= prune.
+// `min_total`: when the initial cells hold fewer points than this the descent is abandoned
+// before anything is scanned (the list stays empty).
 __device__ __forceinline__ void warp_descend(const GridView& g, WarpStack& st, float qx, float qy,
                                              float qz, uint32_t k, float eps, float prune,
-                                             uint64_t ckey, float clb2, bool cvalid, WarpKnn& top,
-                                             int lane)
+                                             uint32_t min_total, uint64_t ckey, float clb2,
+                                             bool cvalid, WarpKnn& top, int lane)
 {
     top.key = kEmptyEntry, top.pos = 0u;
     int sp  = 0;
@@ -122,6 +124,12 @@ __device__ __forceinline__ void warp_descend(const GridView& g, WarpStack& st, f
         bool found = false;
         if (cvalid && clb2 <= tau)
             found = find_cell(g, ckey, start, count);
+        if (min_total != 0u)
+        {
+            if (__reduce_add_sync(kFullMask, found ? count : 0u) < min_total)
+                return;
+            min_total = 0u;
+        }
         int const level = (int)(ckey >> 57);
         bool const room = sp + 32 <= kWarpStackCap;
         bool const leaf = found && (level >= g.lfine || count <= kWarpLeafSize || !room);
@@ -183,17 +191,43 @@ __device__ __forceinline__ void warp_descend(const GridView& g, WarpStack& st, f
             sp += (int)n_in;
         }
         __syncwarp();
-        // ---- next batch: the children of the (up to) four nearest open cells ----
-        if (sp == 0)
-            break;
-        int const P = sp < 4 ? sp : 4, p = lane >> 3;
-        cvalid      = p < P;
+        // ---- next batch: the children of the (up to) four topmost cells still worth opening;
+        // entries whose bound the k-th distance has overtaken are dropped a window at a time ----
         uint64_t pk = 0;
         float plb   = 0.f;
-        if (cvalid)
-            pk = st.key[sp - 1 - p], plb = st.lb2[sp - 1 - p];
-        sp -= P;
+        int P       = 0;
+        while (sp > 0)
+        {
+            int const idx     = sp - 1 - lane;
+            bool const live   = idx >= 0 && st.lb2[idx] <= tau;
+            uint32_t const m  = __ballot_sync(kFullMask, live);
+            int const n_live  = __popc(m);
+            if (n_live == 0)
+            {
+                sp = sp > 32 ? sp - 32 : 0;
+                continue;
+            }
+            P = n_live < 4 ? n_live : 4;
+            // lane of the p-th live entry (p = lane >> 3), and of the last one taken
+            uint32_t t = m;
+            for (int i = 0; i < (lane >> 3); ++i)
+                t &= t - 1u;
+            int const mine = (lane >> 3) < P ? __ffs((int)t) - 1 : -1;
+            uint32_t u = m;
+            for (int i = 1; i < P; ++i)
+                u &= u - 1u;
+            int const last = __ffs((int)u) - 1;
+            if (mine >= 0)
+                pk = st.key[sp - 1 - mine], plb = st.lb2[sp - 1 - mine];
+            // fewer than four live entries in the window: the rest of it is dead too
+            int const used = n_live <= 4 ? 32 : last + 1;
+            sp             = sp > used ? sp - used : 0;
+            break;
+        }
         __syncwarp();
+        if (P == 0)
+            break;
+        cvalid = (lane >> 3) < P;
         cvalid = cvalid && plb <= tau;
         int const cl = (int)(pk >> 57) + 1;
         uint32_t const cx = 2u * (uint32_t)(pk & 0x7FFFFu) + (uint32_t)(lane & 1),
@@ -204,16 +238,19 @@ __device__ __forceinline__ void warp_descend(const GridView& g, WarpStack& st, f
     }
 }
 
-// The whole search of one query by one warp.  Returns true when the first attempt (the block one
-// level above `level`) was final.
+// The whole search of one query by one warp: blocks of 3x3x3 cells around the query at levels
+// level - 1, level - 4, ... (a block is final when the k-th distance lies strictly inside it;
+// a block with fewer than k + 1 points is not even scanned), then the whole tree.  Every failed
+// attempt leaves its k-th distance as the pruning bound of the next.  Returns true when the
+// first attempt was final.
 __device__ __forceinline__ bool warp_knn(const GridView& g, WarpStack& st, float qx, float qy,
                                          float qz, uint32_t k, float eps, int level, WarpKnn& top,
                                          int lane)
 {
     QueryCell const qc = query_cell(g, qx, qy, qz);
     float prune        = INFINITY;
-    int const ls       = level > 0 ? level - 1 : 0;
-    if (ls > 0)
+    bool first         = true;
+    for (int ls = level - 1; ls > 0; ls -= 3, first = false)
     {
         BlockGeom const b = block_geom(g, qc, ls, qx, qy, qz);
         int const dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
@@ -225,14 +262,14 @@ __device__ __forceinline__ bool warp_knn(const GridView& g, WarpStack& st, float
         float const lb2 = warp_cell_lb2(g, ldexpf(g.extent, -ls), (uint32_t)(valid ? cx : 0),
                                         (uint32_t)(valid ? cy : 0), (uint32_t)(valid ? cz : 0), qx,
                                         qy, qz);
-        warp_descend(g, st, qx, qy, qz, k, eps, INFINITY, key, lb2, valid, top, lane);
+        warp_descend(g, st, qx, qy, qz, k, eps, prune, k + 1u, key, lb2, valid, top, lane);
         float const kd2 = top.kth_d2(k);
         if (kd2 < b.block_lb2) // strictly inside the block: nothing outside can tie
-            return true;
-        prune = kd2;
+            return first;
+        prune = fminf(prune, kd2);
     }
-    warp_descend(g, st, qx, qy, qz, k, eps, prune, cell_key(0, 0u, 0u, 0u), 0.f, lane == 0, top,
-                 lane);
+    warp_descend(g, st, qx, qy, qz, k, eps, prune, 0u, cell_key(0, 0u, 0u, 0u), 0.f, lane == 0,
+                 top, lane);
     return false;
 }
 

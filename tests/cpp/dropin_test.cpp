@@ -297,6 +297,43 @@ static void normals_scenarios()
         REQUIRE(kept[i - 1].point() < kept[i].point());
 }
 
+// Two GPUs behind the reference's own calls (pcp::use_devices): the index is replicated, the
+// batched calls are sharded, and every result equals the one-GPU result bit for bit.
+static void two_device_scenario()
+{
+    std::mt19937 gen(7);
+    std::uniform_real_distribution<float> u(0.f, 1.f);
+    std::normal_distribution<float> g(0.f, 1.f);
+    std::vector<pcp::point_t> points;
+    for (int i = 0; i < 200000; ++i)
+        points.push_back({u(gen), u(gen), 0.002f * g(gen)});
+    for (int i = 0; i < 5000; ++i) // stray points: the warp-per-query path on both devices
+        points.push_back({u(gen), u(gen), u(gen) - 0.5f});
+    using octree_type = pcp::basic_linked_octree_t<pcp::point_t>;
+    auto run = [&](std::vector<pcp::normal_t>& normals, pcp::knn_result_t& rows, float& mean) {
+        octree_type octree{points.begin(), points.end(), point_map};
+        normals.assign(points.size(), pcp::normal_t{});
+        pcp::algorithm::estimate_normals(
+            std::execution::par, points.begin(), points.end(), normals.begin(), point_map,
+            pcp::make_gpu_knn_map(octree, 15u, point_map),
+            pcp::algorithm::default_normal_transform<pcp::point_t, pcp::normal_t>);
+        rows = octree.nearest_neighbours(points.begin(), points.begin() + 20000, 10u, point_map);
+        mean = pcp::algorithm::average_distance_to_neighbors(octree, 15u);
+    };
+    std::vector<pcp::normal_t> n1, n2;
+    pcp::knn_result_t r1, r2;
+    float m1 = 0.f, m2 = 0.f;
+    run(n1, r1, m1);
+    pcp::use_devices({0, 1});
+    run(n2, r2, m2);
+    pcp::use_devices({});
+    REQUIRE(r1.indices == r2.indices && r1.squared_distances == r2.squared_distances &&
+            r1.counts == r2.counts);
+    REQUIRE(m1 == m2);
+    for (std::size_t i = 0; i < n1.size(); ++i)
+        REQUIRE(n1[i].x() == n2[i].x() && n1[i].y() == n2[i].y() && n1[i].z() == n2[i].z());
+}
+
 // test/algorithm/bilateral_filter.cpp and test/algorithm/wlop.cpp, same calls
 static void smoothing_scenarios()
 {
@@ -508,6 +545,11 @@ int main()
     orientation_scenario();
     ply_round_trip();
     geometry_helpers();
+    if (pcp::device_count() >= 2)
+    {
+        two_device_scenario();
+        std::printf("dropin_test: two-device scenario holds\n");
+    }
     std::printf("dropin_test: all scenarios hold\n");
     return 0;
 }

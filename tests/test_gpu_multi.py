@@ -49,3 +49,85 @@ def test_two_ranks_equal_one_gpu(tmp_path):
         assert seen.all()
     # the noise mix cannot be answered from the first strip: the repair rounds ran
     assert int(parts[0]["mix_rounds"][0]) > 1
+
+
+def test_sharded_calls_on_one_gpu(pcpx, oracle):
+    """The sharded code path of a multi-device handle on a ONE-GPU box: with
+    PCPX_TEST_SAME_DEVICE_REPLICAS set a device may be listed several times, so three replicas
+    on device 0 answer three shares of every kNN-shaped call — tile ranges, sorted-query ranges,
+    their own hand-on queues.  Rows against the oracle and against the plain one-device handle."""
+    import importlib
+
+    os.environ["PCPX_TEST_SAME_DEVICE_REPLICAS"] = "1"
+    synth = importlib.import_module("point-cloud-processing_b200.synth")
+    rng = np.random.default_rng(4)
+    xyz = synth.noise_mix(120_000, seed=8)
+    q = (xyz[rng.choice(len(xyz), 20_000)] + rng.normal(0, 0.02, (20_000, 3))).astype(np.float32)
+    oc = oracle.cloud(xyz)
+    with pcpx.Index(xyz) as one, pcpx.Index(xyz, devices=[0, 0, 0]) as many:
+        assert many.info()["n_devices"] == 3
+        for k in (8, 15):
+            for qq in (None, q):
+                a, b = one.knn(qq, k), many.knn(qq, k)
+                assert all(np.array_equal(x, y) for x, y in zip(a, b)), (k, qq is None)
+            oi, od2, ocnt = oc.knn(q, k)
+            idx = b[0].astype(np.int64)
+            idx[b[0] == 0xFFFFFFFF] = -1
+            assert np.array_equal(idx, oi) and np.array_equal(b[1], od2) and np.array_equal(b[2], ocnt)
+            assert np.array_equal(one.estimate_normals(None, k), many.estimate_normals(None, k),
+                                  equal_nan=True)
+            pa, ma = one.mean_knn_distance(k)
+            pb, mb = many.mean_knn_distance(k)
+            assert np.array_equal(pa, pb, equal_nan=True) and ma == mb
+        for tile in (0, 1):  # the block-search path shards by sorted-query range
+            pcpx.set_tuning("tile", tile)
+            a, b = one.knn(None, 15), many.knn(None, 15)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), tile
+        pcpx.set_tuning("tile", 1)
+
+
+def test_replicated_index_equals_one_gpu(pcpx):
+    """Several GPUs behind ONE C-ABI handle (pcpx_index_params.devices: replicated index, kNN-shaped
+    calls sharded by tile range / sorted-query range, rows written into the primary's buffers over
+    NVLink): every output equals the one-device answer bit for bit — self queries (tile pass +
+    warp-per-query kernel on every device), external queries, normals, tangent planes, mean
+    distances; host and device-resident outputs; plane and noise mix."""
+    import importlib
+
+    import torch
+
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    synth = importlib.import_module("point-cloud-processing_b200.synth")
+    devices = list(range(min(ndev, 4)))
+    rng = np.random.default_rng(9)
+    for name, xyz in (("plane", synth.noisy_plane(400_000, seed=5)), ("mix", synth.noise_mix(300_000, seed=6))):
+        q = (xyz[rng.choice(len(xyz), 50_000)] + rng.normal(0, 0.01, (50_000, 3))).astype(np.float32)
+        with pcpx.Index(xyz) as one, pcpx.Index(xyz, devices=devices) as many:
+            assert many.info()["n_devices"] == len(devices) and one.info()["n_devices"] == 1
+            for k in (1, 15, 30):
+                for qq in (None, q):
+                    a, b = one.knn(qq, k), many.knn(qq, k)
+                    for x, y in zip(a, b):
+                        assert np.array_equal(x, y), (name, k, qq is None)
+                assert np.array_equal(one.estimate_normals(None, k), many.estimate_normals(None, k),
+                                      equal_nan=True), (name, k)
+                pa, ma = one.mean_knn_distance(k)
+                pb, mb = many.mean_knn_distance(k)
+                assert np.array_equal(pa, pb, equal_nan=True) and (ma == mb or (ma != ma and mb != mb))
+            ca, na = one.estimate_tangent_planes(None, 15)
+            cb, nb = many.estimate_tangent_planes(None, 15)
+            assert np.array_equal(ca, cb, equal_nan=True) and np.array_equal(na, nb, equal_nan=True)
+            # k beyond the register lists is answered by the primary alone
+            a, b = one.knn(q[:2000], 40), many.knn(q[:2000], 40)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+            # device-resident outputs on the primary
+            d_xyz = torch.from_numpy(xyz).cuda(devices[0])
+            out = torch.empty((len(xyz), 3), dtype=torch.float32, device="cuda:%d" % devices[0])
+            many.estimate_normals(None, 15, out=out)
+            assert np.array_equal(out.cpu().numpy(), one.estimate_normals(None, 15), equal_nan=True)
+        # the cloud itself in device memory: replicas fetch it by peer copy
+        with pcpx.Index(d_xyz, devices=devices) as many, pcpx.Index(xyz) as one:
+            assert np.array_equal(many.estimate_normals(None, 15), one.estimate_normals(None, 15),
+                                  equal_nan=True)

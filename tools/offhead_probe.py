@@ -16,7 +16,7 @@ def main():
         idx = torch.empty((n, k), dtype=torch.int32, device="cuda")
         cnt = torch.empty((n,), dtype=torch.int32, device="cuda")
         nrm = torch.empty((n, 3), dtype=torch.float32, device="cuda")
-        for tile, extra in ((0, {}), (1, {})):
+        for tile, extra in ((0, {"warp_retry": 0}), (0, {"warp_retry": 1}), (1, {"warp_retry": 0}), (1, {"warp_retry": 1})):
             pcpx.set_tuning("tile", tile)
             pcpx.set_tuning("tile_min_queries", 24)
             pcpx.set_tuning("tile_margin", 1.15)
