@@ -29,7 +29,9 @@ sort -> cell tables) + the fused kNN -> PCA normal kernel over all of its points
           its own gather-model roofline): knn_k15, radius_r0.01, build on the same 10 M plane;
           density_filter_mix (10 M points, 5 % uniform noise); knn_k8_sphere_10M — N = 1 only.
           For every N: scan100M_k30 (configs[3]: k = 30 normals over a 100 M-point scan cut into
-          N slabs) and, for N > 1, strong (the ONE 10 M-point plane cut into N slabs).
+          N slabs) and, for N > 1, strong (the ONE 10 M-point plane cut into N slabs) and
+          replicated (the same plane through ONE C-ABI handle replicated on all N devices,
+          pcpx_index_params.devices, driven by rank 0).
 
 N > 1 ("weak" headline): every rank owns one 10 M-point slab of an N x 10 M-point plane plus a
 0.05-wide halo of its neighbours' points; the halo strips are exchanged between neighbouring
@@ -439,7 +441,8 @@ def run_ours(args):
     achieved = ALGORITHMIC_BYTES_PER_NORMAL * n_local / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "tile_knn2_kernel<16, MODE_NORMALS, S=2> (+ tile list, + retry kernel)",
+                "kernel": "tile_knn2_kernel<16, MODE_NORMALS, S=2, 96 threads> (+ tile list, + the "
+                          "warp-per-query kernel for what the tile pass hands on)",
                 "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_NORMAL * n_local,
                 "peak_source": peak_src,
@@ -520,8 +523,10 @@ def run_ours(args):
         d_mask = torch.empty((N_POINTS,), dtype=torch.uint8, device="cuda")
         d_keep = torch.empty((N_POINTS, 3), dtype=torch.float32, device="cuda")
         with pcpx.Index(mix, device=local_rank) as ix:
+            ix.mean_knn_distance(K)  # (first use: kernel module load, tile list)
             radius = float(ix.mean_knn_distance(K)[1])
             mean_ms = ix.timings()["kernel_ms"]
+            mean_t = ix.timings()
             kept = [0]
 
             def flt():
@@ -535,7 +540,9 @@ def run_ours(args):
                 "workload": "density filter (radius = mean 15-NN distance, threshold 5) on 10M points with 5% uniform noise",
                 "units_per_s": N_POINTS / (med * 1e-3), "unit": "points/s", "kernel_ms": med,
                 "best_ms": best, "radius": radius, "mean_count": mbar, "kept": int(kept[0]),
-                "mean_knn_distance_kernel_ms": mean_ms, "bytes_per_unit": a_flt,
+                "mean_knn_distance_kernel_ms": mean_ms,
+                "mean_knn_distance_handed_on": int(mean_t["deferred_queries"]),
+                "bytes_per_unit": a_flt,
                 "frac": frac_of(a_flt, N_POINTS, med)}
         del mix, d_mask, d_keep
         # configs[4], one point of the sweep: kNN k=8 over a 10 M-point noisy sphere
@@ -589,6 +596,47 @@ def run_ours(args):
             pts, side * rank / world, side * (rank + 1) / world, 30, 12 + 12 * 30 + 12,
             "estimate_normals k=30 over a 100M-point synthetic scan (height field + sphere), "
             "cut into %d slab(s) along x; index build + halo exchange + normals per step" % world)
+
+    if not args.no_extras and world > 1:
+        # replicated: ONE handle of the C ABI over all N devices (pcpx_index_params.devices): the
+        # index of the seed-7 10 M-point plane is built on every device, the normals call is
+        # sharded by tile range, rows land in device 0's buffer over NVLink.  Rank 0 drives it from
+        # one process while the other ranks wait; timed by the host around the blocking calls.
+        barrier()
+        if rank == 0:
+            full = torch.from_numpy(pcpx.synth.noisy_plane(N_POINTS)).cuda()
+            out1 = torch.empty((N_POINTS, 3), dtype=torch.float32, device="cuda")
+            outn = torch.empty((N_POINTS, 3), dtype=torch.float32, device="cuda")
+            with pcpx.Index(full, device=local_rank) as ix1:
+                ix1.estimate_normals(None, K, out=out1)
+            devs = [local_rank] + [d for d in range(world) if d != local_rank]
+            t0 = time.perf_counter()
+            ixn = pcpx.Index(full, devices=devs)
+            first_build = (time.perf_counter() - t0) * 1e3
+            ixn.close()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ixn = pcpx.Index(full, devices=devs)
+            build_wall = (time.perf_counter() - t0) * 1e3
+            wall, kern = [], []
+            for _ in range(leg_steps + leg_warm):
+                t0 = time.perf_counter()
+                ixn.estimate_normals(None, K, out=outn)
+                wall.append((time.perf_counter() - t0) * 1e3)
+                kern.append(ixn.timings()["kernel_ms"])
+            ixn.close()
+            w = float(np.median(wall[leg_warm:]))
+            extras["replicated"] = {
+                "workload": "estimate_normals k=15 over the ONE 10M-point noisy plane through one C-ABI "
+                            "handle replicated on %d devices (index resident, call sharded by tile "
+                            "range, rows written to device 0 over NVLink); host-timed blocking call" % world,
+                "units_per_s": N_POINTS / (w * 1e-3), "unit": "normals/s", "call_ms": w,
+                "kernel_ms_slowest_device": float(np.median(kern[leg_warm:])),
+                "build_wall_ms": build_wall, "first_build_wall_ms": first_build,
+                "equal_to_one_device": bool(torch.equal(out1, outn)), "n_gpus": world}
+            del full, out1, outn
+            torch.cuda.empty_cache()
+        barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

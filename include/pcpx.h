@@ -429,9 +429,10 @@ typedef struct pcpx_timings
     float kernel_ms;    /* the query kernel proper (kNN / normals / radius / filter) */
     float total_ms;     /* whole call on the device incl. H2D / D2H staging */
     uint32_t kernel_launches; /* kernels launched by the last call */
-    uint32_t retry_queries;   /* queries that needed the exact tie / expansion slow path */
-    uint32_t deferred_queries; /* kNN-shaped calls: queries the tile pass handed to the per-thread path */
-    uint32_t expanded_queries; /* ... queries that went on to the retry kernel (coarser levels / tree) */
+    uint32_t retry_queries;   /* queries the block search answered through its exact tie path */
+    uint32_t deferred_queries; /* kNN-shaped calls: queries the first pass (tile kernel / block search)
+                                  handed on to the warp-per-query kernel (device shards: the primary's) */
+    uint32_t expanded_queries; /* ... of those, queries whose first block attempt there was not final */
 } pcpx_timings;
 
 int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);

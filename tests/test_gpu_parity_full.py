@@ -93,6 +93,40 @@ def test_reference_fixtures(pcpx, fix, name):
         assert np.array_equal(per, fix[name + "_mean15"], equal_nan=True)
 
 
+SCANS = ["stanford_bunny", "fandisk", "detergent", "spray"]
+
+
+@pytest.mark.parametrize("name", SCANS)
+def test_reference_real_scans(pcpx, oracle, name):
+    """the reference's example scans (examples/data/*.ply), answers produced by the
+    UNMODIFIED reference (tests/golden/ref_scans.npz, make_scan_fixtures.py): full-cloud kNN
+    k = 15 rows, per-point mean 15-NN distances and sphere-range counts bit-exact — through the
+    default flow (tile pass + warp-per-query kernel), the block-search flow and the warp-only
+    flow; normals against the oracle's on the same neighbourhoods."""
+    fix = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_scans.npz"))
+    xyz = fix[name + "_xyz"]
+    want_idx, want_d2 = fix[name + "_k15_idx"].astype(np.int64), fix[name + "_k15_d2"]
+    with pcpx.Index(xyz) as ix:
+        for knob, val in (("tile", 1), ("tile", 0), ("warp_all", 1)):
+            pcpx.set_tuning(knob, val)
+            try:
+                idx, d2, cnt = ix.knn(None, 15)
+                per, _ = ix.mean_knn_distance(15)
+            finally:
+                pcpx.set_tuning("tile", 1), pcpx.set_tuning("warp_all", 0)
+            assert np.array_equal(as_i64(idx), want_idx), (name, knob, val)
+            assert np.array_equal(d2, want_d2), (name, knob, val)
+            assert np.all(cnt == 15)
+            assert np.array_equal(per, fix[name + "_mean15"], equal_nan=True), (name, knob, val)
+        assert np.array_equal(ix.radius_count(None, float(fix[name + "_radius_r"])),
+                              fix[name + "_radius_count"])
+        nrm = ix.estimate_normals(None, 15)
+        onrm, gap = oracle.cloud(xyz).normals(None, 15)
+        err = 1 - np.abs((nrm * onrm).sum(1))
+        assert err[gap > 1e-3].max() <= 1e-4
+        assert (gap > 1e-3).mean() > 0.9
+
+
 # ---- (iii) the oracle on seeded clouds and edge cases ---------------------------------------
 @pytest.mark.parametrize("k", [1, 4, 8, 10, 15, 16, 21, 30, 32])
 def test_knn_every_list_size(pcpx, oracle, k):
@@ -149,7 +183,18 @@ def test_exact_ties_take_the_exact_path(pcpx, oracle):
     with pcpx.Index(lattice) as ix:
         for k in (6, 7, 15, 26):
             assert same_knn(ix.knn(None, k), oc.knn(None, k))
-            assert ix.timings()["retry_queries"] > 0  # bit-equal distances were detected
+            # bit-equal distances were detected: handed on by the tile pass (to the exact 64-bit
+            # keys of the warp-per-query kernel) or answered by the block search's exact tie path
+            t = ix.timings()
+            assert t["deferred_queries"] + t["retry_queries"] > 0
+        for knob in ("tile", "warp_retry"):  # the block search and its per-thread retry kernels
+            pcpx.set_tuning(knob, 0)
+        try:
+            for k in (6, 15):
+                assert same_knn(ix.knn(None, k), oc.knn(None, k))
+                assert ix.timings()["retry_queries"] > 0
+        finally:
+            pcpx.set_tuning("tile", 1), pcpx.set_tuning("warp_retry", 1)
         assert np.array_equal(ix.radius_count(None, 0.25), oc.radius_count(None, 0.25))
         nrm = ix.estimate_normals(None, 7)
         onrm, gap = oc.normals(None, 7)
@@ -258,6 +303,45 @@ def test_device_resident_buffers(pcpx, oracle):
         # tangent-plane point = neighbourhood centroid (estimate_tangent_planes.hpp:82-94)
         cen = xyz[oi[:100]].astype(np.float64).mean(1)
         assert np.allclose(pts[:100], cen, atol=1e-5)
+
+
+def test_tangent_planes_reference_scenario(pcpx, oracle):
+    """test/algorithm/estimate_tangent_planes.cpp:9-76 restated: uniform cloud in [-10, 10]^3, the
+    octree over the voxel grid {(-10,-10,-10), (10,10,10)}, k = 5; EVERY plane's point must equal
+    the centre of geometry of the point's 5 nearest neighbours and its normal +- estimate_normal
+    of them, both within the reference's are_vectors_equal tolerance (1e-5 per component,
+    common/vector3d_queries.hpp:48-64) — the normal where the neighbourhood's eigengap makes it
+    well defined (five random points can be near-degenerate; the reference compares two runs of
+    the same Eigen code, here two different solvers are compared).  A larger, surface-like case
+    (k = 15, every row) follows."""
+    rng = np.random.default_rng(12)
+    xyz = rng.uniform(-10, 10, (1000, 3)).astype(np.float32)
+    box = (np.full(3, -10, np.float32), np.full(3, 10, np.float32))
+    oc = oracle.cloud(xyz, bbox=box)
+    with pcpx.Index(xyz, voxel_grid=box) as ix:
+        pts, nrm = ix.estimate_tangent_planes(None, 5)
+        oi, _, ocnt = oc.knn(None, 5)
+        assert np.all(ocnt == 5)
+        centre = xyz[oi].astype(np.float64).mean(1)
+        assert np.abs(pts - centre).max() <= 1e-5
+        onrm, gap = oc.normals(None, 5)
+        assert np.allclose(np.linalg.norm(nrm, axis=1), 1, atol=1e-5)
+        well = gap > 1e-2
+        diff = np.minimum(np.abs(nrm - onrm).max(1), np.abs(nrm + onrm).max(1))
+        assert well.mean() > 0.8 and diff[well].max() <= 1e-4
+        cos = np.abs((nrm * onrm).sum(1))
+        assert (1 - cos[gap > 1e-3]).max() <= 1e-4
+    surf = pcpx.synth.noisy_sphere(150_000, seed=3)
+    oc = oracle.cloud(surf)
+    with pcpx.Index(surf) as ix:
+        pts, nrm = ix.estimate_tangent_planes(None, 15)
+        oi, _, _ = oc.knn(None, 15)
+        centre = surf[oi].astype(np.float64).mean(1)
+        assert np.abs(pts - centre).max() <= 1e-5 * max(1.0, float(np.abs(surf).max()))
+        onrm, gap = oc.normals(None, 15)
+        cos = np.abs((nrm * onrm).sum(1))
+        assert (1 - cos[gap > 1e-3]).max() <= 1e-4
+        assert np.array_equal(nrm, ix.estimate_normals(None, 15))
 
 
 def test_outliers_and_density_filter(pcpx, oracle):
