@@ -292,9 +292,8 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
         ix.timings.kernel_launches = knn_shaped_launches(ix, k, true);
         idx.finish(ix.stream), d2.finish(ix.stream), cnt.finish(ix.stream);
         uint32_t h_retries = 0;
-        PCPX_CUDA(cudaMemcpyAsync(&h_retries, retries.get(), 4, cudaMemcpyDeviceToHost,
-                                  ix.stream));
         timer.done();
+        read_back(ix.stream, &h_retries, retries.get(), 4);
         if (sharded(ix, k))
             ix.timings.kernel_ms = parts.slowest();
         ix.timings.retry_queries = h_retries;
@@ -434,8 +433,8 @@ static void normals_impl(const pcpx_index* index, const float* queries, size_t n
     ix.timings.kernel_launches = knn_shaped_launches(ix, k, false);
     nrm.finish(ix.stream), ctr.finish(ix.stream);
     uint32_t h_ties = 0;
-    PCPX_CUDA(cudaMemcpyAsync(&h_ties, ties.get(), 4, cudaMemcpyDeviceToHost, ix.stream));
     timer.done();
+    read_back(ix.stream, &h_ties, ties.get(), 4);
     if (sharded(ix, k))
         ix.timings.kernel_ms = parts.slowest();
     ix.timings.retry_queries = h_ties;
@@ -543,9 +542,9 @@ int pcpx_mean_knn_distance(const pcpx_index* index, uint32_t k, double eps, floa
         means.finish(ix.stream);
         double h_sum = 0;
         uint32_t h_valid = 0;
-        PCPX_CUDA(cudaMemcpyAsync(&h_sum, sum.get(), 8, cudaMemcpyDeviceToHost, ix.stream));
-        PCPX_CUDA(cudaMemcpyAsync(&h_valid, valid.get(), 4, cudaMemcpyDeviceToHost, ix.stream));
         timer.done();
+        read_back(ix.stream, &h_sum, sum.get(), 8);
+        read_back(ix.stream, &h_valid, valid.get(), 4);
         if (out_mean)
             *out_mean = h_valid == n ? h_sum / (double)n : std::nan("");
     });

@@ -410,9 +410,7 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
         PCPX_CHECK_LAUNCH();
         ++launches;
         std::vector<BBoxPartial> h(nb);
-        PCPX_CUDA(cudaMemcpyAsync(h.data(), partials.get(), partials.bytes(),
-                                  cudaMemcpyDeviceToHost, ix.stream));
-        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        read_back(ix.stream, h.data(), partials.get(), partials.bytes());
         for (auto const& p : h)
         {
             for (int a = 0; a < 3; ++a)
@@ -500,9 +498,7 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
                                      kBlock, 0, ix.stream>>>(g, d_lh.get(), ix.bnd.get());
             PCPX_CHECK_LAUNCH();
             ++launches;
-            PCPX_CUDA(cudaMemcpyAsync(lh.data(), d_lh.get(), d_lh.bytes(), cudaMemcpyDeviceToHost,
-                                      ix.stream));
-            PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+            read_back(ix.stream, lh.data(), d_lh.get(), d_lh.bytes());
         }
         else
             PCPX_CUDA(cudaStreamSynchronize(ix.stream));
