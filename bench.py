@@ -14,7 +14,7 @@ sort -> cell tables) + the fused kNN -> PCA normal kernel over all of its points
           HBM), whole job over all ranks, bracketed by barrier + synchronize, max over ranks.
   e2e     the same step through the public C ABI with HOST buffers: pinned xyz in (H2D inside
           the timed region), host normals out (D2H inside).  Clouds are processed as a stream:
-          --e2e-threads host threads (default 2) each run whole blocking calls on their own
+          --e2e-threads host threads (default 3) each run whole blocking calls on their own
           index, so one cloud's copies overlap another's kernels; `e2e_serial` (extra key) is the
           same with one thread.
   roofline  the dominant kernel (the tile kNN -> normal kernel): algorithmic bytes (SURVEY.md §8d
@@ -338,6 +338,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # a host-side barrier (gloo): ranks waiting in it leave their GPU idle — an NCCL barrier is a
+    # kernel that spins on the device, which would compete with rank 0's replicas on those GPUs
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     def allmax(x):
         if world == 1:
             return float(x)
@@ -377,30 +386,65 @@ def run_ours(args):
             st["launches"].append(tb["kernel_launches"] + tq["kernel_launches"])
             st["retries"].append(tq["retry_queries"])
 
-    # end to end: pinned host buffers in and out, whole blocking calls, T host threads
+    # end to end: pinned host buffers in and out.  N = 1: whole blocking C-ABI calls with HOST
+    # pointers from T host threads (one cloud's copies overlap another's kernels).  N > 1: the
+    # halo exchange is a collective step every rank must issue in the same order, so one thread
+    # per rank pipelines the stream of clouds itself: the H2D of cloud i + 1 and the D2H of cloud
+    # i - 1 run on side streams while cloud i is exchanged, indexed and answered (C-ABI calls
+    # with device pointers); every cloud's 120 MB in and 120 MB out are inside the timed region.
     n_thr = max(1, args.e2e_threads)
-    h_out = [torch.empty((n_local + 65536, 3), dtype=torch.float32).pin_memory() for _ in range(n_thr)]
-    d_stage = None
-    if world > 1:  # N > 1: the owned slab goes up first, then the exchange, then the build
-        d_stage = [ShardedCloud(pcpx, torch, dist, xyz, rank * L, (rank + 1) * L, HALO, rank, world)]
+    n_buf = n_thr if world == 1 else 2
+    h_out = [torch.empty((n_local + 65536, 3), dtype=torch.float32).pin_memory() for _ in range(n_buf)]
+    d_stage = d_res = None
+    if world > 1:
+        d_stage = [ShardedCloud(pcpx, torch, dist, xyz, rank * L, (rank + 1) * L, HALO, rank, world)
+                   for _ in range(2)]
+        d_res = [torch.empty((n_local + 65536, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
 
     def e2e_once(t):
-        if world == 1:
-            ix = pcpx.Index(cloud.h_xyz.numpy(), device=local_rank)  # host pointer: H2D inside
-        else:
-            c = d_stage[t]
-            c.own.copy_(cloud.h_xyz, non_blocking=True)
-            d_xyz = c.local()
-            torch.cuda.synchronize()
-            ix = pcpx.Index(d_xyz, device=local_rank)
+        ix = pcpx.Index(cloud.h_xyz.numpy(), device=local_rank)  # host pointer: H2D inside
         ix.estimate_normals(None, K, out=h_out[t].numpy()[: ix.n])  # host pointer: D2H inside
         ix.close()
 
+    def e2e_pipelined(total_steps, overlap=True):
+        cur = torch.cuda.current_stream()
+
+        def upload(b):
+            with torch.cuda.stream(s_in):
+                d_stage[b].own.copy_(cloud.h_xyz, non_blocking=True)
+                ev_in[b].record(s_in)
+
+        upload(0)
+        for i in range(total_steps):
+            b = i & 1
+            if overlap and i + 1 < total_steps:
+                upload(1 - b)  # (the step that last used this buffer has returned: calls block)
+            ev_in[b].synchronize()
+            d_xyz = d_stage[b].local()  # strip cut + NCCL exchange on the current stream
+            cur.synchronize()
+            if i >= 2:
+                ev_out[b].synchronize()  # the copy that read d_res[b] two clouds ago is done
+            ix = pcpx.Index(d_xyz, device=local_rank)
+            ix.estimate_normals(None, K, out=d_res[b][: ix.n])
+            nloc = ix.n
+            ix.close()
+            with torch.cuda.stream(s_out):
+                h_out[b][:nloc].copy_(d_res[b][:nloc], non_blocking=True)
+                ev_out[b].record(s_out)
+            if not overlap:
+                ev_out[b].synchronize()
+                if i + 1 < total_steps:
+                    upload(1 - b)
+        torch.cuda.synchronize()
+
     def e2e_run(total_steps, threads):
-        """total_steps clouds through `threads` host threads; the collective exchange of N > 1
-        needs every rank to issue it in the same order, so there the threads take turns under
-        a lock for the exchange part only (one thread when world > 1 keeps it simple)."""
-        if threads == 1 or world > 1:
+        if world > 1:
+            e2e_pipelined(total_steps, overlap=threads > 1)
+            return
+        if threads == 1:
             for _ in range(total_steps):
                 e2e_once(0)
             return
@@ -428,12 +472,14 @@ def run_ours(args):
         del stats["build_ms"][: args.warmup], stats["sort_ms"][: args.warmup]
         del stats["kernel_ms"][: args.warmup], stats["retries"][: args.warmup]
         del stats["launches"][: args.warmup]
-        dt_e2e = _timed(lambda: e2e_run(args.steps, n_thr), 1, 1, barrier, world, dist, torch)
+        e2e_steps = max(args.steps, 3 * n_thr)  # (every host thread gets a few clouds)
+        dt_e2e = _timed(lambda: e2e_run(e2e_steps, n_thr if world == 1 else 2), 1, 1, barrier, world,
+                        dist, torch)
         dt_e2e_serial = _timed(lambda: e2e_run(max(2, args.steps // 2), 1), 1, 0, barrier, world,
                                dist, torch)
     total_owned = n_owned * world
     value = total_owned * args.steps / dt_res
-    e2e_value = total_owned * args.steps / dt_e2e
+    e2e_value = total_owned * e2e_steps / dt_e2e
     e2e_serial_value = total_owned * max(2, args.steps // 2) / dt_e2e_serial
 
     kernel_ms = allmax(float(np.mean(stats["kernel_ms"])))
@@ -602,7 +648,7 @@ def run_ours(args):
         # index of the seed-7 10 M-point plane is built on every device, the normals call is
         # sharded by tile range, rows land in device 0's buffer over NVLink.  Rank 0 drives it from
         # one process while the other ranks wait; timed by the host around the blocking calls.
-        barrier()
+        host_barrier()
         if rank == 0:
             full = torch.from_numpy(pcpx.synth.noisy_plane(N_POINTS)).cuda()
             out1 = torch.empty((N_POINTS, 3), dtype=torch.float32, device="cuda")
@@ -636,7 +682,7 @@ def run_ours(args):
                 "equal_to_one_device": bool(torch.equal(out1, outn)), "n_gpus": world}
             del full, out1, outn
             torch.cuda.empty_cache()
-        barrier()
+        host_barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -661,8 +707,12 @@ def run_ours(args):
             },
             "e2e": {"value": e2e_value, "unit": "normals/s",
                     "h2d_bytes_per_step": int(n_owned * 12), "d2h_bytes_per_step": int(n_local * 12),
-                    "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "host_threads": n_thr if world == 1 else 1},
+                    "ms_per_step": dt_e2e / e2e_steps * 1e3, "steps": e2e_steps,
+                    "host_threads": n_thr if world == 1 else 1,
+                    "mode": ("%d host threads, each whole blocking C-ABI calls with host pointers" % n_thr)
+                    if world == 1 else
+                    "one thread per rank; H2D of the next cloud and D2H of the previous one on side "
+                    "streams while the current one is exchanged, indexed and answered"},
             "e2e_serial": {"value": e2e_serial_value, "unit": "normals/s",
                            "ms_per_step": dt_e2e_serial / max(2, args.steps // 2) * 1e3},
             "gpu_launches": int(np.sum(stats["launches"])),
@@ -693,7 +743,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra legs (knn, radius, filter, sweep point, strong, scan100M)")
-    ap.add_argument("--e2e-threads", type=int, default=2,
+    ap.add_argument("--e2e-threads", type=int, default=3,
                     help="host threads streaming clouds through the C ABI in the e2e leg (N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -445,7 +445,7 @@ int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
  *   "tile"            1 (default): calls whose queries are the indexed points themselves take the
  *                     tile-cooperative kernel (shared-memory staged candidates); 0: never.
  *   "tile_sub"        staged layout of the tile kernel: 1 = whole cells (staged in one pass),
- *                     2 = 2 x 2 sub-bins per cell (default).
+ *                     2 = 2 x 2 sub-bins per cell, 0 (default) = chosen per call.
  *   "warp_retry"      1 (default): queries the first pass hands on are answered one warp per query
  *                     (octree descent, exact 64-bit keys); 0: per-thread retry kernels.
  *   "warp_all"        1: every kNN-shaped query takes the warp-per-query search (tests).

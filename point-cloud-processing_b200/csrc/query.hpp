@@ -28,7 +28,7 @@ struct Tuning
     int tile           = 1;    // 0: never
     int tile_first_cap = 0;    // batched form: candidates listed before the ball first shrinks (0: 2 (k + 1))
     int tile_min_queries = 24; // tiles with fewer points go to the per-thread path unstaged
-    int tile_sub       = 2;    // staged layout: 1 = whole cells (staged in one pass), 2 = 2 x 2 sub-bins per cell
+    int tile_sub       = 0;    // staged layout: 1 = whole cells (staged in one pass), 2 = 2 x 2 sub-bins per cell, 0 = by call
     float tile_cap     = 1.0f; // largest scan radius in units of the main-level cell
     int warp_retry     = 1;    // what the first pass hands on: 1 = one warp per query (warp_core.cuh), 0 = per-thread retry kernels
     int warp_all       = 0;    // (tests) every kNN-shaped query by the warp-per-query search

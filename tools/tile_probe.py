@@ -33,7 +33,7 @@ def main():
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 15
     cloud = sys.argv[3] if len(sys.argv) > 3 else "noisy_plane"
     variants = [dict(tile=0),
-                dict(tile=1, tile_sub=4, tile_cap=1.0),
+                dict(tile=1, tile_sub=0, tile_cap=1.0),
                 dict(tile=1, tile_sub=2, tile_cap=1.0),
                 dict(tile=1, tile_sub=1, tile_cap=1.0)]
     if os.environ.get("PCPX_PROBE_VARIANTS"):
