@@ -13,9 +13,9 @@
 //   * children that are leaves (finest level, or <= 32 points) are scanned together: their points
 //     are spread over the lanes by a prefix over the leaf sizes, 32 candidates per round;
 //   * the current k nearest live as ONE 64-bit (bits(d2), original index) key per lane, sorted
-//     across the warp; a round of 32 candidate keys is sorted by a 15-step shuffle bitonic
-//     network and merged in (min with the reversed batch + 5 merge steps) — rounds in which no
-//     candidate beats the k-th key are skipped after one vote;
+//     across the warp; candidates that beat the current k-th key are collected one per lane and
+//     merged in 32 at a time: sorted by a 15-step shuffle bitonic network, min with the reversed
+//     list, 5 merge steps;
 //   * the remaining children go on the stack farthest first, so the nearest is opened next, and
 //     every popped cell is pruned against the k-th distance found so far (a cell whose bound
 //     EQUALS it is still opened: a tie with a smaller index may hide there).
@@ -145,6 +145,12 @@ __device__ __forceinline__ void warp_descend(const GridView& g, WarpStack& st, f
                 incl += up;
         }
         uint32_t const excl = incl - cnt, total = __shfl_sync(kFullMask, incl, 31);
+        // Candidates that beat the current k-th key ("survivors") are collected, one per lane,
+        // and merged into the list 32 at a time: once the list is full only a few candidates of
+        // a round survive, and a merge per round would mostly sort empty keys.
+        uint64_t pkey = kEmptyEntry; // pending survivors: lanes [0, np)
+        uint32_t ppos = 0u, np = 0u;
+        uint64_t kk   = __shfl_sync(kFullMask, top.key, (int)k - 1);
         for (uint32_t base = 0; base < total; base += 32)
         {
             uint32_t const f = base + (uint32_t)lane;
@@ -166,29 +172,48 @@ __device__ __forceinline__ void warp_descend(const GridView& g, WarpStack& st, f
                 if (d2 < INFINITY)
                     bkey = ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)__float_as_uint(c.w);
             }
-            uint64_t const kk = __shfl_sync(kFullMask, top.key, (int)k - 1);
-            if (__any_sync(kFullMask, bkey < kk))
-                warp_merge32(top.key, top.pos, bkey, bpos, lane);
+            uint32_t const m = __ballot_sync(kFullMask, bkey < kk);
+            if (__popc(m) >= 12)
+            {
+                // many survivors (the list is still filling): the round goes in as it is
+                warp_merge32(top.key, top.pos, bkey < kk ? bkey : kEmptyEntry, bpos, lane);
+                kk = __shfl_sync(kFullMask, top.key, (int)k - 1);
+                continue;
+            }
+            for (uint32_t mm = m; mm != 0u; mm &= mm - 1u) // a few: appended one by one
+            {
+                int const j       = __ffs((int)mm) - 1;
+                uint64_t const vk = __shfl_sync(kFullMask, bkey, j);
+                uint32_t const vp = __shfl_sync(kFullMask, bpos, j);
+                if ((uint32_t)lane == np)
+                    pkey = vk, ppos = vp;
+                if (++np == 32u)
+                {
+                    warp_merge32(top.key, top.pos, pkey, ppos, lane);
+                    pkey = kEmptyEntry, np = 0u;
+                    kk   = __shfl_sync(kFullMask, top.key, (int)k - 1);
+                }
+            }
         }
+        if (np != 0u)
+            warp_merge32(top.key, top.pos, (uint32_t)lane < np ? pkey : kEmptyEntry, ppos, lane);
         tau = fminf(tau, top.kth_d2(k));
         // ---- the other children: on the stack, farthest first ----
-        inner                = inner && clb2 <= tau;
-        uint32_t const n_in  = (uint32_t)__popc(__ballot_sync(kFullMask, inner));
-        if (n_in != 0u)
+        inner              = inner && clb2 <= tau;
+        uint32_t const im  = __ballot_sync(kFullMask, inner);
+        if (im != 0u)
         {
-            // (bound bits + 1, lane) ascending; cells that are not pushed sort first
-            uint64_t sk   = inner ? (((uint64_t)__float_as_uint(clb2) + 1ull) << 32) | (uint64_t)lane
-                                  : (uint64_t)lane;
-            uint32_t none = 0u;
-            warp_sort32(sk, none, lane);
-            // descending: lane j takes rank 31 - j
-            uint64_t const dk = __shfl_sync(kFullMask, sk, 31 - lane);
-            int const from    = (int)(dk & 31u);
-            uint64_t const pk = __shfl_sync(kFullMask, ckey, from);
-            float const pl    = __shfl_sync(kFullMask, clb2, from);
-            if ((uint32_t)lane < n_in)
-                st.key[sp + lane] = pk, st.lb2[sp + lane] = pl;
-            sp += (int)n_in;
+            // rank among the cells that go on the stack, farthest first (ties: lower lane first)
+            uint32_t rank = 0u;
+            for (uint32_t mm = im; mm != 0u; mm &= mm - 1u)
+            {
+                int const j    = __ffs((int)mm) - 1;
+                float const lj = __shfl_sync(kFullMask, clb2, j);
+                rank += (lj > clb2 || (lj == clb2 && j < lane)) ? 1u : 0u;
+            }
+            if (inner)
+                st.key[sp + (int)rank] = ckey, st.lb2[sp + (int)rank] = clb2;
+            sp += __popc(im);
         }
         __syncwarp();
         // ---- next batch: the children of the (up to) four topmost cells still worth opening;
