@@ -12,6 +12,7 @@
 #include <mutex>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "pcpx.h"
 
@@ -351,28 +352,47 @@ static __global__ void mailbox_store_kernel(const uint32_t* __restrict__ src,
         dst[i] = src[i];
 }
 
+// Mailboxes are pinned allocations (cudaHostAlloc maps them into every context: milliseconds, and
+// serialised across devices), so they are pooled for the life of the process: a call borrows one
+// and gives it back — the replica threads of a multi-device call are short-lived, a
+// thread_local mailbox cost 24 ms per call on eight devices.
 class HostMailbox
 {
   public:
     static constexpr size_t kBytes = 64 * 1024;
-    static HostMailbox& mine()
+    HostMailbox()
     {
-        static thread_local HostMailbox m;
-        return m;
-    }
-    uint32_t* words()
-    {
+        {
+            std::lock_guard<std::mutex> lock(mutex());
+            if (!spare().empty())
+            {
+                p_ = spare().back();
+                spare().pop_back();
+            }
+        }
         if (!p_)
             PCPX_CUDA(cudaHostAlloc(&p_, kBytes, cudaHostAllocMapped | cudaHostAllocPortable));
-        return static_cast<uint32_t*>(p_);
     }
     ~HostMailbox()
     {
-        if (p_)
-            cudaFreeHost(p_); // (may fail at process teardown: ignored)
+        std::lock_guard<std::mutex> lock(mutex());
+        spare().push_back(p_);
     }
+    HostMailbox(const HostMailbox&)            = delete;
+    HostMailbox& operator=(const HostMailbox&) = delete;
+    uint32_t* words() { return static_cast<uint32_t*>(p_); }
 
   private:
+    static std::mutex& mutex()
+    {
+        static std::mutex m;
+        return m;
+    }
+    static std::vector<void*>& spare()
+    {
+        static std::vector<void*>* v = new std::vector<void*>(); // (never destroyed: no teardown order issues)
+        return *v;
+    }
     void* p_ = nullptr;
 };
 
@@ -390,7 +410,8 @@ inline void read_back(cudaStream_t s, void* dst, const void* src_dev, size_t byt
         PCPX_CUDA(cudaStreamSynchronize(s));
         return;
     }
-    uint32_t* box = HostMailbox::mine().words();
+    HostMailbox mailbox;
+    uint32_t* box = mailbox.words();
     mailbox_store_kernel<<<1, 256, 0, s>>>(static_cast<const uint32_t*>(src_dev), box,
                                            (uint32_t)(bytes / 4));
     PCPX_CHECK_LAUNCH();
