@@ -453,6 +453,12 @@ int pcpx_last_timings(const pcpx_index* index, pcpx_timings* out);
  *   "tile_margin"     like success_margin, for the tile kernel's level (default 1.15). */
 int pcpx_set_tuning(const char* name, double value);
 
+/* Page-locked host memory for buffers handed to the calls above.  Pageable host memory is staged
+ * by the driver through a bounce buffer (a 120 MB cloud: ~12 ms instead of 2.2 ms, and not
+ * asynchronous); include/pcpx/pcp.hpp stages its flattened clouds and results in these. */
+int pcpx_host_alloc(size_t bytes, void** out_ptr);
+void pcpx_host_free(void* ptr);
+
 /* Device memory the library keeps for reuse.  Temporaries and destroyed indices go back to a
  * per-device cache (cudaMalloc / cudaFree synchronise the device and cost up to milliseconds);
  * the cache is capped — one eighth of the device's memory by default (at least 1 GiB),

@@ -22,15 +22,19 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <execution>
 #include <iterator>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -378,7 +382,125 @@ inline std::vector<int>& device_list()
     static std::vector<int> devices; // empty: the current device
     return devices;
 }
+// Page-locked host buffer (pcpx_host_alloc): what the flattened clouds and the results of the
+// batched calls are staged in — pageable memory costs ~5x on both PCIe transfers.
+// (page-locking is expensive — ~0.5 ms per MB —, so released blocks are kept, a few of them, and
+// handed out again: a loop that builds a tree and estimates normals per cloud pins its staging
+// memory once)
+class pinned_pool
+{
+  public:
+    static pinned_pool& instance()
+    {
+        static pinned_pool* p = new pinned_pool(); // (never destroyed: outlives every buffer)
+        return *p;
+    }
+    void* acquire(std::size_t bytes, std::size_t& got)
+    {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            std::size_t best = blocks_.size();
+            for (std::size_t i = 0; i < blocks_.size(); ++i)
+                if (blocks_[i].second >= bytes && blocks_[i].second <= 2 * bytes + 4096 &&
+                    (best == blocks_.size() || blocks_[i].second < blocks_[best].second))
+                    best = i;
+            if (best != blocks_.size())
+            {
+                void* p = blocks_[best].first;
+                got     = blocks_[best].second;
+                blocks_.erase(blocks_.begin() + static_cast<std::ptrdiff_t>(best));
+                return p;
+            }
+        }
+        void* raw = nullptr;
+        check(pcpx_host_alloc(bytes, &raw), "pcpx_host_alloc");
+        got = bytes;
+        return raw;
+    }
+    void release(void* p, std::size_t bytes)
+    {
+        if (!p)
+            return;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            if (blocks_.size() < 6)
+            {
+                blocks_.emplace_back(p, bytes);
+                return;
+            }
+        }
+        pcpx_host_free(p);
+    }
+
+  private:
+    std::mutex m_;
+    std::vector<std::pair<void*, std::size_t>> blocks_;
+};
+
+template <class T>
+class pinned_buffer
+{
+  public:
+    pinned_buffer() = default;
+    explicit pinned_buffer(std::size_t n) { reset(n); }
+    ~pinned_buffer() { pinned_pool::instance().release(p_, bytes_); }
+    pinned_buffer(pinned_buffer const&)            = delete;
+    pinned_buffer& operator=(pinned_buffer const&) = delete;
+    void reset(std::size_t n)
+    {
+        pinned_pool::instance().release(p_, bytes_);
+        p_ = nullptr, n_ = 0, bytes_ = 0;
+        if (n == 0)
+            return;
+        p_ = static_cast<T*>(pinned_pool::instance().acquire(n * sizeof(T), bytes_));
+        n_ = n;
+    }
+    T* data() { return p_; }
+    T const* data() const { return p_; }
+    std::size_t size() const { return n_; }
+    T& operator[](std::size_t i) { return p_[i]; }
+    T const& operator[](std::size_t i) const { return p_[i]; }
+
+  private:
+    T* p_              = nullptr;
+    std::size_t n_     = 0;
+    std::size_t bytes_ = 0;
+};
+
+// f(first, last) over [0, n) cut into contiguous chunks, one host thread per chunk (the
+// element-wise loops either side of a device call — flattening 10 M points, handing 10 M normals
+// to the transform — cost more than the call itself when they run on one core)
+template <class F>
+void parallel_chunks(std::size_t n, F&& f)
+{
+    unsigned const hw      = std::thread::hardware_concurrency();
+    std::size_t const want = n / 65536u;
+    std::size_t const t    = std::min<std::size_t>({want, hw ? hw : 1u, 16u});
+    if (t <= 1)
+    {
+        f(std::size_t{0}, n);
+        return;
+    }
+    std::vector<std::thread> threads;
+    threads.reserve(t - 1);
+    std::size_t const step = (n + t - 1) / t;
+    for (std::size_t c = 1; c < t; ++c)
+        threads.emplace_back([&f, c, step, n] { f(std::min(n, c * step), std::min(n, (c + 1) * step)); });
+    f(std::size_t{0}, std::min(n, step));
+    for (auto& th : threads)
+        th.join();
+}
+template <class Iter>
+inline constexpr bool is_random_access_v =
+    std::is_base_of_v<std::random_access_iterator_tag,
+                      typename std::iterator_traits<Iter>::iterator_category>;
+
+inline index_ptr make_index(float const* xyz, std::size_t n, pcpx_index_params const& prm0);
 inline index_ptr make_index(std::vector<float> const& xyz, pcpx_index_params const& prm0)
+{
+    return make_index(xyz.data(), xyz.size() / 3, prm0);
+}
+inline index_ptr make_index(float const* xyz, std::size_t n, pcpx_index_params const& prm0)
 {
     pcpx_index_params prm = prm0;
     std::vector<int> const& devs = device_list();
@@ -389,7 +511,7 @@ inline index_ptr make_index(std::vector<float> const& xyz, pcpx_index_params con
             prm.devices[i] = devs[i];
     }
     pcpx_index* raw = nullptr;
-    check(pcpx_index_create(xyz.data(), xyz.size() / 3, 12, &prm, &raw), "pcpx_index_create");
+    check(pcpx_index_create(xyz, n, 12, &prm, &raw), "pcpx_index_create");
     return index_ptr(raw);
 }
 template <class PV>
@@ -429,6 +551,20 @@ class device_spatial_index
     std::size_t size() const { return n_indexed_; }
     bool empty() const { return size() == 0u; }
     pcpx_index const* handle() const { return index_.get(); }
+    // Are these n flattened query points the indexed cloud itself, in its original order?  Then a
+    // batched call passes queries == NULL and takes the tile kernel instead of sorting and
+    // searching them as foreign points (same rows: exclusion is by coordinates, not identity).
+    bool is_own_cloud(float const* xyz, std::size_t n) const
+    {
+        if (n == 0 || n != elements_.size() || xyz_.size() != 3 * n)
+            return false;
+        std::atomic<bool> same{true};
+        detail::parallel_chunks(n, [&](std::size_t first, std::size_t last) {
+            if (std::memcmp(xyz + 3 * first, xyz_.data() + 3 * first, 12 * (last - first)) != 0)
+                same.store(false, std::memory_order_relaxed);
+        });
+        return same.load();
+    }
     std::vector<Element> const& elements() const { return elements_; }
 
     knn_result_t knn_batch(std::vector<float> const& queries, std::size_t k, double eps) const
@@ -475,11 +611,13 @@ class device_spatial_index
     void build(ForwardIter begin, ForwardIter end, ToXyz&& to_xyz, pcpx_index_params const& prm)
     {
         elements_.assign(begin, end);
-        std::vector<float> xyz;
-        xyz.reserve(3 * elements_.size());
-        for (auto const& e : elements_)
-            to_xyz(xyz, e);
-        index_ = detail::make_index(xyz, prm);
+        std::size_t const n = elements_.size();
+        xyz_.reset(3 * n); // pinned: one DMA at PCIe speed; kept (is_own_cloud)
+        detail::parallel_chunks(n, [&](std::size_t first, std::size_t last) {
+            for (std::size_t i = first; i < last; ++i)
+                to_xyz(xyz_.data() + 3 * i, elements_[i]);
+        });
+        index_ = detail::make_index(xyz_.data(), n, prm);
         pcpx_index_info info{};
         detail::check(pcpx_index_info_get(index_.get(), &info), "pcpx_index_info_get");
         n_indexed_ = static_cast<std::size_t>(info.n_indexed);
@@ -488,6 +626,7 @@ class device_spatial_index
     }
 
     std::vector<Element> elements_;
+    detail::pinned_buffer<float> xyz_; // the elements' coordinates, original order
     detail::index_ptr index_;
     std::size_t n_indexed_ = 0;
     float bbox_[6]         = {0, 0, 0, 0, 0, 0};
@@ -666,8 +805,10 @@ class basic_linked_octree_t : public device_spatial_index<Element>
                    pcpx_index_params const& prm)
     {
         this->build(begin, end,
-                    [&](std::vector<float>& xyz, element_type const& e) {
-                        detail::push_xyz(xyz, point_view(e));
+                    [&](float* xyz, element_type const& e) {
+                        auto const p = point_view(e);
+                        xyz[0] = static_cast<float>(p.x()), xyz[1] = static_cast<float>(p.y());
+                        xyz[2] = static_cast<float>(p.z());
                     },
                     prm);
     }
@@ -695,11 +836,10 @@ class basic_linked_kdtree_t : public device_spatial_index<Element>
         pcpx_index_params prm{};
         prm.device = -1;
         this->build(begin, end,
-                    [&](std::vector<float>& xyz, element_type const& e) {
+                    [&](float* xyz, element_type const& e) {
                         auto const c = coordinate_map_(e);
-                        xyz.push_back(static_cast<float>(c[0]));
-                        xyz.push_back(static_cast<float>(c[1]));
-                        xyz.push_back(static_cast<float>(c[2]));
+                        xyz[0] = static_cast<float>(c[0]), xyz[1] = static_cast<float>(c[1]);
+                        xyz[2] = static_cast<float>(c[2]);
                     },
                     prm);
     }
@@ -844,15 +984,31 @@ void estimate_normals(ForwardIter1 begin, ForwardIter1 end, ForwardIter2 out_beg
 {
     using knn_type      = std::decay_t<KnnMap>;
     std::size_t const n = static_cast<std::size_t>(std::distance(begin, end));
-    std::vector<float> normals(3 * n);
+    detail::pinned_buffer<float> normals(3 * n);
     if constexpr (detail::is_gpu_knn_map<knn_type>::value)
     {
-        // the whole range in ONE fused kNN -> scatter matrix -> eigensolve kernel
-        std::vector<float> q;
-        q.reserve(3 * n);
-        for (auto it = begin; it != end; ++it)
-            detail::push_xyz(q, point_map(*it));
-        detail::check(pcpx_estimate_normals(knn_map.index->handle(), q.data(), n, 12,
+        // the whole range in ONE fused kNN -> scatter matrix -> eigensolve call
+        detail::pinned_buffer<float> q(3 * n);
+        auto const put = [&](std::size_t i, auto const& element) {
+            auto const p = point_map(element);
+            q[3 * i] = static_cast<float>(p.x()), q[3 * i + 1] = static_cast<float>(p.y());
+            q[3 * i + 2] = static_cast<float>(p.z());
+        };
+        if constexpr (detail::is_random_access_v<ForwardIter1>)
+            detail::parallel_chunks(n, [&](std::size_t first, std::size_t last) {
+                for (std::size_t i = first; i < last; ++i)
+                    put(i, begin[static_cast<std::ptrdiff_t>(i)]);
+            });
+        else
+        {
+            std::size_t i = 0;
+            for (auto it = begin; it != end; ++it, ++i)
+                put(i, *it);
+        }
+        // the range is the indexed cloud itself (the usual call): no query upload, no query
+        // sort, the tile kernel
+        bool const own = knn_map.index->is_own_cloud(q.data(), n);
+        detail::check(pcpx_estimate_normals(knn_map.index->handle(), own ? nullptr : q.data(), n, 12,
                                             static_cast<std::uint32_t>(knn_map.k), knn_map.eps,
                                             normals.data()),
                       "pcpx_estimate_normals");
@@ -874,9 +1030,19 @@ void estimate_normals(ForwardIter1 begin, ForwardIter1 end, ForwardIter2 out_beg
                                                        normals.data()),
                       "pcpx_normals_from_neighbourhoods");
     }
-    std::size_t i = 0;
-    for (auto it = begin; it != end; ++it, ++i, ++out_begin)
-        *out_begin = op(*it, Normal{normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]});
+    if constexpr (detail::is_random_access_v<ForwardIter1> && detail::is_random_access_v<ForwardIter2>)
+        detail::parallel_chunks(n, [&](std::size_t first, std::size_t last) {
+            for (std::size_t i = first; i < last; ++i)
+                out_begin[static_cast<std::ptrdiff_t>(i)] =
+                    op(begin[static_cast<std::ptrdiff_t>(i)],
+                       Normal{normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]});
+        });
+    else
+    {
+        std::size_t i = 0;
+        for (auto it = begin; it != end; ++it, ++i, ++out_begin)
+            *out_begin = op(*it, Normal{normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]});
+    }
 }
 
 // algorithm/estimate_normals.hpp:50-93 (execution policy accepted and ignored: the device call

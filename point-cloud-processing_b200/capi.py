@@ -107,6 +107,8 @@ _SIGNATURES = {
     "pcpx_last_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "pcpx_set_tuning": (C.c_int, [C.c_char_p, C.c_double]),
     "pcpx_trim": (C.c_int, [C.c_int]),
+    "pcpx_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "pcpx_host_free": (None, [C.c_void_p]),
     "pcpx_debug_knn_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]),
 }
 

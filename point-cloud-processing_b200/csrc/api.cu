@@ -15,7 +15,7 @@ using namespace pcpx;
 // kernel alone (rows) or followed by the inverse-order and row-reduction kernels (normals, means)
 static uint32_t knn_shaped_launches(const pcpx_index& ix, uint32_t k, bool rows_only)
 {
-    return k <= kMaxK ? ix.query_launches : (rows_only ? 1u : 3u);
+    return k <= kMaxK ? ix.query_launches.load() : (rows_only ? 1u : 3u);
 }
 
 // ---- several devices behind one handle (pcpx_index_params.devices) --------------------------
@@ -34,8 +34,8 @@ static void on_every_device(pcpx_index& ix, F&& fn)
             try
             {
                 pcpx_index& rep = *ix.replicas[r];
-                std::lock_guard<std::mutex> lock(rep.mtx);
                 ScopedDevice guard(rep.device);
+                CallStream call(rep);
                 fn(rep, (uint32_t)r + 1u);
             }
             catch (Error const& e)
@@ -77,10 +77,10 @@ struct PartTimer
     void run(pcpx_index& part_ix, uint32_t part, F&& launch)
     {
         Event a, b;
-        a.record(part_ix.stream);
+        a.record(part_ix.qstream());
         launch();
-        b.record(part_ix.stream);
-        PCPX_CUDA(cudaStreamSynchronize(part_ix.stream));
+        b.record(part_ix.qstream());
+        PCPX_CUDA(cudaStreamSynchronize(part_ix.qstream()));
         ms[part] = elapsed_ms(a, b);
     }
     float slowest() const { return *std::max_element(ms.begin(), ms.end()); }
@@ -260,8 +260,8 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
         }
         if (!out_idx)
             fail(PCPX_ERR_INVALID_ARG, "out_idx is NULL");
-        std::lock_guard<std::mutex> lock(ix.mtx);
         ScopedDevice guard(ix.device);
+        CallStream call(ix); // own stream: calls on one index may run concurrently
         CallTimer timer(ix);
         Batch batch;
         batch.prepare(ix, queries, nq, query_stride_bytes);
@@ -271,12 +271,12 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
         d2.prepare(out_d2, nq * (size_t)k);
         cnt.prepare(out_count, nq);
         DevBuf<uint32_t> retries(1);
-        PCPX_CUDA(cudaMemsetAsync(retries.get(), 0, 4, ix.stream));
+        PCPX_CUDA(cudaMemsetAsync(retries.get(), 0, 4, ix.qstream()));
         PartTimer parts(ix);
         timer.kernel_begin();
         if (sharded(ix, k))
         {
-            PCPX_CUDA(cudaStreamSynchronize(ix.stream)); // staged queries are in place
+            PCPX_CUDA(cudaStreamSynchronize(ix.qstream())); // staged queries are in place
             on_every_device(ix, [&](pcpx_index& dev_ix, uint32_t part) {
                 QueryBatch qb = batch.qb;
                 qb.part = part, qb.parts = (uint32_t)ix.replicas.size() + 1u;
@@ -290,10 +290,10 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
             launch_knn(ix, batch.qb, k, (float)eps, idx.d, d2.d, cnt.d, retries.get());
         timer.kernel_end();
         ix.timings.kernel_launches = knn_shaped_launches(ix, k, true);
-        idx.finish(ix.stream), d2.finish(ix.stream), cnt.finish(ix.stream);
+        idx.finish(ix.qstream()), d2.finish(ix.qstream()), cnt.finish(ix.qstream());
         uint32_t h_retries = 0;
         timer.done();
-        read_back(ix.stream, &h_retries, retries.get(), 4);
+        read_back(ix.qstream(), &h_retries, retries.get(), 4);
         if (sharded(ix, k))
             ix.timings.kernel_ms = parts.slowest();
         ix.timings.retry_queries = h_retries;
@@ -310,20 +310,20 @@ int pcpx_radius_count(const pcpx_index* index, const float* queries, size_t nq,
             return;
         if (!out_count)
             fail(PCPX_ERR_INVALID_ARG, "out_count is NULL");
-        std::lock_guard<std::mutex> lock(ix.mtx);
         ScopedDevice guard(ix.device);
+        CallStream call(ix); // own stream: calls on one index may run concurrently
         CallTimer timer(ix);
         Batch batch;
         batch.prepare(ix, queries, nq, query_stride_bytes);
         InBuf rad;
-        rad.stage(radii, nq, 4, 1, ix.stream);
+        rad.stage(radii, nq, 4, 1, ix.qstream());
         OutBuf<uint32_t> cnt;
         cnt.prepare(out_count, nq);
         timer.kernel_begin();
         launch_radius_count(ix, batch.qb, rad.d, radius, cnt.d);
         timer.kernel_end();
         ix.timings.kernel_launches = 1;
-        cnt.finish(ix.stream);
+        cnt.finish(ix.qstream());
         timer.done();
     });
 }
@@ -337,13 +337,13 @@ int pcpx_radius_search(const pcpx_index* index, const float* queries, size_t nq,
         if (!out_offsets || !out_idx)
             fail(PCPX_ERR_INVALID_ARG, "out_offsets / out_idx is NULL");
         *out_idx = nullptr;
-        std::lock_guard<std::mutex> lock(ix.mtx);
         ScopedDevice guard(ix.device);
+        CallStream call(ix); // own stream: calls on one index may run concurrently
         CallTimer timer(ix);
         Batch batch;
         batch.prepare(ix, queries, nq, query_stride_bytes);
         InBuf rad;
-        rad.stage(radii, nq, 4, 1, ix.stream);
+        rad.stage(radii, nq, 4, 1, ix.qstream());
         DevBuf<uint32_t> cnt(std::max<size_t>(nq, 1));
         OutBuf<uint64_t> off;
         off.prepare(out_offsets, nq + 1);
@@ -351,13 +351,13 @@ int pcpx_radius_search(const pcpx_index* index, const float* queries, size_t nq,
         launch_radius_count(ix, batch.qb, rad.d, radius, cnt.get());
         launch_exclusive_scan_u32(ix, cnt.get(), (uint32_t)nq, off.d);
         uint64_t total = 0;
-        PCPX_CUDA(cudaMemcpyAsync(&total, off.d + nq, 8, cudaMemcpyDeviceToHost, ix.stream));
-        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        PCPX_CUDA(cudaMemcpyAsync(&total, off.d + nq, 8, cudaMemcpyDeviceToHost, ix.qstream()));
+        PCPX_CUDA(cudaStreamSynchronize(ix.qstream()));
         DevBuf<uint32_t> lists(std::max<uint64_t>(total, 1));
         launch_radius_fill(ix, batch.qb, rad.d, radius, off.d, lists.get());
         timer.kernel_end();
         ix.timings.kernel_launches = 5;
-        off.finish(ix.stream);
+        off.finish(ix.qstream());
         if (out_idx_device)
         {
             timer.done();
@@ -370,9 +370,9 @@ int pcpx_radius_search(const pcpx_index* index, const float* queries, size_t nq,
                 fail(PCPX_ERR_OUT_OF_MEMORY, "host allocation of %llu indices failed",
                      (unsigned long long)total);
             cudaError_t e = cudaMemcpyAsync(host, lists.get(), total * 4, cudaMemcpyDeviceToHost,
-                                            ix.stream);
+                                            ix.qstream());
             if (e == cudaSuccess)
-                e = cudaStreamSynchronize(ix.stream);
+                e = cudaStreamSynchronize(ix.qstream());
             if (e != cudaSuccess)
             {
                 std::free(host);
@@ -403,8 +403,8 @@ static void normals_impl(const pcpx_index* index, const float* queries, size_t n
         return;
     if (!out_normals)
         fail(PCPX_ERR_INVALID_ARG, "out_normals is NULL");
-    std::lock_guard<std::mutex> lock(ix.mtx);
     ScopedDevice guard(ix.device);
+    CallStream call(ix); // own stream: calls on one index may run concurrently
     CallTimer timer(ix);
     Batch batch;
     batch.prepare(ix, queries, nq, query_stride_bytes);
@@ -412,12 +412,12 @@ static void normals_impl(const pcpx_index* index, const float* queries, size_t n
     nrm.prepare(out_normals, nq * 3);
     ctr.prepare(out_points, nq * 3);
     DevBuf<uint32_t> ties(1);
-    PCPX_CUDA(cudaMemsetAsync(ties.get(), 0, 4, ix.stream));
+    PCPX_CUDA(cudaMemsetAsync(ties.get(), 0, 4, ix.qstream()));
     PartTimer parts(ix);
     timer.kernel_begin();
     if (sharded(ix, k))
     {
-        PCPX_CUDA(cudaStreamSynchronize(ix.stream)); // staged queries are in place
+        PCPX_CUDA(cudaStreamSynchronize(ix.qstream())); // staged queries are in place
         on_every_device(ix, [&](pcpx_index& dev_ix, uint32_t part) {
             QueryBatch qb = batch.qb;
             qb.part = part, qb.parts = (uint32_t)ix.replicas.size() + 1u;
@@ -431,10 +431,10 @@ static void normals_impl(const pcpx_index* index, const float* queries, size_t n
         launch_normals(ix, batch.qb, k, (float)eps, ctr.d, nrm.d, ties.get());
     timer.kernel_end();
     ix.timings.kernel_launches = knn_shaped_launches(ix, k, false);
-    nrm.finish(ix.stream), ctr.finish(ix.stream);
+    nrm.finish(ix.qstream()), ctr.finish(ix.qstream());
     uint32_t h_ties = 0;
     timer.done();
-    read_back(ix.stream, &h_ties, ties.get(), 4);
+    read_back(ix.qstream(), &h_ties, ties.get(), 4);
     if (sharded(ix, k))
         ix.timings.kernel_ms = parts.slowest();
     ix.timings.retry_queries = h_ties;
@@ -512,8 +512,8 @@ int pcpx_mean_knn_distance(const pcpx_index* index, uint32_t k, double eps, floa
                 *out_mean = std::nan("");
             return;
         }
-        std::lock_guard<std::mutex> lock(ix.mtx);
         ScopedDevice guard(ix.device);
+        CallStream call(ix); // own stream: calls on one index may run concurrently
         CallTimer timer(ix);
         QueryBatch qb{nullptr, 3u, nullptr, (uint32_t)n};
         OutBuf<float> means;
@@ -539,12 +539,12 @@ int pcpx_mean_knn_distance(const pcpx_index* index, uint32_t k, double eps, floa
         launch_mean_reduce(ix, means.d, (uint32_t)n, sum.get(), valid.get());
         timer.kernel_end();
         ix.timings.kernel_launches = knn_shaped_launches(ix, k, false) + 2u; // + the two-stage reduction
-        means.finish(ix.stream);
+        means.finish(ix.qstream());
         double h_sum = 0;
         uint32_t h_valid = 0;
         timer.done();
-        read_back(ix.stream, &h_sum, sum.get(), 8);
-        read_back(ix.stream, &h_valid, valid.get(), 4);
+        read_back(ix.qstream(), &h_sum, sum.get(), 8);
+        read_back(ix.qstream(), &h_valid, valid.get(), 4);
         if (out_mean)
             *out_mean = h_valid == n ? h_sum / (double)n : std::nan("");
     });
@@ -560,8 +560,8 @@ int pcpx_density_filter(const pcpx_index* index, float radius, uint32_t threshol
             *out_n = 0;
         if (n == 0)
             return;
-        std::lock_guard<std::mutex> lock(ix.mtx);
         ScopedDevice guard(ix.device);
+        CallStream call(ix); // own stream: calls on one index may run concurrently
         CallTimer timer(ix);
         OutBuf<uint8_t> keep;
         DevBuf<uint8_t> keep_scratch;
@@ -583,10 +583,10 @@ int pcpx_density_filter(const pcpx_index* index, float radius, uint32_t threshol
         timer.kernel_end();
         ix.timings.kernel_launches = out_xyz ? 5 : 4;
         uint64_t kept = 0;
-        PCPX_CUDA(cudaMemcpyAsync(&kept, scan.get() + n, 8, cudaMemcpyDeviceToHost, ix.stream));
-        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
-        keep.finish(ix.stream);
-        pts.finish(ix.stream, kept * 3);
+        PCPX_CUDA(cudaMemcpyAsync(&kept, scan.get() + n, 8, cudaMemcpyDeviceToHost, ix.qstream()));
+        PCPX_CUDA(cudaStreamSynchronize(ix.qstream()));
+        keep.finish(ix.qstream());
+        pts.finish(ix.qstream(), kept * 3);
         timer.done();
         if (out_n)
             *out_n = (size_t)kept;
@@ -635,6 +635,26 @@ int pcpx_set_tuning(const char* name, double value)
     });
 }
 
+int pcpx_host_alloc(size_t bytes, void** out_ptr)
+{
+    return guarded([&] {
+        if (!out_ptr)
+            fail(PCPX_ERR_INVALID_ARG, "out_ptr is NULL");
+        *out_ptr = nullptr;
+        if (bytes == 0)
+            return;
+        if (pcpx_device_count() < 1)
+            fail(PCPX_ERR_NO_DEVICE, "no CUDA device: libpcpx has no CPU path");
+        PCPX_CUDA(cudaHostAlloc(out_ptr, bytes, cudaHostAllocPortable));
+    });
+}
+
+void pcpx_host_free(void* ptr)
+{
+    if (ptr)
+        cudaFreeHost(ptr);
+}
+
 int pcpx_trim(int device)
 {
     return guarded([&] {
@@ -654,13 +674,13 @@ int pcpx_debug_knn_stats(const pcpx_index* index, uint32_t k, double eps, uint64
         pcpx_index& ix = checked(index);
         if (!out4)
             fail(PCPX_ERR_INVALID_ARG, "out4 is NULL");
-        std::lock_guard<std::mutex> lock(ix.mtx);
         ScopedDevice guard(ix.device);
+        CallStream call(ix); // own stream: calls on one index may run concurrently
         DevBuf<unsigned long long> st(4);
-        PCPX_CUDA(cudaMemsetAsync(st.get(), 0, 32, ix.stream));
+        PCPX_CUDA(cudaMemsetAsync(st.get(), 0, 32, ix.qstream()));
         launch_knn_stats(ix, k, (float)eps, st.get());
-        PCPX_CUDA(cudaMemcpyAsync(out4, st.get(), 32, cudaMemcpyDeviceToHost, ix.stream));
-        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        PCPX_CUDA(cudaMemcpyAsync(out4, st.get(), 32, cudaMemcpyDeviceToHost, ix.qstream()));
+        PCPX_CUDA(cudaStreamSynchronize(ix.qstream()));
     });
 }
 

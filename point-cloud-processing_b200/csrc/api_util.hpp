@@ -82,14 +82,14 @@ struct CallTimer
         ix.timings.query_sort_ms   = 0.f;
         ix.timings.kernel_launches = 0;
         ix.timings.retry_queries   = 0;
-        t0.record(ix.stream);
+        t0.record(ix.qstream());
     }
-    void kernel_begin() { k0.record(ix.stream); }
-    void kernel_end() { k1.record(ix.stream); }
+    void kernel_begin() { k0.record(ix.qstream()); }
+    void kernel_end() { k1.record(ix.qstream()); }
     void done()
     {
-        t1.record(ix.stream);
-        PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+        t1.record(ix.qstream());
+        PCPX_CUDA(cudaStreamSynchronize(ix.qstream()));
         ix.timings.kernel_ms = elapsed_ms(k0, k1);
         ix.timings.total_ms  = elapsed_ms(t0, t1);
     }
@@ -119,16 +119,16 @@ struct Batch
             stride_bytes = 12;
         if (stride_bytes < 12 || stride_bytes % 4)
             fail(PCPX_ERR_INVALID_ARG, "query_stride_bytes must be a multiple of 4 and >= 12");
-        in.stage(queries, nq, stride_bytes, 3, ix.stream);
+        in.stage(queries, nq, stride_bytes, 3, ix.qstream());
         qb = QueryBatch{in.d, in.stride_f, nullptr, (uint32_t)nq};
         if (nq > 1)
         {
             Event s0, s1;
-            s0.record(ix.stream);
+            s0.record(ix.qstream());
             order.alloc(nq);
             sort_queries_by_cell(ix, in.d, in.stride_f, (uint32_t)nq, order.get());
-            s1.record(ix.stream);
-            PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+            s1.record(ix.qstream());
+            PCPX_CUDA(cudaStreamSynchronize(ix.qstream()));
             ix.timings.query_sort_ms = elapsed_ms(s0, s1);
             qb.order                 = order.get();
         }

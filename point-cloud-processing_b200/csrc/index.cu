@@ -572,15 +572,15 @@ void sort_queries_by_cell(const pcpx_index& ix, const float* d_queries, uint32_t
     sc.vals_alt.alloc(nq);
     uint64_t* keys     = reinterpret_cast<uint64_t*>(sc.keys.get());
     uint64_t* keys_alt = reinterpret_cast<uint64_t*>(sc.keys_alt.get());
-    encode_kernel<uint64_t><<<blocks_for(nq, kBlock), kBlock, 0, ix.stream>>>(
+    encode_kernel<uint64_t><<<blocks_for(nq, kBlock), kBlock, 0, ix.qstream()>>>(
         d_queries, stride_floats, nq, ix.grid, 0, 0, 0, 0, 0, 0, 0, keys, d_order);
     PCPX_CHECK_LAUNCH();
     bool const alt = sort_pairs<uint64_t>(keys, d_order, keys_alt, sc.vals_alt.get(), nq,
-                                          3 * ix.grid.lcap, ix.stream, &launches, sc);
+                                          3 * ix.grid.lcap, ix.qstream(), &launches, sc);
     if (alt)
         PCPX_CUDA(cudaMemcpyAsync(d_order, sc.vals_alt.get(), (size_t)nq * 4,
-                                  cudaMemcpyDeviceToDevice, ix.stream));
-    PCPX_CUDA(cudaStreamSynchronize(ix.stream));
+                                  cudaMemcpyDeviceToDevice, ix.qstream()));
+    PCPX_CUDA(cudaStreamSynchronize(ix.qstream()));
 }
 
 } // namespace pcpx

@@ -1,5 +1,8 @@
 // The GPU-resident index object behind the opaque pcpx_index handle.
 #pragma once
+#include <atomic>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -21,17 +24,32 @@ struct pcpx_index
     pcpx::DevBuf<pcpx::HashSlot> table; // all levels
     pcpx::DevBuf<uint8_t> bnd;          // n_indexed entries: coarsest level at which sorted point i opens a new cell
     pcpx_timings timings{-1.f, -1.f, -1.f, -1.f, -1.f, 0u, 0u, 0u, 0u};
-    std::mutex mtx; // one call at a time per index (calls serialise on `stream`)
-    // tile list of one level (query.cu: ensure_tile_list), built on first use and kept:
-    // tile_starts[i] = first sorted position of tile i, tile_starts[n_tiles] = n_indexed
-    mutable pcpx::DevBuf<uint32_t> tile_starts, tile_count, tile_scratch;
-    mutable pcpx::DevBuf<uint64_t> tile_xyz; // tile coordinates (tile_core.cuh: tile_pack)
-    mutable uint32_t query_launches = 0; // kernels launched by the last kNN-shaped call
-    mutable uint32_t deferred_queries = 0; // ... queries its tile pass handed to the per-thread path
-    mutable uint32_t expanded_queries = 0; // ... queries that needed the retry kernel (coarser levels)
-    mutable int tile_level         = -1;
-    mutable uint32_t tile_capacity = 0;
-    mutable uint32_t tile_region   = 0; // staged-region capacity that fits 97 % of the queries' tiles
+    // Concurrency.  The index is immutable once built, and the query entry points of the path
+    // (kNN, radius, normals, mean distance, density filter) may be called from several host
+    // threads at once: each call borrows its own stream (call_streams, below) and its own
+    // temporaries, the lazily built tile lists are immutable once made, and the statistics of
+    // "the last call" (`timings`, the counters below) are last-writer-wins: with calls in flight
+    // from several threads pcpx_last_timings may mix fields of different calls.  `mtx` still serialises the calls that keep state
+    // on the index's own stream (orientation, smoothing).
+    std::mutex mtx;
+    // tile list of one level (query.cu: ensure_tile_list), built on first use and kept for the
+    // life of the index: starts[i] = first sorted position of tile i, starts[n_tiles] = n_indexed
+    struct TileList
+    {
+        pcpx::DevBuf<uint32_t> starts, count, scratch;
+        pcpx::DevBuf<uint64_t> xyz; // tile coordinates (tile_core.cuh: tile_pack)
+        uint32_t capacity = 0;
+        uint32_t region   = 0; // staged-region capacity that fits 97 % of the queries' tiles
+    };
+    mutable std::mutex tile_mtx;
+    mutable std::map<int, std::unique_ptr<TileList>> tile_lists;
+    mutable std::atomic<uint32_t> query_launches{0};   // kernels launched by the last kNN-shaped call
+    mutable std::atomic<uint32_t> deferred_queries{0}; // ... queries its first pass handed on
+    mutable std::atomic<uint32_t> expanded_queries{0}; // ... of those, not final at the first block
+    // streams for concurrent calls: a call takes an idle one (or makes one) and gives it back
+    mutable std::mutex stream_mtx;
+    mutable std::vector<cudaStream_t> idle_streams;
+    cudaStream_t qstream() const; // the calling thread's stream for this index (index.hpp, below)
     // the same index on further devices (pcpx_index_params.devices[1..]); owned
     std::vector<pcpx_index*> replicas;
 
@@ -43,6 +61,8 @@ struct pcpx_index
             delete r;
         }
         cudaSetDevice(device);
+        for (cudaStream_t s : idle_streams)
+            cudaStreamDestroy(s);
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -50,6 +70,51 @@ struct pcpx_index
 };
 
 namespace pcpx {
+
+// The stream a query call runs on: while a CallStream is alive on this thread for this index its
+// borrowed stream, otherwise the index's own.
+struct CallStreamSlot
+{
+    const pcpx_index* ix = nullptr;
+    cudaStream_t s       = nullptr;
+};
+inline CallStreamSlot& call_stream_slot()
+{
+    static thread_local CallStreamSlot slot;
+    return slot;
+}
+class CallStream
+{
+  public:
+    explicit CallStream(const pcpx_index& ix) : ix_(ix), prev_(call_stream_slot())
+    {
+        cudaStream_t s = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(ix.stream_mtx);
+            if (!ix.idle_streams.empty())
+            {
+                s = ix.idle_streams.back();
+                ix.idle_streams.pop_back();
+            }
+        }
+        if (!s)
+            PCPX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        call_stream_slot() = CallStreamSlot{&ix, s};
+    }
+    ~CallStream()
+    {
+        cudaStream_t const s = call_stream_slot().s;
+        call_stream_slot()   = prev_;
+        std::lock_guard<std::mutex> lock(ix_.stream_mtx);
+        ix_.idle_streams.push_back(s);
+    }
+    CallStream(const CallStream&)            = delete;
+    CallStream& operator=(const CallStream&) = delete;
+
+  private:
+    const pcpx_index& ix_;
+    CallStreamSlot prev_;
+};
 
 // index.cu
 pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
@@ -61,3 +126,9 @@ void sort_queries_by_cell(const pcpx_index& ix, const float* d_queries, uint32_t
                           uint32_t nq, uint32_t* d_order);
 
 } // namespace pcpx
+
+inline cudaStream_t pcpx_index::qstream() const
+{
+    pcpx::CallStreamSlot const& slot = pcpx::call_stream_slot();
+    return slot.ix == this ? slot.s : stream;
+}

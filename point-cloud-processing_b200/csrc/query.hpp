@@ -58,8 +58,8 @@ void launch_mean_reduce(const pcpx_index& ix, const float* v, uint32_t n, double
                         uint32_t* out_valid);
 void launch_normals_from_neighbourhoods(cudaStream_t stream, const float* nbr_xyz,
                                         const uint64_t* offsets, uint32_t n, float* normals);
-// builds (once per level) the tile list the tile path iterates over; returns its capacity
-uint32_t ensure_tile_list(const pcpx_index& ix, int tile_level);
+// builds (once per level, kept for the life of the index) the tile list the tile path iterates over
+pcpx_index::TileList const& ensure_tile_list(const pcpx_index& ix, int tile_level);
 void launch_knn_stats(const pcpx_index& ix, uint32_t k, float eps, unsigned long long* stats4);
 
 } // namespace pcpx

@@ -507,3 +507,45 @@ def test_100m_scan_properties_and_brute_force_sample(pcpx):
         norms = torch.linalg.vector_norm(d_nrm, dim=1)
         assert bool(torch.isfinite(d_nrm).all()) and float((norms - 1).abs().max()) < 1e-5
         assert float(d_nrm[:, 2].abs().median()) > 0.9
+
+
+def test_concurrent_calls_on_one_index(pcpx, oracle):
+    """include/pcpx.h: the query entry points may be called from several host threads on ONE
+    index at once (each call borrows its own stream).  Eight threads run different
+    calls — self and external kNN at several k (different tile lists built lazily and
+    concurrently), normals, radius counts, the density filter, mean distances — three times over;
+    every result must equal the serial answer bit for bit."""
+    import threading
+
+    xyz = pcpx.synth.noise_mix(150_000, seed=21)
+    rng = np.random.default_rng(2)
+    q = (xyz[rng.choice(len(xyz), 30_000)] + rng.normal(0, 0.01, (30_000, 3))).astype(np.float32)
+    jobs = [lambda: ix.knn(None, 15), lambda: ix.knn(q, 15), lambda: ix.knn(None, 4),
+            lambda: ix.knn(q, 30), lambda: (ix.estimate_normals(None, 15),),
+            lambda: (ix.radius_count(None, 0.02),), lambda: ix.density_filter(0.02, 5)[:2],
+            lambda: (ix.mean_knn_distance(8)[0],)]
+    # serial answers on a fresh index, concurrent ones on another (its tile lists are built
+    # inside the race)
+    with pcpx.Index(xyz) as ix:
+        want = [job() for job in jobs]
+    with pcpx.Index(xyz) as ix:
+        got = [[None] * 3 for _ in jobs]
+        errs = []
+
+        def work(j):
+            try:
+                for rep in range(3):
+                    got[j][rep] = jobs[j]()
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(j,)) for j in range(len(jobs))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        for j in range(len(jobs)):
+            for rep in range(3):
+                for a, b in zip(got[j][rep], want[j]):
+                    assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), (j, rep)
+    oi, od2, _ = oracle.cloud(xyz).knn(q, 15)
+    assert np.array_equal(as_i64(want[1][0]), oi) and np.array_equal(want[1][1], od2)
