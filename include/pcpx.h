@@ -20,7 +20,10 @@
  *     common/points/point.hpp:85).
  *   - indices are ORIGINAL positions in the indexed range (what
  *     `view.point() - cloud.data()` is for a pcp::point_view_t element).
- *   - an index is immutable after creation and may be queried from several host threads.
+ *   - an index is immutable after creation and may be queried from several host threads AT ONCE:
+ *     every kNN / radius / normals / mean-distance / density-filter call borrows its own CUDA
+ *     stream and temporaries, so calls from different threads overlap on the device (the reference's
+ *     const member functions are re-entrant the same way); pcpx_last_timings is last-writer-wins.
  */
 #ifndef PCPX_H
 #define PCPX_H

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -396,6 +397,24 @@ class HostMailbox
     void* p_ = nullptr;
 };
 
+// Device-resident index arrays handed in by a caller (neighbour rows, start sets) are checked on
+// the device before any kernel dereferences them: *bad counts the entries that are neither `pad`
+// nor < limit.
+static __global__ void count_bad_indices_kernel(const uint32_t* __restrict__ idx, size_t count,
+                                                uint32_t limit, uint32_t pad,
+                                                uint32_t* __restrict__ bad)
+{
+    uint32_t mine = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count;
+         i += (size_t)gridDim.x * blockDim.x)
+    {
+        uint32_t const v = idx[i];
+        mine += (v != pad && v >= limit) ? 1u : 0u;
+    }
+    if (mine)
+        atomicAdd(bad, mine);
+}
+
 // dst (host) <- src (device), `bytes` a multiple of 4; returns with the stream synchronised
 inline void read_back(cudaStream_t s, void* dst, const void* src_dev, size_t bytes)
 {
@@ -417,6 +436,24 @@ inline void read_back(cudaStream_t s, void* dst, const void* src_dev, size_t byt
     PCPX_CHECK_LAUNCH();
     PCPX_CUDA(cudaStreamSynchronize(s));
     std::memcpy(dst, box, bytes);
+}
+#endif
+
+#ifdef __CUDACC__
+// number of entries of the device array idx[0, count) that are neither `pad` nor < limit
+inline uint32_t count_bad_indices(cudaStream_t s, const uint32_t* d_idx, size_t count, uint32_t limit,
+                                  uint32_t pad)
+{
+    if (count == 0)
+        return 0u;
+    DevBuf<uint32_t> bad(1);
+    PCPX_CUDA(cudaMemsetAsync(bad.get(), 0, 4, s));
+    unsigned const blocks = (unsigned)std::min<size_t>((count + 255) / 256, 148u * 8u);
+    count_bad_indices_kernel<<<blocks, 256, 0, s>>>(d_idx, count, limit, pad, bad.get());
+    PCPX_CHECK_LAUNCH();
+    uint32_t h = 0;
+    read_back(s, &h, bad.get(), 4);
+    return h;
 }
 #endif
 

@@ -616,6 +616,14 @@ int pcpx_orient_normals_graph(const float* xyz, size_t n, size_t stride_bytes,
                                       cudaMemcpyHostToDevice, s));
             d_nbr = nbr_staged.get();
         }
+        else if (k)
+        {
+            // device-resident rows: checked on the device before the search dereferences them
+            uint32_t const bad = count_bad_indices(s, neighbours, n * (size_t)k, (uint32_t)n, kPad);
+            if (bad)
+                fail(PCPX_ERR_INVALID_ARG, "%u entries of neighbours are not vertices (< n) nor "
+                     "PCPX_NO_NEIGHBOUR", bad);
+        }
         bool const direct = is_device_pointer(normals);
         DevBuf<float> staged;
         float* d_nrm = normals;

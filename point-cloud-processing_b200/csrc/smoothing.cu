@@ -315,6 +315,13 @@ int pcpx_wlop(const float* xyz, size_t n, size_t stride_bytes, const uint32_t* i
                              (unsigned long long)i, initial_idx[i]);
             PCPX_CUDA(cudaMemcpyAsync(d_init.get(), initial_idx, n_out * 4, kind, clk.s));
             PCPX_CUDA(cudaStreamSynchronize(clk.s));
+            if (kind == cudaMemcpyDeviceToDevice)
+            {
+                uint32_t const bad =
+                    count_bad_indices(clk.s, d_init.get(), n_out, (uint32_t)n, 0u /* 0 is a point */);
+                if (bad)
+                    fail(PCPX_ERR_INVALID_ARG, "%u entries of initial_idx are not point indices", bad);
+            }
         }
         else
         {

@@ -94,3 +94,30 @@ def test_explicit_graph_entry_point(pcpx, oracle, fix):
         bad[3, 2] = len(xyz)
         pcpx.orient_normals_graph(xyz, bad, nrm.copy())
 
+
+
+def test_device_resident_indices_are_validated(pcpx):
+    """Index arrays handed in as DEVICE memory are range-checked on the device before any kernel
+    dereferences them (host arrays always were): an entry >= n returns PCPX_ERR_INVALID_ARG
+    instead of reading and writing out of bounds."""
+    import torch
+
+    rng = np.random.default_rng(0)
+    n, k = 5_000, 6
+    xyz = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    nbr = rng.integers(0, n, (n, k)).astype(np.uint32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (n, 1))
+    d_nbr = torch.from_numpy(nbr.astype(np.int64)).to(torch.int32).cuda()  # same bits as uint32
+    pcpx.orient_normals_graph(xyz, d_nbr, nrm.copy())  # valid rows pass
+    bad = nbr.copy()
+    bad[123, 2] = n + 7
+    d_bad = torch.from_numpy(bad.astype(np.int64)).to(torch.int32).cuda()
+    with pytest.raises(pcpx.PcpxError) as e:
+        pcpx.orient_normals_graph(xyz, d_bad, nrm.copy())
+    assert e.value.code == -1
+    init = torch.arange(0, 200, dtype=torch.int32, device="cuda")
+    pcpx.wlop(xyz, 200, 0.2, iterations=1, initial=init)
+    init[5] = n
+    with pytest.raises(pcpx.PcpxError) as e:
+        pcpx.wlop(xyz, 200, 0.2, iterations=1, initial=init)
+    assert e.value.code == -1
