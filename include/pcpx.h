@@ -175,11 +175,15 @@ int pcpx_radius_count(
     uint32_t* out_count);
 
 /*
- * Sphere range search, CSR lists.  out_offsets has nq + 1 entries.  *out_idx is allocated by
- * the library in HOST memory (free with pcpx_free) unless out_idx_device != 0, in which case
- * it is device memory of the index's GPU.  Within a query the order is the index's traversal
- * order (deterministic, unspecified — as in the reference, whose order is the tree's DFS).
+ * Sphere range search, CSR lists.  out_offsets has nq + 1 entries.  `out_idx_device` is a set
+ * of flags: PCPX_RADIUS_DEVICE (1) leaves *out_idx in device memory of the index's GPU instead
+ * of HOST memory (free with pcpx_free either way); PCPX_RADIUS_SORTED (2) sorts every query's
+ * list ascending by original index.  Without it the order within a query is the index's
+ * traversal order (deterministic, unspecified — as in the reference, whose order is the tree's
+ * DFS).
  */
+#define PCPX_RADIUS_DEVICE 1
+#define PCPX_RADIUS_SORTED 2
 int pcpx_radius_search(
     const pcpx_index* index,
     const float* queries,

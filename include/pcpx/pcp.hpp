@@ -599,8 +599,9 @@ class device_spatial_index
         std::size_t const n = centres.size() / 3;
         offsets.assign(n + 1, 0u);
         std::uint32_t* lists = nullptr;
+        // (lists ascending by original index: a defined order costs one small kernel)
         detail::check(pcpx_radius_search(index_.get(), centres.data(), n, 12, radii.data(), 0.f,
-                                         offsets.data(), &lists, 0),
+                                         offsets.data(), &lists, PCPX_RADIUS_SORTED),
                       "pcpx_radius_search");
         idx.assign(lists, lists + offsets[n]);
         pcpx_free(lists, 0);

@@ -378,15 +378,16 @@ class Index:
         _check(lib().pcpx_radius_count(self._h, q.ptr, nq, 12, r.ptr, float(radius), bc.ptr))
         return out_count
 
-    def radius_search(self, queries, radius, radii=None):
-        """CSR (offsets[nq + 1], indices) — host arrays."""
+    def radius_search(self, queries, radius, radii=None, sorted=False):
+        """CSR (offsets[nq + 1], indices) — host arrays; sorted: every list ascending by index
+        (PCPX_RADIUS_SORTED), otherwise traversal order."""
         nq = self._nq(queries)
         q = _Buf(queries, np.float32)
         r = _Buf(radii, np.float32)
         off = np.zeros(nq + 1, np.uint64)
         p = C.c_void_p()
         _check(lib().pcpx_radius_search(self._h, q.ptr, nq, 12, r.ptr, float(radius),
-                                        off.ctypes.data, C.byref(p), 0))
+                                        off.ctypes.data, C.byref(p), 2 if sorted else 0))
         total = int(off[-1])
         try:
             idx = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)),

@@ -355,10 +355,12 @@ int pcpx_radius_search(const pcpx_index* index, const float* queries, size_t nq,
         PCPX_CUDA(cudaStreamSynchronize(ix.qstream()));
         DevBuf<uint32_t> lists(std::max<uint64_t>(total, 1));
         launch_radius_fill(ix, batch.qb, rad.d, radius, off.d, lists.get());
+        if (out_idx_device & PCPX_RADIUS_SORTED)
+            launch_sort_lists(ix, off.d, (uint32_t)nq, lists.get());
         timer.kernel_end();
-        ix.timings.kernel_launches = 5;
+        ix.timings.kernel_launches = (out_idx_device & PCPX_RADIUS_SORTED) ? 6 : 5;
         off.finish(ix.qstream());
-        if (out_idx_device)
+        if (out_idx_device & PCPX_RADIUS_DEVICE)
         {
             timer.done();
             *out_idx = lists.detach();

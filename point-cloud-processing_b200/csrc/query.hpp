@@ -48,6 +48,8 @@ void launch_radius_count(const pcpx_index& ix, const QueryBatch& qb, const float
                          uint32_t* count);
 void launch_radius_fill(const pcpx_index& ix, const QueryBatch& qb, const float* radii, float r,
                         const uint64_t* offsets, uint32_t* idx);
+// every list of a CSR (offsets: nq + 1 device values) ascending by value, in place
+void launch_sort_lists(const pcpx_index& ix, const uint64_t* offsets, uint32_t nq, uint32_t* idx);
 void launch_density_keep(const pcpx_index& ix, float r, uint32_t threshold, uint8_t* keep);
 // exclusive scan of `in` (n values) into `out` (n + 1 values, out[n] = total); 64-bit sums
 void launch_exclusive_scan_u32(const pcpx_index& ix, const uint32_t* in, uint32_t n, uint64_t* out);

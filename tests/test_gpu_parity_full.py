@@ -89,6 +89,10 @@ def test_reference_fixtures(pcpx, fix, name):
         seg = np.repeat(np.arange(len(xyz)), np.diff(off.astype(np.int64)))
         order = np.lexsort((idx, seg))
         assert np.array_equal(idx[order].astype(np.int32), fix[name + "_radius_0.02_idx"])
+        # PCPX_RADIUS_SORTED: the same lists, each ascending by index, straight from the device
+        off2, idx2 = ix.radius_search(None, float(fix[name + "_radius_0.02_r"]), sorted=True)
+        assert np.array_equal(off2, off)
+        assert np.array_equal(idx2.astype(np.int32), fix[name + "_radius_0.02_idx"])
         per, mean = ix.mean_knn_distance(15)
         assert np.array_equal(per, fix[name + "_mean15"], equal_nan=True)
 
