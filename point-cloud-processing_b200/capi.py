@@ -294,6 +294,8 @@ class Index:
         prm = IndexParams()
         prm.device = device
         if devices:
+            if len(devices) > 8:
+                raise PcpxError(-1, "at most 8 devices behind one handle")
             prm.n_devices = len(devices)
             for i, d in enumerate(devices):
                 prm.devices[i] = int(d)

@@ -86,11 +86,13 @@ struct PartTimer
     float slowest() const { return *std::max_element(ms.begin(), ms.end()); }
 };
 
-static void build_replicas(pcpx_index& ix, const float* xyz, size_t n, size_t stride_bytes,
-                           const pcpx_index_params& prm)
+static void validate_devices(const pcpx_index_params& prm)
 {
+    if (prm.n_devices == 0)
+        return;
     int ndev = 0;
-    PCPX_CUDA(cudaGetDeviceCount(&ndev));
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        fail(PCPX_ERR_NO_DEVICE, "no CUDA device: libpcpx has no CPU path");
     if (prm.n_devices > 8)
         fail(PCPX_ERR_INVALID_ARG, "n_devices = %u (at most 8)", prm.n_devices);
     for (uint32_t i = 0; i < prm.n_devices; ++i)
@@ -100,11 +102,16 @@ static void build_replicas(pcpx_index& ix, const float* xyz, size_t n, size_t st
                  prm.devices[i], ndev);
         // (PCPX_TEST_SAME_DEVICE_REPLICAS=1: a device may be listed more than once, so that a
         // one-GPU box can exercise the sharded code path — tests only, it buys no speed)
-        static bool const allow_dup = std::getenv("PCPX_TEST_SAME_DEVICE_REPLICAS") != nullptr;
+        bool const allow_dup = std::getenv("PCPX_TEST_SAME_DEVICE_REPLICAS") != nullptr;
         for (uint32_t j = 0; j < i && !allow_dup; ++j)
             if (prm.devices[j] == prm.devices[i])
                 fail(PCPX_ERR_INVALID_ARG, "device %d listed twice", prm.devices[i]);
     }
+}
+
+static void build_replicas(pcpx_index& ix, const float* xyz, size_t n, size_t stride_bytes,
+                           const pcpx_index_params& prm)
+{
     // every replica writes its rows into the primary's buffers (and reads its staged queries)
     for (uint32_t i = 1; i < prm.n_devices; ++i)
     {
@@ -191,6 +198,7 @@ int pcpx_index_create(const float* xyz, size_t n, size_t stride_bytes,
         pcpx_index_params prm{};
         if (params)
             prm = *params;
+        validate_devices(prm);
         if (prm.n_devices >= 1)
             prm.device = prm.devices[0];
         std::unique_ptr<pcpx_index> ix(build_index(xyz, n, stride_bytes, &prm));

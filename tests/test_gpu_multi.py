@@ -131,3 +131,41 @@ def test_replicated_index_equals_one_gpu(pcpx):
         with pcpx.Index(d_xyz, devices=devices) as many, pcpx.Index(xyz) as one:
             assert np.array_equal(many.estimate_normals(None, 15), one.estimate_normals(None, 15),
                                   equal_nan=True)
+
+
+def test_sharded_calls_edge_cases(pcpx, oracle):
+    """Multi-device handles at the edges: an empty cloud, clouds and query sets smaller than the
+    number of shares, k beyond the sharded kernels, a one-entry device list, bad device lists."""
+    os.environ["PCPX_TEST_SAME_DEVICE_REPLICAS"] = "1"
+    rng = np.random.default_rng(1)
+    with pcpx.Index(np.zeros((0, 3), np.float32), devices=[0, 0]) as ix:
+        assert ix.info()["n_indexed"] == 0 and ix.info()["n_devices"] == 2
+        idx, d2, cnt = ix.knn(rng.uniform(0, 1, (5, 3)).astype(np.float32), 3)
+        assert np.all(cnt == 0) and np.all(idx == 0xFFFFFFFF)
+    tiny = rng.uniform(0, 1, (5, 3)).astype(np.float32)
+    q1 = rng.uniform(0, 1, (1, 3)).astype(np.float32)
+    with pcpx.Index(tiny, devices=[0, 0, 0, 0]) as many, pcpx.Index(tiny) as one:
+        for qq in (None, q1, tiny[:2] + np.float32(0.01)):
+            for k in (1, 3, 8, 40):
+                a, b = one.knn(qq, k), many.knn(qq, k)
+                assert all(np.array_equal(x, y) for x, y in zip(a, b)), k
+        assert np.array_equal(one.estimate_normals(None, 4), many.estimate_normals(None, 4), equal_nan=True)
+        pa, ma = one.mean_knn_distance(3)
+        pb, mb = many.mean_knn_distance(3)
+        assert np.array_equal(pa, pb, equal_nan=True) and ma == mb
+    mid = rng.uniform(0, 1, (3000, 3)).astype(np.float32)  # below the tile path's minimum size
+    oc = oracle.cloud(mid)
+    with pcpx.Index(mid, devices=[0]) as single, pcpx.Index(mid, devices=[0, 0, 0]) as many:
+        assert single.info()["n_devices"] == 1
+        oi, od2, ocnt = oc.knn(None, 15)
+        for ix in (single, many):
+            idx, d2, cnt = ix.knn(None, 15)
+            assert np.array_equal(idx.astype(np.int64), oi) and np.array_equal(d2, od2)
+    for bad in ([0, 99], [-2], list(range(9))):
+        with pytest.raises(pcpx.PcpxError) as e:
+            pcpx.Index(mid, devices=bad)
+        assert e.value.code == -1
+    del os.environ["PCPX_TEST_SAME_DEVICE_REPLICAS"]
+    with pytest.raises(pcpx.PcpxError) as e:  # the same device twice is an error outside tests
+        pcpx.Index(mid, devices=[0, 0])
+    assert e.value.code in (-1,)
