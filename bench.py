@@ -646,7 +646,7 @@ def run_ours(args):
     if not args.no_extras and world > 1:
         # replicated: ONE handle of the C ABI over all N devices (pcpx_index_params.devices): the
         # index of the seed-7 10 M-point plane is built on every device, the normals call is
-        # sharded by tile range, rows land in device 0's buffer over NVLink.  Rank 0 drives it from
+        # sharded by tile range, device 0 gathers the replicas' answers over NVLink.  Rank 0 drives it from
         # one process while the other ranks wait; timed by the host around the blocking calls.
         host_barrier()
         if rank == 0:
@@ -675,7 +675,8 @@ def run_ours(args):
             extras["replicated"] = {
                 "workload": "estimate_normals k=15 over the ONE 10M-point noisy plane through one C-ABI "
                             "handle replicated on %d devices (index resident, call sharded by tile "
-                            "range, rows written to device 0 over NVLink); host-timed blocking call" % world,
+                            "range, replicas answer into local buffers that device 0 gathers over NVLink); host-timed "
+                            "blocking call" % world,
                 "units_per_s": N_POINTS / (w * 1e-3), "unit": "normals/s", "call_ms": w,
                 "kernel_ms_slowest_device": float(np.median(kern[leg_warm:])),
                 "build_wall_ms": build_wall, "first_build_wall_ms": first_build,

@@ -74,9 +74,9 @@ typedef struct pcpx_index_params
      * `device`; the cloud reaches the others by peer copy when xyz is device memory) and every
      * kNN-shaped call with k <= 32 — pcpx_knn, pcpx_estimate_normals, pcpx_estimate_tangent_planes,
      * pcpx_mean_knn_distance — is answered by all of them at once: device i takes the i-th
-     * contiguous share of the tile list (queries == NULL) or of the Morton-sorted queries and
-     * writes its rows straight into the primary's output buffer over NVLink (peer access is
-     * required: PCPX_ERR_UNSUPPORTED without it).  Results are bit-identical to a one-device
+     * contiguous share of the tile list (queries == NULL) or of the Morton-sorted queries; the
+     * primary reads the replicas' answers over NVLink and scatters them to the caller's rows
+     * (peer access is required in both directions: PCPX_ERR_UNSUPPORTED without it).  Results are bit-identical to a one-device
      * index.  Every other call runs on the primary alone.  0 or 1: one device.
      * (Clouds too large for one GPU are cut into slabs with halo strips one level up:
      * point-cloud-processing_b200/sharding.py over torch.distributed, pcpx_extract_bands.) */

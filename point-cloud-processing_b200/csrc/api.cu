@@ -86,6 +86,44 @@ struct PartTimer
     float slowest() const { return *std::max_element(ms.begin(), ms.end()); }
 };
 
+// One output array of a sharded call.  The primary writes its rows in place; a replica fills a
+// local buffer indexed by SORTED query position (QueryBatch::by_position) which the primary then
+// reads in order over NVLink and scatters to the rows (launch_gather_rows) — rows written one by
+// one across NVLink cost several times the kernel (4 devices: 2.2 ms per call against 0.6 ms
+// of kernel).
+template <typename T>
+struct ShardedOut
+{
+    T* primary = nullptr;
+    size_t rows = 0;
+    uint32_t width = 0;
+    std::vector<DevBuf<T>> local; // one per replica, on the replica's device
+
+    ShardedOut(T* dst, size_t n_rows, uint32_t w, size_t n_replicas)
+        : primary(dst), rows(n_rows), width(w), local(n_replicas)
+    {
+    }
+    // the pointer the kernels of `part` write through (called on the part's own thread/device)
+    T* target(uint32_t part)
+    {
+        if (!primary)
+            return nullptr;
+        if (part == 0)
+            return primary;
+        local[part - 1].alloc(std::max<size_t>(rows * width, 1));
+        return local[part - 1].get();
+    }
+    void gather(const pcpx_index& ix, const QueryBatch& qb, const std::vector<ShardInfo>& shards)
+    {
+        if (!primary)
+            return;
+        for (size_t r = 0; r < local.size(); ++r)
+            launch_gather_rows(ix, qb, shards[r + 1],
+                               reinterpret_cast<const uint32_t*>(local[r].get()),
+                               reinterpret_cast<uint32_t*>(primary), width);
+    }
+};
+
 static void validate_devices(const pcpx_index_params& prm)
 {
     if (prm.n_devices == 0)
@@ -122,12 +160,21 @@ static void build_replicas(pcpx_index& ix, const float* xyz, size_t n, size_t st
         if (!can)
             fail(PCPX_ERR_UNSUPPORTED, "device %d cannot access device %d's memory (no peer access)",
                  prm.devices[i], ix.device);
-        ScopedDevice guard(prm.devices[i]);
-        cudaError_t const e = cudaDeviceEnablePeerAccess(ix.device, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-            fail(PCPX_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", prm.devices[i], ix.device,
-                 cudaGetErrorString(e));
-        cudaGetLastError();
+        // both ways: a replica reads the primary's staged queries, the primary reads the
+        // replica's answers
+        for (int dir = 0; dir < 2; ++dir)
+        {
+            int const from = dir ? ix.device : prm.devices[i], to = dir ? prm.devices[i] : ix.device;
+            PCPX_CUDA(cudaDeviceCanAccessPeer(&can, from, to));
+            if (!can)
+                fail(PCPX_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", from, to);
+            ScopedDevice guard(from);
+            cudaError_t const e = cudaDeviceEnablePeerAccess(to, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                fail(PCPX_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", from, to,
+                     cudaGetErrorString(e));
+            cudaGetLastError();
+        }
     }
     size_t const nrep = prm.n_devices - 1;
     ix.replicas.assign(nrep, nullptr);
@@ -285,14 +332,25 @@ int pcpx_knn(const pcpx_index* index, const float* queries, size_t nq, size_t qu
         if (sharded(ix, k))
         {
             PCPX_CUDA(cudaStreamSynchronize(ix.qstream())); // staged queries are in place
+            size_t const nrep = ix.replicas.size();
+            std::vector<ShardInfo> shards(nrep + 1);
+            ShardedOut<uint32_t> s_idx(idx.d, nq, k, nrep), s_cnt(cnt.d, nq, 1, nrep);
+            ShardedOut<float> s_d2(d2.d, nq, k, nrep);
             on_every_device(ix, [&](pcpx_index& dev_ix, uint32_t part) {
                 QueryBatch qb = batch.qb;
-                qb.part = part, qb.parts = (uint32_t)ix.replicas.size() + 1u;
+                qb.part = part, qb.parts = (uint32_t)nrep + 1u;
+                qb.by_position = part != 0, qb.shard_info = &shards[part];
+                uint32_t* p_idx = s_idx.target(part);
+                float* p_d2     = s_d2.target(part);
+                uint32_t* p_cnt = s_cnt.target(part);
                 parts.run(dev_ix, part, [&] {
-                    launch_knn(dev_ix, qb, k, (float)eps, idx.d, d2.d, cnt.d,
+                    launch_knn(dev_ix, qb, k, (float)eps, p_idx, p_d2, p_cnt,
                                part == 0 ? retries.get() : nullptr);
                 });
             });
+            s_idx.gather(ix, batch.qb, shards), s_d2.gather(ix, batch.qb, shards);
+            s_cnt.gather(ix, batch.qb, shards);
+            PCPX_CUDA(cudaStreamSynchronize(ix.qstream())); // before the replicas' buffers go
         }
         else
             launch_knn(ix, batch.qb, k, (float)eps, idx.d, d2.d, cnt.d, retries.get());
@@ -428,14 +486,22 @@ static void normals_impl(const pcpx_index* index, const float* queries, size_t n
     if (sharded(ix, k))
     {
         PCPX_CUDA(cudaStreamSynchronize(ix.qstream())); // staged queries are in place
+        size_t const nrep = ix.replicas.size();
+        std::vector<ShardInfo> shards(nrep + 1);
+        ShardedOut<float> s_nrm(nrm.d, nq, 3, nrep), s_ctr(ctr.d, nq, 3, nrep);
         on_every_device(ix, [&](pcpx_index& dev_ix, uint32_t part) {
             QueryBatch qb = batch.qb;
-            qb.part = part, qb.parts = (uint32_t)ix.replicas.size() + 1u;
+            qb.part = part, qb.parts = (uint32_t)nrep + 1u;
+            qb.by_position = part != 0, qb.shard_info = &shards[part];
+            float* p_ctr = s_ctr.target(part);
+            float* p_nrm = s_nrm.target(part);
             parts.run(dev_ix, part, [&] {
-                launch_normals(dev_ix, qb, k, (float)eps, ctr.d, nrm.d,
+                launch_normals(dev_ix, qb, k, (float)eps, p_ctr, p_nrm,
                                part == 0 ? ties.get() : nullptr);
             });
         });
+        s_nrm.gather(ix, batch.qb, shards), s_ctr.gather(ix, batch.qb, shards);
+        PCPX_CUDA(cudaStreamSynchronize(ix.qstream())); // before the replicas' buffers go
     }
     else
         launch_normals(ix, batch.qb, k, (float)eps, ctr.d, nrm.d, ties.get());
@@ -539,11 +605,20 @@ int pcpx_mean_knn_distance(const pcpx_index* index, uint32_t k, double eps, floa
         DevBuf<uint32_t> valid(1);
         timer.kernel_begin();
         if (sharded(ix, k))
+        {
+            size_t const nrep = ix.replicas.size();
+            std::vector<ShardInfo> shards(nrep + 1);
+            ShardedOut<float> s_mean(means.d, n, 1, nrep);
             on_every_device(ix, [&](pcpx_index& dev_ix, uint32_t part) {
                 QueryBatch q = qb;
-                q.part = part, q.parts = (uint32_t)ix.replicas.size() + 1u;
-                launch_mean_distance(dev_ix, q, k, (float)eps, means.d);
+                q.part = part, q.parts = (uint32_t)nrep + 1u;
+                q.by_position = part != 0, q.shard_info = &shards[part];
+                float* p_mean = s_mean.target(part);
+                launch_mean_distance(dev_ix, q, k, (float)eps, p_mean);
             });
+            s_mean.gather(ix, qb, shards);
+            PCPX_CUDA(cudaStreamSynchronize(ix.qstream())); // before the replicas' buffers go
+        }
         else
             launch_mean_distance(ix, qb, k, (float)eps, means.d);
         launch_mean_reduce(ix, means.d, (uint32_t)n, sum.get(), valid.get());

@@ -18,6 +18,20 @@ struct QueryBatch
     // other rows of the output untouched
     uint32_t t_begin = 0;
     uint32_t part = 0, parts = 1;
+    // by_position != 0: output rows are indexed by the query's SORTED position t instead of its
+    // original row (a replica fills a local buffer the primary then reads in order — scattered
+    // 12-byte rows written across NVLink cost several times what the kernel itself does)
+    uint32_t by_position = 0;
+    struct ShardInfo* shard_info = nullptr; // (host) filled by the launcher: which rows were answered
+};
+
+// What a sharded kNN-shaped launch answered: tiles [lo, hi) of the tile list of `tile_level`
+// (use_tiles != 0), or the sorted positions [lo, hi).
+struct ShardInfo
+{
+    int use_tiles   = 0;
+    int tile_level  = 0;
+    uint32_t lo = 0, hi = 0;
 };
 
 struct Tuning
@@ -48,6 +62,10 @@ void launch_radius_count(const pcpx_index& ix, const QueryBatch& qb, const float
                          uint32_t* count);
 void launch_radius_fill(const pcpx_index& ix, const QueryBatch& qb, const float* radii, float r,
                         const uint64_t* offsets, uint32_t* idx);
+// dst[row(t) * width + j] = src[t * width + j] for the sorted positions t a shard answered (see
+// QueryBatch::by_position); src may be peer memory, read in order
+void launch_gather_rows(const pcpx_index& ix, const QueryBatch& qb, const ShardInfo& shard,
+                        const uint32_t* src, uint32_t* dst, uint32_t width);
 // every list of a CSR (offsets: nq + 1 device values) ascending by value, in place
 void launch_sort_lists(const pcpx_index& ix, const uint64_t* offsets, uint32_t nq, uint32_t* idx);
 void launch_density_keep(const pcpx_index& ix, float r, uint32_t threshold, uint8_t* keep);

@@ -87,6 +87,7 @@ struct TileParams
     uint32_t first_cap;  // candidates listed before the ball is first shrunk
     int threads;         // threads of the CTA
     uint32_t min_queries; // tiles with fewer queries are handed on without staging
+    uint32_t by_position; // output rows indexed by sorted position (QueryBatch::by_position)
 };
 
 template <int S>
@@ -116,6 +117,7 @@ inline TileParams make_tile_params(const GridView& g, int level, uint32_t max_po
     tp.first_cap     = (uint32_t)kTileCandCap;
     tp.threads       = 96;
     tp.min_queries   = 0;
+    tp.by_position   = 0;
     return tp;
 }
 
