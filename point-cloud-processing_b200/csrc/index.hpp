@@ -46,9 +46,6 @@ struct pcpx_index
     mutable std::atomic<uint32_t> query_launches{0};   // kernels launched by the last kNN-shaped call
     mutable std::atomic<uint32_t> deferred_queries{0}; // ... queries its first pass handed on
     mutable std::atomic<uint32_t> expanded_queries{0}; // ... of those, not final at the first block
-    // streams for concurrent calls: a call takes an idle one (or makes one) and gives it back
-    mutable std::mutex stream_mtx;
-    mutable std::vector<cudaStream_t> idle_streams;
     cudaStream_t qstream() const; // the calling thread's stream for this index (index.hpp, below)
     // the same index on further devices (pcpx_index_params.devices[1..]); owned
     std::vector<pcpx_index*> replicas;
@@ -61,8 +58,6 @@ struct pcpx_index
             delete r;
         }
         cudaSetDevice(device);
-        for (cudaStream_t s : idle_streams)
-            cudaStreamDestroy(s);
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -83,36 +78,51 @@ inline CallStreamSlot& call_stream_slot()
     static thread_local CallStreamSlot slot;
     return slot;
 }
+// Streams for concurrent calls are pooled per DEVICE for the life of the process (a serving loop
+// that rebuilds its index for every cloud would otherwise create and destroy one per cloud).
+struct CallStreamPool
+{
+    std::mutex m;
+    std::map<int, std::vector<cudaStream_t>> idle;
+    static CallStreamPool& instance()
+    {
+        static CallStreamPool* p = new CallStreamPool(); // (never destroyed: no teardown order issues)
+        return *p;
+    }
+};
 class CallStream
 {
   public:
-    explicit CallStream(const pcpx_index& ix) : ix_(ix), prev_(call_stream_slot())
+    explicit CallStream(const pcpx_index& ix) : device_(ix.device), prev_(call_stream_slot())
     {
         cudaStream_t s = nullptr;
         {
-            std::lock_guard<std::mutex> lock(ix.stream_mtx);
-            if (!ix.idle_streams.empty())
+            CallStreamPool& pool = CallStreamPool::instance();
+            std::lock_guard<std::mutex> lock(pool.m);
+            auto& idle = pool.idle[device_];
+            if (!idle.empty())
             {
-                s = ix.idle_streams.back();
-                ix.idle_streams.pop_back();
+                s = idle.back();
+                idle.pop_back();
             }
         }
         if (!s)
-            PCPX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            PCPX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); // (current device = ix.device)
         call_stream_slot() = CallStreamSlot{&ix, s};
     }
     ~CallStream()
     {
         cudaStream_t const s = call_stream_slot().s;
         call_stream_slot()   = prev_;
-        std::lock_guard<std::mutex> lock(ix_.stream_mtx);
-        ix_.idle_streams.push_back(s);
+        CallStreamPool& pool = CallStreamPool::instance();
+        std::lock_guard<std::mutex> lock(pool.m);
+        pool.idle[device_].push_back(s);
     }
     CallStream(const CallStream&)            = delete;
     CallStream& operator=(const CallStream&) = delete;
 
   private:
-    const pcpx_index& ix_;
+    int device_;
     CallStreamSlot prev_;
 };
 
