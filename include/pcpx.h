@@ -82,8 +82,14 @@ typedef struct pcpx_index_params
      * point-cloud-processing_b200/sharding.py over torch.distributed, pcpx_extract_bands.) */
     uint32_t n_devices;
     int32_t devices[8];
-    uint32_t reserved[7];
+    uint32_t shard_mode; /* PCPX_SHARD_REPLICATED (0, the only mode inside the library);
+                            PCPX_SHARD_SLAB returns PCPX_ERR_UNSUPPORTED: slabs are one process
+                            per GPU (sharding.py + pcpx_extract_bands) */
+    uint32_t reserved[6];
 } pcpx_index_params;
+
+#define PCPX_SHARD_REPLICATED 0u
+#define PCPX_SHARD_SLAB 1u
 
 /* Facts about a built index (all filled by pcpx_index_info). */
 typedef struct pcpx_index_info
@@ -122,6 +128,9 @@ int pcpx_index_create(
 
 void pcpx_index_destroy(pcpx_index* index);
 int pcpx_index_info_get(const pcpx_index* index, pcpx_index_info* out_info);
+/* The root voxel alone: pcp::bounding_box of the cloud (common/axis_aligned_bounding_box.hpp:
+ * 214-251) or the user's voxel grid — what basic_linked_octree_t::voxel_grid() returns. */
+int pcpx_index_bbox(const pcpx_index* index, float out_min[3], float out_max[3]);
 
 /* ---- queries ----------------------------------------------------------------------------
  * `queries`: nq points (fp32 xyz, query_stride_bytes apart), or NULL for "the indexed cloud's

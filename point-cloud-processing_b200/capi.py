@@ -28,7 +28,8 @@ class IndexParams(C.Structure):
         ("min_cell_occupancy", C.c_uint32),
         ("n_devices", C.c_uint32),
         ("devices", C.c_int32 * 8),
-        ("reserved", C.c_uint32 * 7),
+        ("shard_mode", C.c_uint32),
+        ("reserved", C.c_uint32 * 6),
     ]
 
 
@@ -70,6 +71,7 @@ _SIGNATURES = {
                                     C.POINTER(C.c_void_p)]),
     "pcpx_index_destroy": (None, [C.c_void_p]),
     "pcpx_index_info_get": (C.c_int, [C.c_void_p, C.POINTER(IndexInfo)]),
+    "pcpx_index_bbox": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pcpx_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32,
                            C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcpx_radius_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
@@ -339,6 +341,11 @@ class Index:
                     finest_level=i.finest_level, n_cells=i.n_cells,
                     device_bytes=i.device_bytes, device=i.device, build_ms=i.build_ms,
                     n_devices=i.n_devices)
+
+    def bbox(self):
+        lo, hi = (C.c_float * 3)(), (C.c_float * 3)()
+        _check(lib().pcpx_index_bbox(self._h, lo, hi))
+        return np.array(lo[:], np.float32), np.array(hi[:], np.float32)
 
     def timings(self):
         t = Timings()

@@ -126,6 +126,10 @@ struct ShardedOut
 
 static void validate_devices(const pcpx_index_params& prm)
 {
+    if (prm.shard_mode != PCPX_SHARD_REPLICATED)
+        fail(PCPX_ERR_UNSUPPORTED,
+             "shard_mode %u: inside the library an index is replicated on its devices; slabs are "
+             "one process per GPU (sharding.py, pcpx_extract_bands)", prm.shard_mode);
     if (prm.n_devices == 0)
         return;
     int ndev = 0;
@@ -299,6 +303,17 @@ int pcpx_index_info_get(const pcpx_index* index, pcpx_index_info* out)
         out->n_devices    = (uint32_t)ix.replicas.size() + 1u;
         for (pcpx_index const* r : ix.replicas)
             out->build_ms = std::max(out->build_ms, r->timings.build_ms);
+    });
+}
+
+int pcpx_index_bbox(const pcpx_index* index, float out_min[3], float out_max[3])
+{
+    return guarded([&] {
+        pcpx_index& ix = checked(index);
+        if (!out_min || !out_max)
+            fail(PCPX_ERR_INVALID_ARG, "out_min / out_max is NULL");
+        for (int a = 0; a < 3; ++a)
+            out_min[a] = ix.bbox_min[a], out_max[a] = ix.bbox_max[a];
     });
 }
 

@@ -31,6 +31,17 @@ def test_index_facts(pcpx, index, ocloud, sphere):
     assert info["n_input"] == N and info["n_indexed"] == ocloud.size() == N
     bb = ocloud.bbox()
     assert np.array_equal(info["bbox_min"], bb[:3]) and np.array_equal(info["bbox_max"], bb[3:])
+    lo, hi = index.bbox()  # pcpx_index_bbox: the root voxel alone
+    assert np.array_equal(lo, bb[:3]) and np.array_equal(hi, bb[3:])
+    prm_err = None
+    try:
+        prm = pcpx.capi.IndexParams()
+        prm.device, prm.shard_mode = -1, 1  # PCPX_SHARD_SLAB: not inside the library
+        import ctypes as C
+        h = C.c_void_p()
+        prm_err = pcpx.lib().pcpx_index_create(sphere.ctypes.data, len(sphere), 12, C.byref(prm), C.byref(h))
+    finally:
+        assert prm_err == -5  # PCPX_ERR_UNSUPPORTED
 
 
 def test_knn_bit_exact(index, ocloud):
