@@ -106,47 +106,40 @@ __global__ void __launch_bounds__(kBlock) encode_kernel(
     vals[i]           = i;
 }
 
-// ---- SoA reorder ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) reorder_kernel(
-    const float* __restrict__ xyz, const uint32_t* __restrict__ order, uint32_t n,
-    float4* __restrict__ pts)
-{
-    uint32_t const i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n)
-        return;
-    uint32_t const o = order[i];
-    pts[i] = make_float4(xyz[3 * (size_t)o], xyz[3 * (size_t)o + 1], xyz[3 * (size_t)o + 2],
-                         __uint_as_float(o));
-}
-
-// ---- cell boundaries -----------------------------------------------------------------------
-// b(i) = coarsest level at which sorted point i opens a new cell (0 for i == 0, lcap + 1 when it
-// shares even the finest cell with its predecessor).  Point i starts a cell at every level >= b.
-__device__ __forceinline__ int boundary_level(const GridView& g, const float4* pts, uint32_t i)
-{
-    if (i == 0)
-        return 0;
-    float4 const a = pts[i - 1], b = pts[i];
-    QueryCell const ca = query_cell(g, a.x, a.y, a.z), cb = query_cell(g, b.x, b.y, b.z);
-    uint32_t const diff = (ca.ux ^ cb.ux) | (ca.uy ^ cb.uy) | (ca.uz ^ cb.uz);
-    if (diff == 0)
-        return g.lcap + 1;
-    int const hb = 31 - __clz(diff); // highest differing bit of the lcap-bit coordinates
-    return g.lcap - hb;
-}
-
-__global__ void __launch_bounds__(kBlock) level_histogram_kernel(
-    GridView g, uint32_t* __restrict__ hist /* [kMaxLevel + 2] */, uint8_t* __restrict__ bnd)
+// ---- SoA reorder + cell boundaries ---------------------------------------------------------
+// One pass behind the sort: sorted point i is gathered into the float4 array, and — from the
+// sorted CODES, so that no thread waits for a neighbour's gather — b(i), the coarsest level at
+// which point i opens a new cell, is written and counted per level.  b(i) = 0 for i == 0,
+// lcap + 1 when i shares even the finest cell with its predecessor; two Morton codes differ
+// first at bit h <=> their coordinates differ first at bit h / 3.  Point i starts a cell at
+// every level >= b(i).
+template <typename KeyT>
+__global__ void __launch_bounds__(kBlock) reorder_levels_kernel(
+    const float* __restrict__ xyz, const uint32_t* __restrict__ order,
+    const KeyT* __restrict__ codes, uint32_t n, uint32_t n_indexed, int lcap,
+    float4* __restrict__ pts, uint8_t* __restrict__ bnd, uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t sh[kMaxLevel + 2];
     if (threadIdx.x < kMaxLevel + 2)
         sh[threadIdx.x] = 0;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < g.n; i += gridDim.x * kBlock)
+    // (grid-stride: a few global atomics per block on the ~20 counters, not per 256 points)
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock)
     {
-        int const b = boundary_level(g, g.pts, i);
-        bnd[i]      = (uint8_t)b; // kept: the table build and the tile lists read it
-        atomicAdd(&sh[b], 1u);
+        uint32_t const o = order[i];
+        pts[i] = make_float4(xyz[3 * (size_t)o], xyz[3 * (size_t)o + 1], xyz[3 * (size_t)o + 2],
+                             __uint_as_float(o));
+        if (i < n_indexed)
+        {
+            int b = 0;
+            if (i > 0)
+            {
+                uint64_t const diff = (uint64_t)(codes[i - 1] ^ codes[i]);
+                b = diff == 0 ? lcap + 1 : lcap - (63 - __clzll((long long)diff)) / 3;
+            }
+            bnd[i] = (uint8_t)b;
+            atomicAdd(&sh[b], 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x < kMaxLevel + 2 && sh[threadIdx.x])
@@ -167,57 +160,44 @@ __device__ __forceinline__ uint32_t claim_slot(HashSlot* table, uint32_t size, u
     }
 }
 
-__device__ __forceinline__ uint32_t find_slot(const HashSlot* table, uint32_t size, uint64_t key)
-{
-    uint32_t s = hash_slot(key, size);
-    for (;;)
-    {
-        unsigned long long const k =
-            *reinterpret_cast<const unsigned long long*>(table + s);
-        if (k == (unsigned long long)key)
-            return s;
-        s = s + 1 == size ? 0u : s + 1;
-    }
-}
-
-__global__ void __launch_bounds__(kBlock) table_insert_kernel(GridView g, HashSlot* table,
-                                                              const uint8_t* __restrict__ bnd)
-{
-    uint32_t const i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= g.n)
-        return;
-    int const b = bnd[i];
-    if (b > g.lfine)
-        return;
-    float4 const p    = g.pts[i];
-    QueryCell const c = query_cell(g, p.x, p.y, p.z);
-    for (int l = b; l <= g.lfine; ++l)
-    {
-        int const sh       = g.lcap - l;
-        uint32_t const s   = claim_slot(table, g.table_size,
-                                        cell_key(l, c.ux >> sh, c.uy >> sh, c.uz >> sh));
-        table[s].start     = i;
-    }
-}
-
-// The cell that point i - 1 belongs to ends where point i opens a new one.
-__global__ void __launch_bounds__(kBlock) table_count_kernel(GridView g, HashSlot* table,
+// One pass over the cell boundaries: point i OPENS its cell at every level >= b(i) (start = i)
+// and CLOSES the cell of point i - 1 at the same levels (it ends at i); i == n closes the last
+// point's cells at every level.  Either side claims the slot if it comes first.  A slot's count
+// starts at 0xFFFFFFFF (the table is cleared to 0xFF bytes): the opener subtracts start, the
+// closer adds end + 1, in either order, which leaves count = end - start.
+__global__ void __launch_bounds__(kBlock) table_build_kernel(GridView g, HashSlot* table,
                                                              const uint8_t* __restrict__ bnd)
 {
-    uint32_t const i = blockIdx.x * kBlock + threadIdx.x + 1; // 1 .. n
+    uint32_t const i = blockIdx.x * kBlock + threadIdx.x; // 0 .. n
     if (i > g.n)
         return;
     int const b = i == g.n ? 0 : bnd[i];
     if (b > g.lfine)
         return;
-    float4 const p    = g.pts[i - 1];
-    QueryCell const c = query_cell(g, p.x, p.y, p.z);
-    for (int l = b; l <= g.lfine; ++l)
+    if (i < g.n)
     {
-        int const sh     = g.lcap - l;
-        uint32_t const s = find_slot(table, g.table_size,
-                                     cell_key(l, c.ux >> sh, c.uy >> sh, c.uz >> sh));
-        table[s].count   = i - table[s].start;
+        float4 const p    = g.pts[i];
+        QueryCell const c = query_cell(g, p.x, p.y, p.z);
+        for (int l = b; l <= g.lfine; ++l)
+        {
+            int const sh     = g.lcap - l;
+            uint32_t const s = claim_slot(table, g.table_size,
+                                          cell_key(l, c.ux >> sh, c.uy >> sh, c.uz >> sh));
+            table[s].start   = i;
+            atomicSub(&table[s].count, i);
+        }
+    }
+    if (i > 0)
+    {
+        float4 const p    = g.pts[i - 1];
+        QueryCell const c = query_cell(g, p.x, p.y, p.z);
+        for (int l = b; l <= g.lfine; ++l)
+        {
+            int const sh     = g.lcap - l;
+            uint32_t const s = claim_slot(table, g.table_size,
+                                          cell_key(l, c.ux >> sh, c.uy >> sh, c.uz >> sh));
+            atomicAdd(&table[s].count, i + 1u);
+        }
     }
 }
 
@@ -481,21 +461,25 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
                 encode_and_sort<uint32_t>(ix, d_xyz, n32, prm, sc, &launches, ev_sort0, ev_sort1);
             else
                 encode_and_sort<uint64_t>(ix, d_xyz, n32, prm, sc, &launches, ev_sort0, ev_sort1);
-            reorder_kernel<<<blocks_for(n, kBlock), kBlock, 0, ix.stream>>>(d_xyz, sc.order(), n32,
-                                                                             ix.pts.get());
-            PCPX_CHECK_LAUNCH();
-            ++launches;
         }
 
-        // 5. cells per level -> finest stored level
+        // 5. SoA + cells per level -> finest stored level
         std::vector<uint32_t> lh(kMaxLevel + 2, 0u);
-        if (g.n)
+        if (n)
         {
             DevBuf<uint32_t> d_lh(kMaxLevel + 2);
             PCPX_CUDA(cudaMemsetAsync(d_lh.get(), 0, d_lh.bytes(), ix.stream));
-            ix.bnd.alloc(g.n);
-            level_histogram_kernel<<<std::min<uint32_t>(blocks_for(g.n, kBlock * 4), 148u * 8u),
-                                     kBlock, 0, ix.stream>>>(g, d_lh.get(), ix.bnd.get());
+            ix.bnd.alloc(std::max<uint32_t>(g.n, 1u));
+            uint32_t const reorder_blocks = std::min<uint32_t>(blocks_for(n, kBlock), 148u * 8u);
+            const void* codes = sc.in_alt ? (const void*)sc.keys_alt.get() : (const void*)sc.keys.get();
+            if (ix.code_bits + 1 <= 32)
+                reorder_levels_kernel<uint32_t><<<reorder_blocks, kBlock, 0, ix.stream>>>(
+                    d_xyz, sc.order(), static_cast<const uint32_t*>(codes), n32, g.n, g.lcap,
+                    ix.pts.get(), ix.bnd.get(), d_lh.get());
+            else
+                reorder_levels_kernel<uint64_t><<<reorder_blocks, kBlock, 0, ix.stream>>>(
+                    d_xyz, sc.order(), static_cast<const uint64_t*>(codes), n32, g.n, g.lcap,
+                    ix.pts.get(), ix.bnd.get(), d_lh.get());
             PCPX_CHECK_LAUNCH();
             ++launches;
             read_back(ix.stream, lh.data(), d_lh.get(), d_lh.bytes());
@@ -542,13 +526,10 @@ pcpx_index* build_index(const float* xyz, size_t n, size_t stride_bytes,
     PCPX_CUDA(cudaMemsetAsync(ix.table.get(), 0xFF, ix.table.bytes(), ix.stream));
     if (g.n)
     {
-        table_insert_kernel<<<blocks_for(g.n, kBlock), kBlock, 0, ix.stream>>>(g, ix.table.get(),
-                                                                               ix.bnd.get());
+        table_build_kernel<<<blocks_for(g.n + 1u, kBlock), kBlock, 0, ix.stream>>>(g, ix.table.get(),
+                                                                                   ix.bnd.get());
         PCPX_CHECK_LAUNCH();
-        table_count_kernel<<<blocks_for(g.n, kBlock), kBlock, 0, ix.stream>>>(g, ix.table.get(),
-                                                                              ix.bnd.get());
-        PCPX_CHECK_LAUNCH();
-        launches += 2;
+        launches += 1;
     }
     ev_end.record(ix.stream);
     PCPX_CUDA(cudaStreamSynchronize(ix.stream));
