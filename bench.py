@@ -237,6 +237,21 @@ def cpu_reference_step(xyz, k, sample_size, seed=123):
             "sample": desc, "build_s": t_build, "query_sample_s": t_query}
 
 
+def headline_config(world, n_local, numa_node):
+    """`config` of the JSON line — the same object for both arms (the reference arm runs this
+    workload's one-GPU share on the host cores)."""
+    return {
+        "workload": "estimate_normals k=15 over a 10M-point noisy plane per GPU (seed 7+rank, "
+                    "L=10, sigma_z=1e-3): device index build + fused kNN->PCA normal kernel",
+        "n_points_per_gpu": N_POINTS, "k": K, "halo": HALO if world > 1 else 0.0,
+        "local_points": n_local,
+        "cache": "inputs larger than L2 (160 MB sorted float4 SoA + cell table vs 126 MB "
+                 "L2); the index is rebuilt from scratch every step",
+        "parallelism": "one process per GPU, spatial slabs; halo strips exchanged with the neighbouring ranks over NCCL (isend/irecv) inside the timed step",
+        "numa_node_rank0": numa_node,
+    }
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -256,9 +271,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "estimate_normals k=15, 10M-point noisy plane (seed 7, L=10), "
-                               "reference CPU path: octree build + kNN + PCA normal",
-                   "n_points": N_POINTS, "k": K},
+        # the repo arm's config (same workload: rank 0's 10 M-point cloud, k = 15), answered by
+        # the reference's own CPU path: octree build + kNN + PCA normal
+        "config": headline_config(max(1, args.gpus), N_POINTS, None),
         "cpu_baseline": {k_: last[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": "normals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -700,16 +715,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt_res / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "estimate_normals k=15 over a 10M-point noisy plane per GPU (seed 7+rank, "
-                            "L=10, sigma_z=1e-3): device index build + fused kNN->PCA normal kernel",
-                "n_points_per_gpu": N_POINTS, "k": K, "halo": HALO if world > 1 else 0.0,
-                "local_points": n_local,
-                "cache": "inputs larger than L2 (160 MB sorted float4 SoA + cell table vs 126 MB "
-                         "L2); the index is rebuilt from scratch every step",
-                "parallelism": "one process per GPU, spatial slabs; halo strips exchanged with the neighbouring ranks over NCCL (isend/irecv) inside the timed step",
-                "numa_node_rank0": numa_node,
-            },
+            "config": headline_config(world, n_local, numa_node),
             "e2e": {"value": e2e_value, "unit": "normals/s",
                     "h2d_bytes_per_step": int(n_owned * 12), "d2h_bytes_per_step": int(n_local * 12),
                     "ms_per_step": dt_e2e / e2e_steps * 1e3, "steps": e2e_steps,
